@@ -1,0 +1,438 @@
+"""MCPL-3 particle-list I/O (host side, numpy).
+
+The reference reads particle lists through the third-party ``mcpl`` Python
+module (``python/kdsource/plist.py:292-301,349-360``) and writes them through
+libmcpl (``clib/src/writemcpl.c:15-69``, ``clib/src/resamplemcpl.c:30-44``).
+Neither library ships with the reference tree, so this module implements the
+MCPL-3 on-disk format directly.  ``MCPLFile`` mirrors the subset of the
+``mcpl.MCPLFile`` interface that ``plist.py`` uses: ``nparticles``,
+``particle_blocks``, ``read_block()``, ``skip_forward()`` and block attributes
+``ekin,x,y,z,ux,uy,uz,time,weight,pdgcode`` (+ ``polx/poly/polz/userflags``).
+
+On-disk layout (little or big endian, flagged in the magic):
+
+    "MCPL" "003" 'L'|'B'
+    u64 nparticles
+    u32 ncomments, nblobs, opt_userflags, opt_polarisation, opt_singleprec
+    i32 opt_universalpdgcode
+    u32 particlesize
+    u32 opt_universalweight  (+ f64 value when set)
+    string srcname ; comments ; blob keys ; blobs   (string = u32 len + bytes)
+    particle records: [pol x3 FP]? pos x3 FP, dirpack x2 FP, ekin FP (sign bit
+                      carries one direction bit), time FP, [weight FP]?,
+                      [pdgcode i32]?, [userflags u32]?
+
+Directions use MCPL's "adaptive projection packing": the two stored numbers are
+(x, y), (1/z, y) or (x, 1/z) depending on which component is largest, and the
+sign of the dropped component rides on the sign bit of ``ekin``.
+"""
+
+import gzip
+import os
+import struct
+
+import numpy as np
+
+__all__ = [
+    "MCPLFile",
+    "MCPLHeader",
+    "ParticleBlock",
+    "pack_direction",
+    "unpack_direction",
+    "record_dtype",
+    "build_header",
+    "write_mcpl_file",
+    "patch_nparticles",
+]
+
+
+class MCPLHeader:
+    """Decoded MCPL header (format version 2 and 3 share this layout)."""
+
+    def __init__(self):
+        self.version = 3
+        self.endian = "<"
+        self.nparticles = 0
+        self.opt_userflags = False
+        self.opt_polarisation = False
+        self.opt_singleprec = True
+        self.opt_universalpdgcode = 0
+        self.opt_universalweight = 0.0
+        self.particlesize = 0
+        self.srcname = ""
+        self.comments = []
+        self.blobs = {}
+        self.headersize = 0
+
+
+def record_dtype(
+    singleprec=True,
+    polarisation=False,
+    universal_pdg=False,
+    universal_weight=False,
+    userflags=False,
+    endian="<",
+):
+    """numpy structured dtype of one particle record for the given options."""
+    fp = endian + ("f4" if singleprec else "f8")
+    fields = []
+    if polarisation:
+        fields.append(("pol", fp, (3,)))
+    fields.append(("pos", fp, (3,)))
+    fields.append(("dirpack", fp, (2,)))
+    fields.append(("ekin", fp))
+    fields.append(("time", fp))
+    if not universal_weight:
+        fields.append(("weight", fp))
+    if not universal_pdg:
+        fields.append(("pdgcode", endian + "i4"))
+    if userflags:
+        fields.append(("userflags", endian + "u4"))
+    return np.dtype(fields)
+
+
+def pack_direction(ux, uy, uz, ekin):
+    """Adaptive projection packing of unit vectors.
+
+    Returns (p0, p1, signed_ekin) as float64 arrays.  Mirrors libmcpl's
+    ``mcpl_unitvect_pack_adaptproj`` as used by ``mcpl_add_particle`` (called
+    from ``clib/src/resamplemcpl.c:42`` and ``clib/src/writemcpl.c:66``).
+    """
+    ux = np.asarray(ux, dtype=np.float64)
+    uy = np.asarray(uy, dtype=np.float64)
+    uz = np.asarray(uz, dtype=np.float64)
+    ekin = np.abs(np.asarray(ekin, dtype=np.float64))
+    ax, ay, az = np.abs(ux), np.abs(uy), np.abs(uz)
+    zsmall = az < np.maximum(ax, ay)
+    with np.errstate(divide="ignore"):
+        invz = np.where(uz != 0.0, 1.0 / np.where(uz != 0.0, uz, 1.0), np.inf)
+    xbig = zsmall & (ax >= ay)
+    ybig = zsmall & ~(ax >= ay)
+    p0 = np.where(xbig, invz, ux)
+    p1 = np.where(ybig, invz, uy)
+    signsrc = np.where(xbig, ux, np.where(ybig, uy, uz))
+    sek = np.copysign(ekin, signsrc)
+    return p0, p1, sek
+
+
+def unpack_direction(p0, p1, signed_ekin):
+    """Inverse of :func:`pack_direction`; returns (ux, uy, uz, ekin)."""
+    p0 = np.asarray(p0, dtype=np.float64)
+    p1 = np.asarray(p1, dtype=np.float64)
+    sek = np.asarray(signed_ekin, dtype=np.float64)
+    sgn = np.where(np.signbit(sek), -1.0, 1.0)
+    c0 = np.abs(p0) > 1.0
+    c1 = ~c0 & (np.abs(p1) > 1.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv0 = 1.0 / p0
+        inv1 = 1.0 / p1
+    # case 0: (1/z, y) + sign(x)
+    z0 = inv0
+    x0 = sgn * np.sqrt(np.maximum(0.0, 1.0 - (p1 * p1 + z0 * z0)))
+    # case 1: (x, 1/z) + sign(y)
+    z1 = inv1
+    y1 = sgn * np.sqrt(np.maximum(0.0, 1.0 - (p0 * p0 + z1 * z1)))
+    # case 2: (x, y) + sign(z)
+    z2 = sgn * np.sqrt(np.maximum(0.0, 1.0 - (p0 * p0 + p1 * p1)))
+    ux = np.where(c0, x0, p0)
+    uy = np.where(c1, y1, p1)
+    uz = np.where(c0, z0, np.where(c1, z1, z2))
+    return ux, uy, uz, np.abs(sek)
+
+
+class ParticleBlock:
+    """A block of decoded particles (float64 columns, like ``mcpl`` blocks)."""
+
+    def __init__(self, rec, hdr):
+        n = len(rec)
+        pos = rec["pos"].astype(np.float64)
+        self.x = np.ascontiguousarray(pos[:, 0])
+        self.y = np.ascontiguousarray(pos[:, 1])
+        self.z = np.ascontiguousarray(pos[:, 2])
+        dp = rec["dirpack"].astype(np.float64)
+        ux, uy, uz, ek = unpack_direction(
+            dp[:, 0], dp[:, 1], rec["ekin"].astype(np.float64)
+        )
+        self.ux, self.uy, self.uz, self.ekin = ux, uy, uz, ek
+        self.time = rec["time"].astype(np.float64)
+        if hdr.opt_universalweight:
+            self.weight = np.full(n, hdr.opt_universalweight, dtype=np.float64)
+        else:
+            self.weight = rec["weight"].astype(np.float64)
+        if hdr.opt_universalpdgcode:
+            self.pdgcode = np.full(n, hdr.opt_universalpdgcode, dtype=np.int32)
+        else:
+            self.pdgcode = rec["pdgcode"].astype(np.int32)
+        if hdr.opt_polarisation:
+            pol = rec["pol"].astype(np.float64)
+            self.polx, self.poly, self.polz = pol[:, 0], pol[:, 1], pol[:, 2]
+        else:
+            self.polx = self.poly = self.polz = np.zeros(n)
+        if hdr.opt_userflags:
+            self.userflags = rec["userflags"].astype(np.uint32)
+        else:
+            self.userflags = np.zeros(n, dtype=np.uint32)
+
+    def __len__(self):
+        return len(self.x)
+
+
+def _open_maybe_gz(filename):
+    with open(filename, "rb") as fh:
+        magic = fh.read(2)
+    if magic == b"\x1f\x8b":
+        return gzip.open(filename, "rb")
+    return open(filename, "rb")
+
+
+def _read_exact(fh, n):
+    buf = fh.read(n)
+    if len(buf) != n:
+        raise IOError("MCPL: unexpected end of file")
+    return buf
+
+
+def _read_string(fh, endian):
+    (n,) = struct.unpack(endian + "I", _read_exact(fh, 4))
+    return _read_exact(fh, n)
+
+
+class MCPLFile:
+    """Sequential reader for ``.mcpl`` / ``.mcpl.gz`` files."""
+
+    def __init__(self, filename, blocklength=10000):
+        self.filename = str(filename)
+        self.blocklength = int(blocklength)
+        self._fh = _open_maybe_gz(self.filename)
+        self.hdr = self._read_header()
+        self.nparticles = self.hdr.nparticles
+        self._pos = 0
+        self._dtype = record_dtype(
+            singleprec=self.hdr.opt_singleprec,
+            polarisation=self.hdr.opt_polarisation,
+            universal_pdg=bool(self.hdr.opt_universalpdgcode),
+            universal_weight=bool(self.hdr.opt_universalweight),
+            userflags=self.hdr.opt_userflags,
+            endian=self.hdr.endian,
+        )
+        if self._dtype.itemsize != self.hdr.particlesize:
+            raise IOError(
+                "MCPL: particle size {} in header does not match options "
+                "({})".format(self.hdr.particlesize, self._dtype.itemsize)
+            )
+
+    def _read_header(self):
+        fh = self._fh
+        h = MCPLHeader()
+        magic = _read_exact(fh, 8)
+        if magic[:4] != b"MCPL":
+            raise IOError("Not an MCPL file: {}".format(self.filename))
+        try:
+            h.version = int(magic[4:7])
+        except ValueError:
+            raise IOError("MCPL: bad version field")
+        if h.version not in (2, 3):
+            raise IOError("MCPL: unsupported format version {}".format(h.version))
+        if magic[7:8] == b"L":
+            h.endian = "<"
+        elif magic[7:8] == b"B":
+            h.endian = ">"
+        else:
+            raise IOError("MCPL: bad endianness field")
+        e = h.endian
+        (h.nparticles,) = struct.unpack(e + "Q", _read_exact(fh, 8))
+        arr = struct.unpack(e + "IIIIIiII", _read_exact(fh, 32))
+        ncomments, nblobs = arr[0], arr[1]
+        h.opt_userflags = bool(arr[2])
+        h.opt_polarisation = bool(arr[3])
+        h.opt_singleprec = bool(arr[4])
+        h.opt_universalpdgcode = int(arr[5])
+        h.particlesize = int(arr[6])
+        size = 48
+        if arr[7]:
+            (h.opt_universalweight,) = struct.unpack(e + "d", _read_exact(fh, 8))
+            size += 8
+        s = _read_string(fh, e)
+        size += 4 + len(s)
+        h.srcname = s.decode("utf8", "replace")
+        for _ in range(ncomments):
+            s = _read_string(fh, e)
+            size += 4 + len(s)
+            h.comments.append(s.decode("utf8", "replace"))
+        keys = []
+        for _ in range(nblobs):
+            s = _read_string(fh, e)
+            size += 4 + len(s)
+            keys.append(s.decode("utf8", "replace"))
+        for k in keys:
+            s = _read_string(fh, e)
+            size += 4 + len(s)
+            h.blobs[k] = s
+        h.headersize = size
+        return h
+
+    # -- interface used by PList (plist.py:292-301, 349-360) ---------------
+    def skip_forward(self, n):
+        n = int(min(max(n, 0), self.nparticles - self._pos))
+        if n:
+            self._fh.read(n * self._dtype.itemsize)
+            self._pos += n
+
+    def read_raw(self, n):
+        """Read up to n raw records as a structured array (None at EOF)."""
+        n = int(min(n, self.nparticles - self._pos))
+        if n <= 0:
+            return None
+        buf = _read_exact(self._fh, n * self._dtype.itemsize)
+        self._pos += n
+        return np.frombuffer(buf, dtype=self._dtype, count=n)
+
+    def read_block(self):
+        rec = self.read_raw(self.blocklength)
+        if rec is None:
+            return None
+        return ParticleBlock(rec, self.hdr)
+
+    @property
+    def particle_blocks(self):
+        while True:
+            pb = self.read_block()
+            if pb is None:
+                return
+            yield pb
+
+    def rewind(self):
+        self._fh.close()
+        self._fh = _open_maybe_gz(self.filename)
+        self._read_header()
+        self._pos = 0
+
+    def close(self):
+        self._fh.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def _pack_string(s, endian="<"):
+    if isinstance(s, str):
+        s = s.encode("utf8")
+    return struct.pack(endian + "I", len(s)) + s
+
+
+def build_header(
+    nparticles,
+    srcname,
+    singleprec=True,
+    polarisation=False,
+    universal_pdg=0,
+    universal_weight=0.0,
+    userflags=False,
+    comments=(),
+):
+    """Serialised MCPL-3 little-endian header."""
+    dt = record_dtype(
+        singleprec, polarisation, bool(universal_pdg), bool(universal_weight),
+        userflags,
+    )
+    out = b"MCPL003L" + struct.pack("<Q", int(nparticles))
+    out += struct.pack(
+        "<IIIIIiII",
+        len(comments),
+        0,
+        int(bool(userflags)),
+        int(bool(polarisation)),
+        int(bool(singleprec)),
+        int(universal_pdg),
+        dt.itemsize,
+        int(bool(universal_weight)),
+    )
+    if universal_weight:
+        out += struct.pack("<d", float(universal_weight))
+    out += _pack_string(srcname)
+    for c in comments:
+        out += _pack_string(c)
+    return out
+
+
+def patch_nparticles(filename, nparticles):
+    """Rewrite the particle count of an *uncompressed* MCPL file in place."""
+    with open(filename, "r+b") as fh:
+        fh.seek(8)
+        fh.write(struct.pack("<Q", int(nparticles)))
+
+
+def write_mcpl_file(
+    filename,
+    *,
+    ekin,
+    x,
+    y,
+    z,
+    ux,
+    uy,
+    uz,
+    time,
+    weight,
+    pdgcode,
+    polx=None,
+    poly=None,
+    polz=None,
+    userflags=None,
+    double_prec=False,
+    srcname="KDSource MCPL writer",
+    compress=None,
+    compresslevel=6,
+):
+    """Write arrays to an MCPL-3 file (host path; record layout as libmcpl).
+
+    ``weight`` / ``pdgcode`` scalars select the universal-weight /
+    universal-pdgcode header options (flags bit2 / bit1 of
+    ``clib/src/writemcpl.c:4-13``).
+    """
+    import numbers
+
+    filename = str(filename)
+    if compress is None:
+        compress = filename.endswith(".gz")
+    n = len(ekin)
+    uni_pdg = int(pdgcode) if isinstance(pdgcode, numbers.Integral) else 0
+    uni_w = float(weight) if isinstance(weight, numbers.Number) else 0.0
+    has_pol = polx is not None
+    dt = record_dtype(
+        not double_prec, has_pol, bool(uni_pdg), bool(uni_w), userflags is not None
+    )
+    rec = np.zeros(n, dtype=dt)
+    p0, p1, sek = pack_direction(ux, uy, uz, ekin)
+    rec["pos"][:, 0] = x
+    rec["pos"][:, 1] = y
+    rec["pos"][:, 2] = z
+    rec["dirpack"][:, 0] = p0
+    rec["dirpack"][:, 1] = p1
+    rec["ekin"] = sek
+    rec["time"] = time
+    if not uni_w:
+        rec["weight"] = weight
+    if not uni_pdg:
+        rec["pdgcode"] = pdgcode
+    if has_pol:
+        rec["pol"][:, 0] = polx
+        rec["pol"][:, 1] = poly
+        rec["pol"][:, 2] = polz
+    if userflags is not None:
+        rec["userflags"] = userflags
+    hdr = build_header(
+        n, srcname, not double_prec, has_pol, uni_pdg, uni_w, userflags is not None
+    )
+    opener = (
+        (lambda f: gzip.open(f, "wb", compresslevel=compresslevel))
+        if compress
+        else (lambda f: open(f, "wb"))
+    )
+    with opener(filename) as fh:
+        fh.write(hdr)
+        fh.write(rec.tobytes())
+    return os.path.abspath(filename)
