@@ -1,0 +1,129 @@
+/*
+ * kdsb200.h -- C ABI of libkdsb200.so, the B200 (sm_100a) kernel-density hot
+ * path of KDSource.  Plain pointers and sizes only.  Unless stated otherwise
+ * every `d_*` pointer is a DEVICE pointer owned by the caller, `h_*` is a host
+ * pointer, `stream` is a cudaStream_t passed as void*, and every function
+ * returns 0 on success / non-zero on failure with the reason available from
+ * kdsb200_last_error() (thread-local).  No function synchronises the stream
+ * unless documented.
+ *
+ * Each entry point cites the reference interface (paths relative to the
+ * KDSource tree) whose arithmetic it replaces.
+ */
+#ifndef KDSB200_H
+#define KDSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ---------------------------------------------------------- */
+const char* kdsb200_last_error(void);
+int kdsb200_version(void);
+int kdsb200_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+/* Pipe-rate calibration (mode 0 FFMA, 1 FFMA2, 2 MUFU.EX2): lane-ops/s measured
+ * with CUDA events; the roofline denominators of bench.py.  Synchronises. */
+int kdsb200_calibrate_pipe(int mode, float* d_scratch, int iters, double* ops_per_s,
+                           void* stream);
+
+/* ---- source / query packing ------------------------------------------ */
+/* Number of floats of the packed fp32 source set: tiles of 512 sources x (D+2)
+ * rows (see csrc/common.cuh). */
+uint64_t kdsb200_packed_floats(uint64_t N, int D);
+/* Query count padded to the evaluation kernel's CTA tile. */
+uint64_t kdsb200_eval_mpad(uint64_t M);
+/* d_data (N,D) row-major fp64 = KDEpy `kde.data` (vecs/scaling, kdsource.py:212);
+ * d_w (N) or NULL; d_bw (N) or NULL (-> bw_scalar) = `kde.bw`;
+ * mode 0: kde_eval layout, mode 1: mlcv layout. */
+int kdsb200_pack_sources_f32(const double* d_data, const double* d_w, const double* d_bw,
+                             double bw_scalar, uint64_t N, int D, const double* h_center,
+                             double w_scale, double lc_ref, int mode, float* d_packed,
+                             void* stream);
+int kdsb200_pack_queries_f32(const double* d_pts, uint64_t M, uint64_t Mpad, int D,
+                             const double* h_center, float* d_qT, void* stream);
+
+/* ---- evaluation: KDEpy TreeKDE.evaluate (kdsource.py:239, kde.py:146-151) */
+/* Source-dimension split that fills the GPU for (N, M). */
+int kdsb200_eval_nsplit(uint64_t N, uint64_t M);
+/* out[m] = out_scale * sum_i 2^-nlc_i exp(-|q_m-x_i|^2/(2 h_i^2)); cutoff > 0
+ * drops sources farther than `cutoff` (hard support radius).  d_partial holds
+ * nsplit*Mpad doubles. */
+int kdsb200_kde_eval_f32(const float* d_packed, uint64_t N, int D, const float* d_qT, uint64_t M,
+                         uint64_t Mpad, double cutoff, double out_scale, int nsplit,
+                         double* d_partial, double* d_out, void* stream);
+/* fp64 mode (1e-12 parity).  d_scratch: 2N + nsplit*M doubles. */
+int kdsb200_kde_eval_f64(const double* d_data, const double* d_w, const double* d_bw,
+                         double bw_scalar, uint64_t N, int D, double w_scale,
+                         const double* d_pts, uint64_t M, double cutoff, int nsplit,
+                         double* d_scratch, double* d_out, void* stream);
+
+/* ---- MLCV: _kde_cv_score x grid (kde.py:106-153, :204-211) --------------- */
+int kdsb200_mlcv_gtile(int G);          /* grid slots the kernel computes for G factors */
+uint64_t kdsb200_mlcv_mpad(uint64_t M); /* test-point count padded to the CTA tile */
+int kdsb200_mlcv_nsplit(uint64_t N, uint64_t M);
+/* Sources packed with mode 1.  Test points d_qT [D][Mpad]; per test point the
+ * excluded source interval [lo,hi) (its fold; [i,i+1) for leave-one-out), the
+ * coefficient coefw = w_i / (n_fold * K) and lwtr = ln(sum of train weights).
+ * h_nk[g] = -log2(e) / (2 grid[g]^2), G <= 32 per call.
+ * d_partial[(Mpad/256)][gtile]: per-CTA sums of coefw*(ln S_ig - lwtr), in fixed
+ * order (deterministic).  d_sbuf: nsplit*Mpad*gtile doubles, needed if nsplit>1. */
+int kdsb200_mlcv_scores_f32(const float* d_packed, uint64_t N, int D, const float* d_qT,
+                            uint64_t M, uint64_t Mpad, const int32_t* d_excl_lo,
+                            const int32_t* d_excl_hi, const double* d_coefw,
+                            const double* d_lwtr, const float* h_nk, int G, int nsplit,
+                            double* d_sbuf, double* d_partial, void* stream);
+
+/* ---- kNN: NearestNeighbors(k+1).kneighbors inside batches (kde.py:91-98) -- */
+/* d_data (N,D) fp64 row-major; d_batch_off: nb+1 int64 offsets (np.array_split
+ * bounds); kk = k+1 (self included).  use_f64 != 0 reproduces numpy/sklearn
+ * distances bit for bit; 0 is the fp32 fast mode.  d_scratch: N*D elements of
+ * the compute type.  Outputs (each may be NULL): d_kth (N) distance to the
+ * kk-th neighbour, d_dist (N,kk) ascending, d_idx (N,kk) index inside the batch,
+ * ordered by (distance, index). */
+int kdsb200_knn(const double* d_data, uint64_t N, int D, const int64_t* d_batch_off, int nb,
+                int64_t max_batch, int kk, int use_f64, void* d_scratch, double* d_kth,
+                double* d_dist, int32_t* d_idx, void* stream);
+
+/* ---- resampling: KDS_rand_sample2 loop (kdsource.c:282-330, resamplemcpl.c:40-43)
+ * with the metric perturbations of geom.c:192-650 ------------------------- */
+#define KDSB200_MAX_METRICS 8
+typedef struct {
+  int32_t type;      /* index into _metric_names, geom.c:13-16 */
+  int32_t dim;
+  float scaling[6];  /* float, as Metric_create stores it (geom.c:35-38) */
+  int32_t nps;
+  double params[8];
+} kdsb200_metric;
+typedef struct {
+  int32_t order;
+  kdsb200_metric ms[KDSB200_MAX_METRICS];
+  char kernel;       /* 'g' | 'e' | 'b' */
+  int32_t has_trasl, has_rot;
+  double trasl[3], rot[3];
+} kdsb200_geom;
+
+uint64_t kdsb200_cdf_scratch_words(uint64_t N);
+/* Fixed-point CDF: c_i = floor(w_i * 2^62 / sum_w) (>=1 if w_i>0), inclusive
+ * uint64 prefix sums (order independent, hence bit-reproducible). */
+int kdsb200_weights_cdf(const double* d_w, uint64_t N, double sum_w, uint64_t* d_scratch,
+                        uint64_t* d_cdf, void* stream);
+/* (N,8) fp64 particles [ekin,x,y,z,ux,uy,uz,t] -> fp32 or fp64 device store */
+int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void* d_out,
+                              void* stream);
+/* Output particle n (global index first+n): Philox4x32-10 counter (index, block),
+ * key = seed; pick = first i with cdf[i] > mulhi64(R64, total); then Geom_perturb.
+ * d_ext_uniforms (count x slots doubles) replaces Philox (test mode).
+ * Outputs (each may be NULL): 36-byte MCPL-3 single-precision records, picked
+ * source index, full-precision particle (8 doubles). */
+int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf, const float* d_bw,
+                     double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
+                     uint64_t seed, uint64_t first, uint64_t count, const double* d_ext_uniforms,
+                     int slots, int perturb, void* d_out36, int64_t* d_out_idx,
+                     double* d_out_parts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDSB200_H */

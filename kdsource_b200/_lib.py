@@ -1,0 +1,164 @@
+"""ctypes binding of ``libkdsb200.so`` (the C ABI declared in include/kdsb200.h).
+
+Plays the role of the reference's ``python/kdsource/_chooks.py`` /
+``_chooks_loadlib.py``: the shared library is located next to this file and
+loaded with ``ctypes.CDLL``.  There is no CPU fallback: if the library is not
+built or no CUDA device is present, the first use raises.
+
+PyTorch is used only as a device-buffer allocator and stream provider
+(``tensor.data_ptr()`` / ``torch.cuda.current_stream().cuda_stream``).
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBNAME = "libkdsb200.so"
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_u64 = ctypes.c_uint64
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_i32 = ctypes.c_int32
+c_double = ctypes.c_double
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+
+MAX_METRICS = 8
+
+
+class Metric(ctypes.Structure):
+    """kdsb200_metric"""
+
+    _fields_ = [
+        ("type", ctypes.c_int32),
+        ("dim", ctypes.c_int32),
+        ("scaling", ctypes.c_float * 6),
+        ("nps", ctypes.c_int32),
+        ("params", ctypes.c_double * 8),
+    ]
+
+
+class Geom(ctypes.Structure):
+    """kdsb200_geom"""
+
+    _fields_ = [
+        ("order", ctypes.c_int32),
+        ("ms", Metric * MAX_METRICS),
+        ("kernel", ctypes.c_char),
+        ("has_trasl", ctypes.c_int32),
+        ("has_rot", ctypes.c_int32),
+        ("trasl", ctypes.c_double * 3),
+        ("rot", ctypes.c_double * 3),
+    ]
+
+
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "kdsb200_last_error": (ctypes.c_char_p, []),
+    "kdsb200_version": (c_int, []),
+    "kdsb200_device_info": (c_int, [ctypes.POINTER(c_int)] * 4),
+    "kdsb200_calibrate_pipe": (c_int, [c_int, c_void_p, c_int, c_double_p, c_void_p]),
+    "kdsb200_packed_floats": (c_u64, [c_u64, c_int]),
+    "kdsb200_eval_mpad": (c_u64, [c_u64]),
+    "kdsb200_pack_sources_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_u64, c_int,
+                                         c_double_p, c_double, c_double, c_int, c_void_p,
+                                         c_void_p]),
+    "kdsb200_pack_queries_f32": (c_int, [c_void_p, c_u64, c_u64, c_int, c_double_p, c_void_p,
+                                         c_void_p]),
+    "kdsb200_eval_nsplit": (c_int, [c_u64, c_u64]),
+    "kdsb200_kde_eval_f32": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_u64, c_u64, c_double,
+                                     c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "kdsb200_kde_eval_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_u64, c_int,
+                                     c_double, c_void_p, c_u64, c_double, c_int, c_void_p,
+                                     c_void_p, c_void_p]),
+    "kdsb200_mlcv_gtile": (c_int, [c_int]),
+    "kdsb200_mlcv_mpad": (c_u64, [c_u64]),
+    "kdsb200_mlcv_nsplit": (c_int, [c_u64, c_u64]),
+    "kdsb200_mlcv_scores_f32": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_u64, c_u64, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_float_p, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p]),
+    "kdsb200_knn": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_int, c_i64, c_int, c_int,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kdsb200_cdf_scratch_words": (c_u64, [c_u64]),
+    "kdsb200_weights_cdf": (c_int, [c_void_p, c_u64, c_double, c_void_p, c_void_p, c_void_p]),
+    "kdsb200_convert_particles": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_void_p]),
+    "kdsb200_resample": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_i64,
+                                 ctypes.POINTER(Geom), c_i32, c_u64, c_u64, c_u64, c_void_p,
+                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+EXPORTS = sorted(_SIGNATURES)
+
+
+def libpath():
+    return os.path.join(_HERE, LIBNAME)
+
+
+def load():
+    """Load the shared library (no GPU needed just to load and bind symbols)."""
+    global _lib
+    if _lib is None:
+        path = libpath()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                "{} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C kdsource_b200/csrc`".format(path))
+        L = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libkdsb200: " + load().kdsb200_last_error().decode("utf8", "replace"))
+
+
+_torch = None
+
+
+def torch():
+    """torch with a CUDA device, or a loud failure (no CPU fallback)."""
+    global _torch
+    if _torch is None:
+        import torch as _t
+
+        if not _t.cuda.is_available():
+            raise RuntimeError(
+                "kdsource_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        _torch = _t
+    return _torch
+
+
+def stream():
+    return ctypes.c_void_p(torch().cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def to_dev(a, dtype=np.float64):
+    """numpy (host) -> contiguous device tensor."""
+    t = torch()
+    arr = np.ascontiguousarray(a, dtype=dtype)
+    return t.from_numpy(arr).to("cuda", non_blocking=False)
+
+
+def empty(n, dtype):
+    t = torch()
+    return t.empty(int(n), dtype=dtype, device="cuda")
+
+
+def hostvec(a):
+    """numpy float64 vector -> (keepalive, POINTER(double))."""
+    v = np.ascontiguousarray(a, dtype=np.float64)
+    return v, v.ctypes.data_as(c_double_p)

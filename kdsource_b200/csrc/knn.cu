@@ -1,0 +1,341 @@
+// knn_kth_dist: brute-force k-nearest-neighbour search inside contiguous batches,
+// the arithmetic of sklearn NearestNeighbors(n_neighbors=k+1).fit(b).kneighbors(b)
+// at python/kdsource/kde.py:93-98 (self point included, distances ascending).
+//
+// One CTA owns a chunk of query rows of one batch; each warp owns a subset of the
+// rows.  Candidates stream through shared memory in tiles; every lane keeps JL
+// candidates in registers and the row coordinates arrive as broadcast LDS.  Per
+// row the state in shared memory is a sorted (distance^2, index) list of KP
+// entries, a 32-entry candidate queue and the current threshold tau (the kk-th
+// best so far).  Lanes ballot `d2 <= tau`; survivors are compacted into the
+// queue, and a full queue is sorted with a warp-shuffle bitonic network and
+// merged into the list with bitonic merges (one per 32-entry chunk).
+// Neighbour order is (distance^2, index) lexicographic, which makes indices
+// deterministic under ties.
+//
+// T = double reproduces numpy/sklearn bit for bit (sub, mul, add in coordinate
+// order, no FMA contraction); T = float is the fast mode (FMA chain).
+#include <math.h>
+
+#include "common.cuh"
+#include "kdsb200.h"
+
+namespace kdsb {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_WARPS = KNN_THREADS / 32;
+
+template <typename T>
+struct Ent {
+  T d;
+  int i;
+};
+
+template <typename T>
+__device__ __forceinline__ bool ent_less(const Ent<T>& a, const Ent<T>& b) {
+  return a.d < b.d || (a.d == b.d && a.i < b.i);
+}
+
+template <typename T>
+__device__ __forceinline__ Ent<T> ent_shfl_xor(const Ent<T>& a, int m) {
+  Ent<T> r;
+  r.d = __shfl_xor_sync(0xffffffffu, a.d, m);
+  r.i = __shfl_xor_sync(0xffffffffu, a.i, m);
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ Ent<T> ent_shfl(const Ent<T>& a, int src) {
+  Ent<T> r;
+  r.d = __shfl_sync(0xffffffffu, a.d, src);
+  r.i = __shfl_sync(0xffffffffu, a.i, src);
+  return r;
+}
+
+// compare-exchange step of a bitonic network across lanes
+template <typename T>
+__device__ __forceinline__ Ent<T> cex(const Ent<T>& v, int j, bool take_min) {
+  const Ent<T> o = ent_shfl_xor(v, j);
+  const bool o_less = ent_less(o, v);
+  return (o_less == take_min) ? o : v;
+}
+
+// full bitonic sort of 32 entries (one per lane), ascending
+template <typename T>
+__device__ __forceinline__ Ent<T> warp_sort32(Ent<T> v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const bool up = (lane & k) == 0;
+      const bool lower = (lane & j) == 0;
+      v = cex(v, j, lower == up);
+    }
+  }
+  return v;
+}
+
+// sorts a bitonic sequence of 32 entries ascending
+template <typename T>
+__device__ __forceinline__ Ent<T> warp_bitonic_merge32(Ent<T> v, int lane) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) v = cex(v, j, (lane & j) == 0);
+  return v;
+}
+
+template <typename T>
+struct KnnSmem {
+  T* rowq;     // [RC][D]
+  T* tau;      // [RC]
+  int* qcnt;   // [RC]
+  T* list_d;   // [RC][KP]
+  int* list_i; // [RC][KP]
+  T* que_d;    // [RC][32]
+  int* que_i;  // [RC][32]
+  T* cand;     // [D][CT]
+};
+
+// merge the 32 queue entries of row r (padded with +inf beyond `cnt`) into its list
+template <typename T>
+__device__ __forceinline__ void merge_queue(const KnnSmem<T>& S, int r, int cnt, int KP, int kk,
+                                            int lane) {
+  Ent<T> b;
+  if (lane < cnt) {
+    b.d = S.que_d[r * 32 + lane];
+    b.i = S.que_i[r * 32 + lane];
+  } else {
+    b.d = (T)INFINITY;
+    b.i = 0x7fffffff;
+  }
+  b = warp_sort32(b, lane);
+  for (int c = 0; c < KP; c += 32) {
+    Ent<T> a;
+    a.d = S.list_d[r * KP + c + lane];
+    a.i = S.list_i[r * KP + c + lane];
+    const Ent<T> br = ent_shfl(b, 31 - lane);
+    const bool a_less = ent_less(a, br);
+    Ent<T> lo = a_less ? a : br;
+    Ent<T> hi = a_less ? br : a;
+    lo = warp_bitonic_merge32(lo, lane);
+    hi = warp_bitonic_merge32(hi, lane);
+    S.list_d[r * KP + c + lane] = lo.d;
+    S.list_i[r * KP + c + lane] = lo.i;
+    b = hi;
+  }
+  __syncwarp();
+  if (lane == 0) S.tau[r] = S.list_d[r * KP + kk - 1];
+  __syncwarp();
+}
+
+template <typename T, int D>
+__device__ __forceinline__ T dist2(const T (&q)[D], const T* x) {
+  if constexpr (sizeof(T) == 8) {
+    // numpy order: ((d0*d0 + d1*d1) + d2*d2) ... without contraction
+    double t = __dsub_rn(q[0], x[0]);
+    double acc = __dmul_rn(t, t);
+#pragma unroll
+    for (int k = 1; k < D; k++) {
+      t = __dsub_rn(q[k], x[k]);
+      acc = __dadd_rn(acc, __dmul_rn(t, t));
+    }
+    return acc;
+  } else {
+    float t = q[0] - x[0];
+    float acc = t * t;
+#pragma unroll
+    for (int k = 1; k < D; k++) {
+      t = q[k] - x[k];
+      acc = fmaf(t, t, acc);
+    }
+    return acc;
+  }
+}
+
+template <typename T, int D, int JL>
+__global__ void __launch_bounds__(KNN_THREADS)
+    knn_kernel(const T* __restrict__ dataT /* [D][Nstride] */, uint64_t Nstride,
+               const int64_t* __restrict__ batch_off, int chunks, int RC, int KP, int kk,
+               double* __restrict__ out_kth, double* __restrict__ out_dist,
+               int32_t* __restrict__ out_idx) {
+  constexpr int CT = 32 * JL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KnnSmem<T> S;
+  {
+    unsigned char* p = smem_raw;
+    S.rowq = reinterpret_cast<T*>(p);   p += sizeof(T) * RC * D;
+    S.tau = reinterpret_cast<T*>(p);    p += sizeof(T) * RC;
+    S.list_d = reinterpret_cast<T*>(p); p += sizeof(T) * RC * KP;
+    S.que_d = reinterpret_cast<T*>(p);  p += sizeof(T) * RC * 32;
+    S.cand = reinterpret_cast<T*>(p);   p += sizeof(T) * D * CT;
+    S.qcnt = reinterpret_cast<int*>(p); p += sizeof(int) * RC;
+    S.list_i = reinterpret_cast<int*>(p); p += sizeof(int) * RC * KP;
+    S.que_i = reinterpret_cast<int*>(p);
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bidx = blockIdx.x / chunks;  // batch
+  const int64_t b0 = batch_off[bidx], b1 = batch_off[bidx + 1];
+  const int bn = (int)(b1 - b0);
+  const int r0 = (blockIdx.x % chunks) * RC;
+  if (r0 >= bn) return;
+  const int nrows = min(RC, bn - r0);
+
+  for (int e = tid; e < nrows * D; e += KNN_THREADS) {
+    const int r = e / D, k = e % D;
+    S.rowq[r * D + k] = dataT[(uint64_t)k * Nstride + b0 + r0 + r];
+  }
+  for (int e = tid; e < nrows; e += KNN_THREADS) {
+    S.tau[e] = (T)INFINITY;
+    S.qcnt[e] = 0;
+  }
+  for (int e = tid; e < nrows * KP; e += KNN_THREADS) {
+    S.list_d[e] = (T)INFINITY;
+    S.list_i[e] = 0x7fffffff;
+  }
+
+  for (int cbase = 0; cbase < bn; cbase += CT) {
+    __syncthreads();
+    for (int e = tid; e < D * CT; e += KNN_THREADS) {
+      const int k = e / CT, c = e % CT;
+      S.cand[e] = (cbase + c < bn) ? dataT[(uint64_t)k * Nstride + b0 + cbase + c] : (T)0;
+    }
+    __syncthreads();
+    T x[JL][D];
+#pragma unroll
+    for (int e = 0; e < JL; e++)
+#pragma unroll
+      for (int k = 0; k < D; k++) x[e][k] = S.cand[k * CT + e * 32 + lane];
+
+    for (int r = warp; r < nrows; r += KNN_WARPS) {
+      T q[D];
+#pragma unroll
+      for (int k = 0; k < D; k++) q[k] = S.rowq[r * D + k];
+      T tau = S.tau[r];
+#pragma unroll
+      for (int e = 0; e < JL; e++) {
+        const int j = cbase + e * 32 + lane;
+        const T d2 = dist2<T, D>(q, x[e]);
+        const bool pred = (j < bn) && (d2 <= tau);
+        const unsigned mask = __ballot_sync(0xffffffffu, pred);
+        if (mask) {
+          const int cnt = S.qcnt[r];
+          const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+          if (pred && pos < 32) {
+            S.que_d[r * 32 + pos] = d2;
+            S.que_i[r * 32 + pos] = j;
+          }
+          int total = cnt + __popc(mask);
+          __syncwarp();
+          if (total >= 32) {
+            merge_queue<T>(S, r, 32, KP, kk, lane);
+            if (pred && pos >= 32) {
+              S.que_d[r * 32 + pos - 32] = d2;
+              S.que_i[r * 32 + pos - 32] = j;
+            }
+            total -= 32;
+            tau = S.tau[r];
+          }
+          if (lane == 0) S.qcnt[r] = total;
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // flush leftovers and write results
+  for (int r = warp; r < nrows; r += KNN_WARPS) {
+    const int cnt = S.qcnt[r];
+    if (cnt > 0) merge_queue<T>(S, r, cnt, KP, kk, lane);
+    const uint64_t row = (uint64_t)(b0 + r0 + r);
+    for (int e = lane; e < kk; e += 32) {
+      const double dd = sqrt((double)S.list_d[r * KP + e]);
+      if (out_dist) out_dist[row * kk + e] = dd;
+      if (out_idx) out_idx[row * kk + e] = S.list_i[r * KP + e] == 0x7fffffff ? -1 : S.list_i[r * KP + e];
+      if (e == kk - 1 && out_kth) out_kth[row] = dd;
+    }
+  }
+}
+
+template <typename T>
+__global__ void knn_transpose_kernel(const double* __restrict__ data, uint64_t N, int D,
+                                     uint64_t Nstride, T* __restrict__ dataT) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  for (int k = 0; k < D; k++) dataT[(uint64_t)k * Nstride + i] = (T)data[i * D + k];
+}
+
+template <typename T>
+static size_t knn_smem_bytes(int RC, int KP, int D, int CT) {
+  return sizeof(T) * ((size_t)RC * D + RC + (size_t)RC * KP + (size_t)RC * 32 + (size_t)D * CT) +
+         sizeof(int) * ((size_t)RC + (size_t)RC * KP + (size_t)RC * 32);
+}
+
+template <typename T, int D>
+static int launch_knn(const double* d_data, uint64_t N, const int64_t* d_batch_off, int nb,
+                      int64_t max_batch, int kk, void* d_scratch, double* out_kth,
+                      double* out_dist, int32_t* out_idx, cudaStream_t st) {
+  constexpr int JL = sizeof(T) == 8 ? 4 : 8;
+  constexpr int CT = 32 * JL;
+  const int KP = (kk + 31) / 32 * 32;
+  int RC = 128;
+  while (RC > KNN_WARPS && knn_smem_bytes<T>(RC, KP, D, CT) > 200 * 1024) RC /= 2;
+  const size_t smem = knn_smem_bytes<T>(RC, KP, D, CT);
+  if (smem > 227 * 1024) {
+    set_error("knn: k+1=%d needs %zu bytes of shared memory per CTA (limit 227 KB)", kk, smem);
+    return 1;
+  }
+  T* dataT = reinterpret_cast<T*>(d_scratch);
+  knn_transpose_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_data, N, D, N, dataT);
+  KDSB_CUDA(cudaGetLastError());
+  KDSB_CUDA(cudaFuncSetAttribute(knn_kernel<T, D, JL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  const int64_t chunks = (max_batch + RC - 1) / RC;
+  if (chunks * nb >= (1ll << 31)) {
+    set_error("knn: grid too large (%lld CTAs)", (long long)(chunks * nb));
+    return 1;
+  }
+  knn_kernel<T, D, JL><<<(unsigned)(chunks * nb), KNN_THREADS, smem, st>>>(
+      dataT, N, d_batch_off, (int)chunks, RC, KP, kk, out_kth, out_dist, out_idx);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace kdsb
+
+using namespace kdsb;
+
+extern "C" {
+
+int kdsb200_knn(const double* d_data, uint64_t N, int D, const int64_t* d_batch_off, int nb,
+                int64_t max_batch, int kk, int use_f64, void* d_scratch, double* d_kth,
+                double* d_dist, int32_t* d_idx, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0 || nb == 0) return 0;
+  if (kk < 1 || kk > 1024) {
+    set_error("knn: k+1=%d out of range 1..1024", kk);
+    return 1;
+  }
+  if (max_batch >= (1ll << 31)) {
+    set_error("knn: batch too large (%lld rows)", (long long)max_batch);
+    return 1;
+  }
+  switch (D) {
+#define KDSB_CASE(d)                                                                            \
+  case d:                                                                                       \
+    return use_f64 ? launch_knn<double, d>(d_data, N, d_batch_off, nb, max_batch, kk, d_scratch, \
+                                           d_kth, d_dist, d_idx, st)                            \
+                   : launch_knn<float, d>(d_data, N, d_batch_off, nb, max_batch, kk, d_scratch,  \
+                                          d_kth, d_dist, d_idx, st);
+    KDSB_CASE(1)
+    KDSB_CASE(2)
+    KDSB_CASE(3)
+    KDSB_CASE(4)
+    KDSB_CASE(5)
+    KDSB_CASE(6)
+    KDSB_CASE(7)
+    KDSB_CASE(8)
+#undef KDSB_CASE
+  }
+  set_error("knn: D=%d out of range 1..8", D);
+  return 1;
+}
+
+}  // extern "C"

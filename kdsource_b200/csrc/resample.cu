@@ -1,0 +1,704 @@
+// resample: weighted particle pick (fixed-point prefix sum + binary search) followed
+// by the per-metric kernel perturbation of clib/src/geom.c:139-650, one output
+// particle per thread, driven by counter-based Philox4x32-10 (or by caller-supplied
+// uniforms in the test mode).  Replaces the serial loop of
+// clib/src/resamplemcpl.c:40-43 over KDS_rand_sample2 (clib/src/kdsource.c:282-330)
+// and packs the result straight into 36-byte single-precision MCPL-3 records, the
+// format mcpl_add_particle writes for resamplemcpl.c:31-42.
+//
+// The pick is this library's own contract (the reference walks the list
+// sequentially); the perturbation maps, deviate maps (clib/src/utils.c:9-67) and
+// uniform-consumption order follow the reference.
+#include <math.h>
+
+#include "common.cuh"
+#include "kdsb200.h"
+
+namespace kdsb {
+
+#define KDS_PI 3.1415926535897932384626433832795028841971694
+
+enum {
+  M_ENERGY = 0, M_LETHARGY, M_WAVELENGTH, M_VOL, M_SURFXY, M_SURFR, M_SURFR2, M_SURFCIRCLE,
+  M_GUIDE, M_ISOTROP, M_POLAR, M_POLARMU, M_TIME, M_DECADE
+};  // order of _metric_names, clib/src/geom.c:13-16
+
+// ---- weights -> fixed-point CDF -------------------------------------------
+// c_i = floor(w_i * 2^62 / sum w) (>= 1 for w_i > 0); inclusive prefix sums in
+// uint64 are exactly associative, so any scan order gives the same CDF.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint64_t quantise_w(double w, double scale) {
+  uint64_t c = (uint64_t)(w * scale);
+  if (c == 0 && w > 0) c = 1;
+  return c;
+}
+
+__device__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* total) {
+  __shared__ uint64_t wsum[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  uint64_t woff = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; w++) {
+    if (w < warp) woff += wsum[w];
+    tot += wsum[w];
+  }
+  __syncthreads();
+  *total = tot;
+  return woff + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+    cdf_block_sums_kernel(const double* __restrict__ w, uint64_t N, double scale,
+                          uint64_t* __restrict__ bsum) {
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint64_t s = 0;
+#pragma unroll
+  for (int e = 0; e < SCAN_ITEMS; e++)
+    if (base + e < N) s += quantise_w(w[base + e], scale);
+  uint64_t tot;
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+// single-block exclusive scan of the per-block sums (in place)
+__global__ void __launch_bounds__(SCAN_THREADS)
+    cdf_scan_sums_kernel(uint64_t* __restrict__ bsum, uint64_t nblocks) {
+  uint64_t carry = 0;
+  for (uint64_t base = 0; base < nblocks; base += SCAN_THREADS) {
+    const uint64_t i = base + threadIdx.x;
+    const uint64_t v = i < nblocks ? bsum[i] : 0;
+    uint64_t tot;
+    const uint64_t ex = block_exclusive_scan(v, &tot);
+    if (i < nblocks) bsum[i] = carry + ex;
+    carry += tot;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+    cdf_write_kernel(const double* __restrict__ w, uint64_t N, double scale,
+                     const uint64_t* __restrict__ bsum, uint64_t* __restrict__ cdf) {
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint64_t c[SCAN_ITEMS];
+  uint64_t s = 0;
+#pragma unroll
+  for (int e = 0; e < SCAN_ITEMS; e++) {
+    c[e] = base + e < N ? quantise_w(w[base + e], scale) : 0;
+    s += c[e];
+  }
+  uint64_t tot;
+  uint64_t run = bsum[blockIdx.x] + block_exclusive_scan(s, &tot);
+#pragma unroll
+  for (int e = 0; e < SCAN_ITEMS; e++) {
+    run += c[e];
+    if (base + e < N) cdf[base + e] = run;
+  }
+}
+
+// ---- Philox4x32-10 --------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// per-particle uniform stream (see oracle/kds_oracle.c "orc_stream")
+template <bool EXT>
+struct Stream {
+  uint32_t k0, k1, p0, p1, blk;
+  uint32_t buf[4];
+  int have;
+  const double* ext;
+  int slots, next;
+
+  __device__ __forceinline__ void init(uint64_t seed, uint64_t p, const double* e, int nslots) {
+    if (EXT) {
+      ext = e + p * (uint64_t)nslots;
+      slots = nslots;
+      next = 0;
+    } else {
+      k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+      p0 = (uint32_t)p; p1 = (uint32_t)(p >> 32);
+      blk = 0;
+      philox4x32_10(p0, p1, 0u, 0u, k0, k1, buf);
+      have = 4;
+    }
+  }
+  __device__ __forceinline__ uint32_t word() {
+    if (have == 0) {
+      blk += 1;
+      philox4x32_10(p0, p1, blk, 0u, k0, k1, buf);
+      have = 4;
+    }
+    // buf[4 - have] without dynamic register indexing
+    const int sel = 4 - have;
+    const uint32_t w = sel == 0 ? buf[0] : sel == 1 ? buf[1] : sel == 2 ? buf[2] : buf[3];
+    have--;
+    return w;
+  }
+  __device__ __forceinline__ double ext_next() {
+    const double u = ext[next % slots];
+    next++;
+    return u;
+  }
+  __device__ __forceinline__ uint64_t pick_target(uint64_t total) {
+    if (EXT) {
+      uint64_t T = (uint64_t)(ext_next() * (double)total);
+      return T >= total ? total - 1 : T;
+    }
+    const uint64_t hi = word(), lo = word();
+    return __umul64hi((hi << 32) | lo, total);
+  }
+  // 23-bit integer k of the next uniform u = (k + 0.5) 2^-23 (Philox mode only)
+  __device__ __forceinline__ int kint() { return (int)(word() >> 9); }
+};
+
+template <typename R>
+struct Mth;
+template <>
+struct Mth<float> {
+  static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+  static __device__ __forceinline__ float log_(float x) { return logf(x); }
+  static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
+  static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
+  static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+  static __device__ __forceinline__ float acos_(float x) { return acosf(x); }
+  static __device__ __forceinline__ float asin_(float x) { return asinf(x); }
+  static __device__ __forceinline__ float pow10_(float x) { return exp10f(x); }
+};
+template <>
+struct Mth<double> {
+  static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+  static __device__ __forceinline__ double log_(double x) { return log(x); }
+  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static __device__ __forceinline__ double sin_(double x) { return sin(x); }
+  static __device__ __forceinline__ double cos_(double x) { return cos(x); }
+  static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+  static __device__ __forceinline__ double acos_(double x) { return acos(x); }
+  static __device__ __forceinline__ double asin_(double x) { return asin(x); }
+  static __device__ __forceinline__ double pow10_(double x) { return pow(10.0, x); }
+};
+
+template <typename R, bool EXT>
+__device__ __forceinline__ R uniform(Stream<EXT>& s) {
+  if (EXT) return (R)s.ext_next();
+  return ((R)s.kint() + (R)0.5) * (R)(1.0 / 8388608.0);
+}
+
+// kds_rand_norm: Marsaglia polar method, second value discarded (utils.c:9-29).
+// Accept/reject is decided exactly (integers for Philox, fp64 for external
+// uniforms) so fp32 and fp64 modes consume the same number of uniforms.
+template <typename R, bool EXT>
+__device__ R rand_norm(Stream<EXT>& s) {
+  if (EXT) {
+    double t, g1, g2;
+    do {
+      g1 = 2.0 * s.ext_next() - 1.0;
+      g2 = 2.0 * s.ext_next() - 1.0;
+      t = g1 * g1 + g2 * g2;
+    } while (t >= 1.0 || t == 0.0);
+    if (sizeof(R) == 8) return (R)(g1 * sqrt((-2.0 * log(t)) / t));
+    const float tf = (float)t;
+    const float lt = t > 0.5 ? log1pf((float)(t - 1.0)) : logf(tf);
+    return (R)((float)g1 * sqrtf((-2.0f * lt) / tf));
+  } else {
+    int G1, G2;
+    long long ti;
+    do {
+      G1 = 2 * s.kint() + 1 - (1 << 23);
+      G2 = 2 * s.kint() + 1 - (1 << 23);
+      ti = (long long)G1 * G1 + (long long)G2 * G2;
+    } while (ti >= (1ll << 46));
+    if (sizeof(R) == 8) {
+      const double t = (double)ti * (1.0 / 70368744177664.0);
+      const double g1 = (double)G1 * (1.0 / 8388608.0);
+      return (R)(g1 * sqrt((-2.0 * log(t)) / t));
+    }
+    const float tf = (float)ti * (1.0f / 70368744177664.0f);
+    const float g1 = (float)G1 * (1.0f / 8388608.0f);
+    const float lt = ti > (1ll << 45)
+                         ? log1pf(-(float)((1ll << 46) - ti) * (1.0f / 70368744177664.0f))
+                         : logf(tf);
+    return (R)(g1 * sqrtf((-2.0f * lt) / tf));
+  }
+}
+
+// kds_rand_epan (utils.c:32-46)
+template <typename R, bool EXT>
+__device__ R rand_epan(Stream<EXT>& s) {
+  const R x1 = uniform<R, EXT>(s) * (R)2 - (R)1;
+  const R x2 = uniform<R, EXT>(s) * (R)2 - (R)1;
+  const R x3 = uniform<R, EXT>(s) * (R)2 - (R)1;
+  if (fabs(x3) >= fabs(x2) && fabs(x3) >= fabs(x1)) return x2;
+  return x3;
+}
+
+// kds_rand_type (utils.c:55-67)
+template <typename R, bool EXT>
+__device__ R rand_type(Stream<EXT>& s, char kernel) {
+  if (kernel == 'g') return rand_norm<R, EXT>(s);
+  if (kernel == 'e') return rand_epan<R, EXT>(s);
+  if (kernel == 'b') return uniform<R, EXT>(s) * (R)2 - (R)1;
+  return (R)0;
+}
+
+template <typename R>
+struct Part {
+  R ekin, pos[3], dir[3], time;
+};
+
+template <typename R>
+__device__ __forceinline__ void reflect(R& x, R lo, R hi) {
+  while ((x < lo) || (x > hi)) {
+    if (x < lo)
+      x += 2 * (lo - x);
+    else
+      x -= 2 * (x - hi);
+  }
+}
+
+// rotv (Rodrigues, utils.c:82-103)
+template <typename R>
+__device__ void rotv(R* v, const double* rv, int inverse) {
+  using M = Mth<R>;
+  R r0 = (R)rv[0], r1 = (R)rv[1], r2 = (R)rv[2];
+  R theta = M::sqrt_(r0 * r0 + r1 * r1 + r2 * r2);
+  if (theta == 0) return;
+  if (inverse) theta = -theta;
+  const R kdotv = r0 * v[0] + r1 * v[1] + r2 * v[2];
+  const R kx[3] = {r1 * v[2] - r2 * v[1], r2 * v[0] - r0 * v[2], r0 * v[1] - r1 * v[0]};
+  const R rr[3] = {r0, r1, r2};
+  const R ct = M::cos_(theta), st = M::sin_(theta);
+  R o[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    o[i] = v[i] * ct + (kx[i] / fabs(theta)) * st + rr[i] * kdotv / (theta * theta) * (1 - ct);
+#pragma unroll
+  for (int i = 0; i < 3; i++) v[i] = o[i];
+}
+
+// _vMF_perturb (geom.c:557-573)
+template <typename R, bool EXT>
+__device__ void vmf_perturb(Stream<EXT>& s, R bw, R& dx, R& dy, R& dz) {
+  using M = Mth<R>;
+  const R xi = uniform<R, EXT>(s);
+  R w, uv;
+  if (sizeof(R) == 8) {
+    w = 1;
+    w += bw * bw * M::log_(xi + (1 - xi) * M::exp_(-2 / (bw * bw)));
+    uv = M::sqrt_(1 - w * w);
+  } else {
+    // same map, arranged so 1 - w*w does not cancel in fp32
+    const R m = -bw * bw * M::log_(xi + (1 - xi) * M::exp_(-2 / (bw * bw)));
+    w = 1 - m;
+    uv = M::sqrt_(fmax(m * (2 - m), (R)0));
+  }
+  const R u01 = uniform<R, EXT>(s);
+  R sphi, cphi;
+  if (sizeof(R) == 8) {
+    const R phi = (R)(2. * KDS_PI) * u01;
+    sphi = M::sin_(phi);
+    cphi = M::cos_(phi);
+  } else {
+    float sf, cf;
+    sincospif(2.0f * (float)u01, &sf, &cf);
+    sphi = sf;
+    cphi = cf;
+  }
+  const R u = uv * cphi, v = uv * sphi;
+  const R dx0 = dx, dy0 = dy, dz0 = dz;
+  if (dz0 > 0) {
+    dx = u * dz0 + w * dx0 - (v * dx0 - u * dy0) * dy0 / (1 + dz0);
+    dy = v * dz0 + w * dy0 + (v * dx0 - u * dy0) * dx0 / (1 + dz0);
+  } else {
+    dx = u * dz0 + w * dx0 + (v * dx0 - u * dy0) * dy0 / (1 - dz0);
+    dy = v * dz0 + w * dy0 - (v * dx0 - u * dy0) * dx0 / (1 - dz0);
+  }
+  dz = w * dz0 - u * dx0 - v * dy0;
+}
+
+// Guide_perturb (geom.c:386-555)
+template <typename R, bool EXT>
+__device__ void guide_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>& p, R bw,
+                              char kernel) {
+  using M = Mth<R>;
+  R x = p.pos[0], y = p.pos[1], z = p.pos[2];
+  R dx = p.dir[0], dy = p.dir[1], dz = p.dir[2], dx2, dz2;
+  const R xw = (R)m.params[0], yh = (R)m.params[1], zmax = (R)m.params[2], rc = (R)m.params[3];
+  R t = 0, mu = 0, mu2 = 0, phi = 0;
+  int mirror;
+  if (rc != 0) {
+    const R r = M::sqrt_((rc + x) * (rc + x) + z * z);
+    x = copysign((R)1, rc) * r - rc;
+    z = fabs(rc) * M::asin_(z / r);
+    dx2 = dx;
+    dz2 = dz;
+    dx = dx2 * M::cos_(z / rc) + dz2 * M::sin_(z / rc);
+    dz = -dx2 * M::sin_(z / rc) + dz2 * M::cos_(z / rc);
+  }
+  if ((y / yh > -x / xw) && (y / yh < x / xw))
+    mirror = 0;
+  else if ((y / yh > x / xw) && (y / yh > -x / xw))
+    mirror = 1;
+  else if ((y / yh < -x / xw) && (y / yh > x / xw))
+    mirror = 2;
+  else
+    mirror = 3;
+  R lo = 0, hi = 0;
+  switch (mirror) {
+    case 0: t = (R)0.5 * yh + y; mu = dx; phi = M::atan2_(-dy, dz); lo = 0; hi = yh; break;
+    case 1: t = yh + (R)0.5 * xw - x; mu = dy; phi = M::atan2_(dx, dz); lo = yh; hi = yh + xw; break;
+    case 2: t = (R)1.5 * yh + xw - y; mu = -dx; phi = M::atan2_(dy, dz); lo = yh + xw; hi = 2 * yh + xw; break;
+    default: t = 2 * yh + (R)1.5 * xw + x; mu = -dy; phi = M::atan2_(-dx, dz); lo = 2 * yh + xw; hi = 2 * yh + 2 * xw; break;
+  }
+  z += bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+  reflect<R>(z, (R)0, zmax);
+  t += bw * (R)m.scaling[1] * rand_type<R, EXT>(s, kernel);
+  reflect<R>(t, lo, hi);
+  if (isinf(m.scaling[2]))
+    mu = -1 + 2 * uniform<R, EXT>(s);
+  else {
+    mu2 = mu + bw * (R)m.scaling[2] * rand_type<R, EXT>(s, kernel);
+    if (mu >= 0)
+      reflect<R>(mu2, (R)0, (R)1);
+    else
+      reflect<R>(mu2, (R)-1, (R)0);
+    mu = mu2;
+  }
+  if (isinf(m.scaling[3]))
+    phi = (R)(2. * KDS_PI) * uniform<R, EXT>(s);
+  else
+    phi += bw * (R)m.scaling[3] * (R)(KDS_PI / 180) * rand_type<R, EXT>(s, kernel);
+  const R sq = M::sqrt_(1 - mu * mu), cp = M::cos_(phi), sp = M::sin_(phi);
+  switch (mirror) {
+    case 0: x = xw / 2; y = t - (R)0.5 * yh; dx = mu; dz = sq * cp; dy = -sq * sp; break;
+    case 1: y = yh / 2; x = -t + yh + (R)0.5 * xw; dy = mu; dz = sq * cp; dx = sq * sp; break;
+    case 2: x = -xw / 2; y = -t + (R)1.5 * yh + xw; dx = -mu; dz = sq * cp; dy = sq * sp; break;
+    default: y = -yh / 2; x = t - 2 * yh - (R)1.5 * xw; dy = -mu; dz = sq * cp; dx = -sq * sp; break;
+  }
+  if (rc != 0) {
+    const R r = (rc + x) * copysign((R)1, rc), ang = z / rc;
+    x = copysign((R)1, rc) * r * M::cos_(ang) - rc;
+    z = r * M::sin_(fabs(ang));
+    dx2 = dx;
+    dz2 = dz;
+    dx = dx2 * M::cos_(ang) - dz2 * M::sin_(ang);
+    dz = dx2 * M::sin_(ang) + dz2 * M::cos_(ang);
+  }
+  p.pos[0] = x; p.pos[1] = y; p.pos[2] = z;
+  p.dir[0] = dx; p.dir[1] = dy; p.dir[2] = dz;
+}
+
+// one metric's perturbation: geom.c:192-650
+template <typename R, bool EXT>
+__device__ void metric_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>& p, R bw,
+                               char kernel) {
+  using M = Mth<R>;
+  const R PI180 = (R)(KDS_PI / 180);
+  switch (m.type) {
+    case M_ENERGY:  // E_perturb geom.c:192-198
+      p.ekin += bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      if (p.ekin < 0) p.ekin *= -1;
+      break;
+    case M_LETHARGY: {  // Let_perturb geom.c:200-210
+      R E = p.ekin * M::exp_(bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel));
+      while (E > (R)m.params[0])
+        E = p.ekin * M::exp_(bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel));
+      p.ekin = E;
+    } break;
+    case M_WAVELENGTH: {  // wl_perturb geom.c:212-221
+      const R wl = (R)9.045 / M::sqrt_(p.ekin * (R)1e9);
+      const R wl2 = wl + bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      p.ekin = (R)81.82e-9 / (wl2 * wl2);
+      if (p.ekin < 0) p.ekin *= -1;
+    } break;
+    case M_TIME:  // t_perturb geom.c:223-227
+      p.time += bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      break;
+    case M_DECADE:  // Dec_perturb geom.c:228-233
+      p.time *= M::pow10_(bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel));
+      break;
+    case M_VOL:  // Vol_perturb geom.c:235-265
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        p.pos[a] += bw * (R)m.scaling[a] * rand_type<R, EXT>(s, kernel);
+        reflect<R>(p.pos[a], (R)m.params[2 * a], (R)m.params[2 * a + 1]);
+      }
+      break;
+    case M_SURFXY:  // SurfXY_perturb geom.c:266-287
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+        p.pos[a] += bw * (R)m.scaling[a] * rand_type<R, EXT>(s, kernel);
+        reflect<R>(p.pos[a], (R)m.params[2 * a], (R)m.params[2 * a + 1]);
+      }
+      break;
+    case M_SURFR:    // SurfR_perturb geom.c:288-319
+    case M_SURFR2: { // SurfR2_perturb geom.c:320-354
+      const bool sq = m.type == M_SURFR2;
+      R rmin = (R)m.params[0], rmax = (R)m.params[1];
+      if (sq) { rmin *= rmin; rmax *= rmax; }
+      R rho = p.pos[0] * p.pos[0] + p.pos[1] * p.pos[1];
+      if (!sq) rho = M::sqrt_(rho);
+      const R psi = M::atan2_(p.pos[1], p.pos[0]);
+      R rho2 = rho + bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      R psi2 = psi + bw * (R)m.scaling[1] * PI180 * rand_type<R, EXT>(s, kernel);
+      reflect<R>(rho2, rmin, rmax);
+      reflect<R>(psi2, (R)m.params[2], (R)m.params[3]);
+      if (sq) rho2 = M::sqrt_(rho2);
+      p.pos[0] = rho2 * M::cos_(psi2);
+      p.pos[1] = rho2 * M::sin_(psi2);
+    } break;
+    case M_SURFCIRCLE: {  // SurfCircle_perturb geom.c:355-385
+      const R x = p.pos[0] + bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      const R y = p.pos[1] + bw * (R)m.scaling[1] * rand_type<R, EXT>(s, kernel);
+      R rho2 = M::sqrt_(x * x + y * y);
+      R psi2 = M::atan2_(y, x);
+      reflect<R>(rho2, (R)m.params[0], (R)m.params[1]);
+      reflect<R>(psi2, (R)m.params[2], (R)m.params[3]);
+      p.pos[0] = rho2 * M::cos_(psi2);
+      p.pos[1] = rho2 * M::sin_(psi2);
+    } break;
+    case M_GUIDE:
+      guide_perturb<R, EXT>(s, m, p, bw, kernel);
+      break;
+    case M_ISOTROP: {  // Isotrop_perturb geom.c:575-600 (kernel ignored)
+      const R sc = bw * (R)m.scaling[0];
+      if (isinf(sc)) {
+        p.dir[2] = -1 + 2 * uniform<R, EXT>(s);
+        const R dxy = M::sqrt_(1 - p.dir[2] * p.dir[2]);
+        const R phi = (R)(2. * KDS_PI) * uniform<R, EXT>(s);
+        p.dir[0] = dxy * M::cos_(phi);
+        p.dir[1] = dxy * M::sin_(phi);
+      } else if (sc > 0) {
+        const R dx = p.dir[0], dy = p.dir[1], dz = p.dir[2];
+        vmf_perturb<R, EXT>(s, sc, p.dir[0], p.dir[1], p.dir[2]);
+        if ((int)m.params[0] && (dx * p.dir[0] < 0)) p.dir[0] *= -1;
+        if ((int)m.params[1] && (dy * p.dir[1] < 0)) p.dir[1] *= -1;
+        if ((int)m.params[2] && (dz * p.dir[2] < 0)) p.dir[2] *= -1;
+      }
+    } break;
+    case M_POLAR: {  // Polar_perturb geom.c:602-620 (reflected theta is overwritten there too)
+      R theta = M::acos_(p.dir[2]);
+      R phi = M::atan2_(p.dir[1], p.dir[0]);
+      theta = theta + bw * (R)m.scaling[0] * PI180 * rand_type<R, EXT>(s, kernel);
+      phi += bw * (R)m.scaling[1] * PI180 * rand_type<R, EXT>(s, kernel);
+      p.dir[0] = M::sin_(theta) * M::cos_(phi);
+      p.dir[1] = M::sin_(theta) * M::sin_(phi);
+      p.dir[2] = M::cos_(theta);
+    } break;
+    case M_POLARMU: {  // PolarMu_perturb geom.c:622-650
+      R mu = p.dir[2];
+      R phi = M::atan2_(p.dir[1], p.dir[0]);
+      R mu2 = mu + bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      if (mu >= 0) {
+        while ((mu2 < 0) || (mu2 > 1)) {
+          if (mu2 < 0) mu2 *= -1;
+          if (mu2 > 1) mu2 -= 2 * (mu2 - 1);
+        }
+      } else {
+        while ((mu2 < -1) || (mu2 > 0)) {
+          if (mu2 < -1) mu2 += 2 * (-1 - mu2);
+          if (mu2 > 0) mu2 *= -1;
+        }
+      }
+      mu = mu2;
+      phi += bw * (R)m.scaling[1] * PI180 * rand_type<R, EXT>(s, kernel);
+      const R sq = M::sqrt_(1 - mu * mu);
+      p.dir[0] = sq * M::cos_(phi);
+      p.dir[1] = sq * M::sin_(phi);
+      p.dir[2] = mu;
+    } break;
+    default:
+      break;
+  }
+}
+
+template <typename R, bool EXT>
+__global__ void __launch_bounds__(256)
+    resample_kernel(const R* __restrict__ src8, const uint64_t* __restrict__ cdf,
+                    const float* __restrict__ bw, double bw_scalar, int64_t N, kdsb200_geom g,
+                    int32_t pdg, uint64_t seed, uint64_t first, uint64_t count,
+                    const double* __restrict__ ext, int slots, int perturb,
+                    unsigned char* __restrict__ out36, int64_t* __restrict__ out_idx,
+                    double* __restrict__ out_parts) {
+  const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= count) return;
+  Stream<EXT> s;
+  s.init(seed, EXT ? n : first + n, ext, slots);
+  const uint64_t total = cdf[N - 1];
+  const uint64_t T = s.pick_target(total);
+  // upper_bound: first i with cdf[i] > T
+  int64_t lo = 0, hi = N;
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(cdf + mid) > T)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  const int64_t i = lo < N ? lo : N - 1;
+
+  Part<R> p;
+  {
+    const R* r = src8 + i * 8;
+    if (sizeof(R) == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(r));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(r) + 1);
+      p.ekin = a.x; p.pos[0] = a.y; p.pos[1] = a.z; p.pos[2] = a.w;
+      p.dir[0] = b.x; p.dir[1] = b.y; p.dir[2] = b.z; p.time = b.w;
+    } else {
+      p.ekin = r[0]; p.pos[0] = r[1]; p.pos[1] = r[2]; p.pos[2] = r[3];
+      p.dir[0] = r[4]; p.dir[1] = r[5]; p.dir[2] = r[6]; p.time = r[7];
+    }
+  }
+  const R h = bw ? (R)__ldg(bw + i) : (R)bw_scalar;
+  if (perturb) {  // Geom_perturb geom.c:139-158
+    if (g.has_trasl)
+      for (int k = 0; k < 3; k++) p.pos[k] -= (R)g.trasl[k];
+    if (g.has_rot) {
+      rotv<R>(p.pos, g.rot, 1);
+      rotv<R>(p.dir, g.rot, 1);
+    }
+    for (int k = 0; k < g.order; k++) metric_perturb<R, EXT>(s, g.ms[k], p, h, g.kernel);
+    if (g.has_rot) {
+      rotv<R>(p.pos, g.rot, 0);
+      rotv<R>(p.dir, g.rot, 0);
+    }
+    if (g.has_trasl)
+      for (int k = 0; k < 3; k++) p.pos[k] += (R)g.trasl[k];
+  }
+  if (out_idx) out_idx[n] = i;
+  if (out_parts) {
+    double* o = out_parts + n * 8;
+    o[0] = p.ekin; o[1] = p.pos[0]; o[2] = p.pos[1]; o[3] = p.pos[2];
+    o[4] = p.dir[0]; o[5] = p.dir[1]; o[6] = p.dir[2]; o[7] = p.time;
+  }
+  if (out36) {
+    // MCPL adaptive projection packing (libmcpl mcpl_unitvect_pack_adaptproj)
+    const R ax = fabs(p.dir[0]), ay = fabs(p.dir[1]), az = fabs(p.dir[2]);
+    R p0, p1, sg;
+    if (az < fmax(ax, ay)) {
+      const R invz = p.dir[2] != 0 ? 1 / p.dir[2] : (R)INFINITY;
+      if (ax >= ay) { p0 = invz; p1 = p.dir[1]; sg = p.dir[0]; }
+      else { p0 = p.dir[0]; p1 = invz; sg = p.dir[1]; }
+    } else {
+      p0 = p.dir[0]; p1 = p.dir[1]; sg = p.dir[2];
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(out36 + n * 36);
+    o[0] = __float_as_uint((float)p.pos[0]);
+    o[1] = __float_as_uint((float)p.pos[1]);
+    o[2] = __float_as_uint((float)p.pos[2]);
+    o[3] = __float_as_uint((float)p0);
+    o[4] = __float_as_uint((float)p1);
+    o[5] = __float_as_uint((float)copysign(fabs(p.ekin), sg));
+    o[6] = __float_as_uint((float)p.time);
+    o[7] = __float_as_uint(1.0f);  // weight = 1/bias, kdsource.c:325
+    o[8] = (uint32_t)pdg;
+  }
+}
+
+template <typename R>
+__global__ void convert_src_kernel(const double* __restrict__ src, uint64_t n8, R* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n8) out[i] = (R)src[i];
+}
+
+}  // namespace kdsb
+
+using namespace kdsb;
+
+extern "C" {
+
+uint64_t kdsb200_cdf_scratch_words(uint64_t N) { return (N + SCAN_BLOCK - 1) / SCAN_BLOCK + 1; }
+
+int kdsb200_weights_cdf(const double* d_w, uint64_t N, double sum_w, uint64_t* d_scratch,
+                        uint64_t* d_cdf, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 0) return 0;
+  if (!(sum_w > 0)) {
+    set_error("weights_cdf: sum of weights must be positive");
+    return 1;
+  }
+  const double scale = 4611686018427387904.0 / sum_w;
+  const uint64_t nb = (N + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  cdf_block_sums_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_w, N, scale, d_scratch);
+  KDSB_CUDA(cudaGetLastError());
+  cdf_scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(d_scratch, nb);
+  KDSB_CUDA(cudaGetLastError());
+  cdf_write_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_w, N, scale, d_scratch, d_cdf);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void* d_out,
+                              void* stream) {
+  const uint64_t n8 = N * 8;
+  if (!n8) return 0;
+  if (to_f32)
+    convert_src_kernel<float><<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_src8, n8, (float*)d_out);
+  else
+    convert_src_kernel<double><<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_src8, n8, (double*)d_out);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf, const float* d_bw,
+                     double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
+                     uint64_t seed, uint64_t first, uint64_t count, const double* d_ext_uniforms,
+                     int slots, int perturb, void* d_out36, int64_t* d_out_idx,
+                     double* d_out_parts, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (count == 0) return 0;
+  if (N <= 0) {
+    set_error("resample: empty source list");
+    return 1;
+  }
+  if (h_geom->order < 0 || h_geom->order > KDSB200_MAX_METRICS) {
+    set_error("resample: geometry order %d out of range", h_geom->order);
+    return 1;
+  }
+  if (d_ext_uniforms && slots < 1) {
+    set_error("resample: external uniforms need slots >= 1");
+    return 1;
+  }
+  const unsigned blocks = (unsigned)((count + 255) / 256);
+  unsigned char* o36 = (unsigned char*)d_out36;
+#define KDSB_LAUNCH(R, EXT)                                                                      \
+  resample_kernel<R, EXT><<<blocks, 256, 0, st>>>((const R*)d_src8, d_cdf, d_bw, bw_scalar, N,   \
+                                                  *h_geom, pdgcode, seed, first, count,          \
+                                                  d_ext_uniforms, slots, perturb, o36,           \
+                                                  d_out_idx, d_out_parts)
+  if (src_is_f32) {
+    if (d_ext_uniforms) KDSB_LAUNCH(float, true);
+    else KDSB_LAUNCH(float, false);
+  } else {
+    if (d_ext_uniforms) KDSB_LAUNCH(double, true);
+    else KDSB_LAUNCH(double, false);
+  }
+#undef KDSB_LAUNCH
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+"""Bandwidth selection on the GPU, mirroring ``python/kdsource/kde.py``.
+
+Same public names, arguments and error behaviour as the reference module
+(``bw_silv``, ``bw_knn``, ``_kde_cv_score``, ``bw_mlcv``, ``bw_auto``,
+``optimize_bw``, ``bw_methods``); the arithmetic that the reference delegates
+to scikit-learn (``NearestNeighbors``, ``KFold``), joblib and KDEpy runs in
+the ``knn`` and ``mlcv_score`` CUDA kernels behind the C ABI.
+
+Multi-GPU: when ``torch.distributed`` is initialised with more than one rank,
+``bw_knn`` shards whole batches and ``mlcv_scores`` shards test rows over the
+ranks (sources replicated); results are combined with an all-gather /
+all-reduce and are identical on every rank.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import dist as _dist
+from .treekde import TreeKDE
+
+_LOG2E = 1.4426950408889634
+
+
+def bw_silv(dim, N_eff):
+    """Silverman's Rule (reference kde.py:18-38)."""
+    return (4 / (2 + dim)) ** (1 / (4 + dim)) * N_eff ** (-1 / (4 + dim))
+
+
+# ---------------------------------------------------------------------------
+# kNN
+# ---------------------------------------------------------------------------
+
+def array_split_bounds(N, batches):
+    """Boundaries of ``np.array_split(data, batches)`` (kde.py:91)."""
+    sizes = np.full(batches, N // batches, dtype=np.int64)
+    sizes[: N % batches] += 1
+    return np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+
+
+def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_idx=False):
+    """kk nearest neighbours (self included) of every row inside its batch.
+
+    Returns (kth, dist, idx): ``kth`` (N,) distance to the kk-th neighbour,
+    ``dist`` (N,kk) ascending, ``idx`` (N,kk) int32 indices inside the batch
+    ordered by (distance, index).  Batches are sharded over ranks.
+    """
+    L = _lib.load()
+    t = _lib.torch()
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    N, D = data.shape
+    batch_off = np.ascontiguousarray(batch_off, dtype=np.int64)
+    nb = len(batch_off) - 1
+    rank, world = _dist.rank_world()
+    b_lo, b_hi = _dist.shard_range(nb, rank, world)
+    r_lo, r_hi = int(batch_off[b_lo]), int(batch_off[b_hi])
+    kth = np.zeros(N)
+    dist = np.zeros((N, kk)) if want_dist else None
+    idx = np.zeros((N, kk), dtype=np.int32) if want_idx else None
+    n_loc = r_hi - r_lo
+    if n_loc > 0:
+        loc_off = batch_off[b_lo:b_hi + 1] - r_lo
+        d_data = _lib.to_dev(data[r_lo:r_hi])
+        d_off = _lib.to_dev(loc_off, np.int64)
+        use_f64 = precision == "float64"
+        scratch = _lib.empty(n_loc * D, t.float64 if use_f64 else t.float32)
+        d_kth = _lib.empty(n_loc, t.float64)
+        d_dist = _lib.empty(n_loc * kk, t.float64) if want_dist else None
+        d_idx = _lib.empty(n_loc * kk, t.int32) if want_idx else None
+        _lib.check(L.kdsb200_knn(
+            _lib.ptr(d_data), n_loc, D, _lib.ptr(d_off), b_hi - b_lo,
+            int(np.max(np.diff(loc_off))), kk, int(use_f64), _lib.ptr(scratch),
+            _lib.ptr(d_kth), _lib.ptr(d_dist), _lib.ptr(d_idx), _lib.stream()))
+        kth[r_lo:r_hi] = d_kth.cpu().numpy()
+        if want_dist:
+            dist[r_lo:r_hi] = d_dist.cpu().numpy().reshape(n_loc, kk)
+        if want_idx:
+            idx[r_lo:r_hi] = d_idx.cpu().numpy().reshape(n_loc, kk)
+    if world > 1:
+        kth = _dist.allreduce_sum_numpy(kth)
+        if want_dist:
+            dist = _dist.allreduce_sum_numpy(dist)
+        if want_idx:
+            idx = _dist.allreduce_sum_numpy(idx.astype(np.int64)).astype(np.int32)
+    return kth, dist, idx
+
+
+def bw_knn(data, weights=None, K_eff=100, k=None, batch_size=10000, precision="float64"):
+    """K Nearest Neighbors method (reference kde.py:41-103).
+
+    For each sample, the bandwidth is the distance to its k-th neighbour inside
+    its batch (``np.array_split`` into ``round(N / batch_size)`` batches), times
+    ``f_k ** (1/dim)``.  ``precision="float64"`` reproduces the reference's
+    distances bit for bit; ``"float32"`` is the fast mode.
+    """
+    data = np.asarray(data)
+    N, dim = data.shape
+    batches = int(max(1, np.round(N / batch_size)))
+    # The reference's branches are inverted (kde.py:70-74): with weights
+    # N_eff = N, without weights it raises on np.sum(None ** 2).
+    if weights is None:
+        raise TypeError("unsupported operand type(s) for ** or pow(): 'NoneType' and 'int'")
+    N_eff = N
+    if k is None:  # Compute k based on K_eff
+        k_float = batch_size * K_eff / N_eff
+        k = int(max(1, round(k_float)))
+        f_k = k_float / k  # Correction factor for k
+    else:  # k set by user
+        f_k = 1.0
+        K_eff = k * N_eff / batch_size
+    print("Using k = {} neighbors per batch (batch_size = {})".format(k, batch_size))
+    print("Correction factor: f_k = k_float / k = {}".format(f_k))
+    print("Effective total neighbors: K_eff = {}".format(K_eff))
+    off = array_split_bounds(N, batches)
+    kth, _, _ = knn_batched(data, k + 1, off, precision=precision)
+    return kth * (f_k) ** (1 / dim)
+
+
+# ---------------------------------------------------------------------------
+# MLCV
+# ---------------------------------------------------------------------------
+
+def kfold_bounds(N, K):
+    """Fold boundaries of sklearn ``KFold(n_splits=K)`` without shuffle
+    (kde.py:134-136): contiguous, the first ``N % K`` folds one longer."""
+    sizes = np.full(K, N // K, dtype=np.int64)
+    sizes[: N % K] += 1
+    return np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+
+
+class MLCVPlan:
+    """Device-resident state of one MLCV grid search: packed sources, the test
+    rows of this rank with their fold intervals, and the output buffers.
+
+    ``launch()`` enqueues the pair kernel(s) for the whole grid on the current
+    stream (no host work, no synchronisation); ``collect()`` downloads the
+    per-CTA partial sums and assembles the scores of the rows of this rank.
+    """
+
+    def __init__(self, data, weights, seed, grid, n_splits=10, rows=None):
+        L = _lib.load()
+        t = _lib.torch()
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        N, D = data.shape
+        self.N, self.D = N, D
+        self.grid = np.ascontiguousarray(grid, dtype=np.float64).reshape(-1)
+        K = int(min(n_splits, N))
+        if K < 2:
+            raise ValueError("n_splits must be at least 2")
+        if np.ndim(seed) == 1:
+            if len(seed) < N:
+                raise ValueError("If bw is array, must have same len as data")
+            seed_arr = np.ascontiguousarray(seed, dtype=np.float64)[:N]
+            seed_scalar = 0.0
+            hmin = float(seed_arr.min())
+        else:
+            seed_arr = None
+            seed_scalar = float(seed)
+            hmin = seed_scalar
+        if not hmin > 0:
+            raise ValueError("bandwidths must be positive")
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)[:N]
+        fb = kfold_bounds(N, K)
+        nf = np.diff(fb).astype(np.float64)
+        wsum_all = float(np.sum(w)) if w is not None else float(N)
+        wfold = np.add.reduceat(w, fb[:-1]) if w is not None else nf
+        wtrain = wsum_all - wfold
+        fold_of = np.repeat(np.arange(K), np.diff(fb))
+        if rows is None:
+            rank, world = _dist.rank_world()
+            rows = _dist.shard_range(N, rank, world)
+        r_lo, r_hi = rows
+        M = self.M = r_hi - r_lo
+        wmax = float(np.max(w)) if w is not None else 1.0
+        self.w_scale = 1.0 / wmax
+        self.lc_ref = -D * np.log2(hmin)
+        self.h2d_bytes = 0
+        if M == 0:
+            return
+        f_loc = fold_of[r_lo:r_hi]
+        wi = w[r_lo:r_hi] if w is not None else np.ones(M)
+        coefw = wi / (nf[f_loc] * K)
+        self.sum_cw = float(np.sum(coefw))
+        Mpad = self.Mpad = L.kdsb200_mlcv_mpad(M)
+
+        def padded(a, dtype):
+            out = np.zeros(Mpad, dtype=dtype)
+            out[:M] = a
+            return out
+
+        host = [(padded(fb[f_loc], np.int32), np.int32), (padded(fb[f_loc + 1], np.int32), np.int32),
+                (padded(coefw, np.float64), np.float64),
+                (padded(np.log(wtrain[f_loc]), np.float64), np.float64)]
+        self.d_lo, self.d_hi, self.d_cw, self.d_lw = [_lib.to_dev(a, dt) for a, dt in host]
+        d_data = _lib.to_dev(data)
+        d_w = _lib.to_dev(w) if w is not None else None
+        d_bw = _lib.to_dev(seed_arr) if seed_arr is not None else None
+        self.h2d_bytes = (sum(a.nbytes for a, _ in host) + data.nbytes
+                          + (w.nbytes if w is not None else 0)
+                          + (seed_arr.nbytes if seed_arr is not None else 0))
+        cen_keep, cen_p = _lib.hostvec(data.mean(axis=0))
+        self.packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
+        _lib.check(L.kdsb200_pack_sources_f32(
+            _lib.ptr(d_data), _lib.ptr(d_w), _lib.ptr(d_bw), seed_scalar, N, D, cen_p,
+            self.w_scale, self.lc_ref, 1, _lib.ptr(self.packed), _lib.stream()))
+        self.qT = _lib.empty(Mpad * D, t.float32)
+        d_rows = d_data[r_lo:r_hi]  # contiguous row slice of the (N,D) tensor
+        _lib.check(L.kdsb200_pack_queries_f32(_lib.ptr(d_rows), M, Mpad, D, cen_p,
+                                              _lib.ptr(self.qT), _lib.stream()))
+        self.nsplit = L.kdsb200_mlcv_nsplit(N, M)
+        self.nblk = Mpad // 256
+        self.chunks = []
+        for g0 in range(0, len(self.grid), 32):
+            gsub = self.grid[g0:g0 + 32]
+            gt = L.kdsb200_mlcv_gtile(len(gsub))
+            nk = np.ascontiguousarray(-_LOG2E / (2.0 * gsub ** 2), dtype=np.float32)
+            sbuf = (_lib.empty(self.nsplit * Mpad * gt, t.float64) if self.nsplit > 1 else None)
+            partial = _lib.empty(self.nblk * gt, t.float64)
+            self.chunks.append((g0, gsub, gt, nk, sbuf, partial))
+        #: kernel launches per launch() call
+        self.n_launches = len(self.chunks) * (2 if self.nsplit > 1 else 1)
+        #: kernel evaluations (exponentials that enter a score) per launch() call
+        tr = float(N) - nf[f_loc]
+        self.n_evals = float(np.sum(tr)) * len(self.grid)
+
+    def launch(self):
+        if self.M == 0:
+            return
+        L = _lib.load()
+        for g0, gsub, gt, nk, sbuf, partial in self.chunks:
+            _lib.check(L.kdsb200_mlcv_scores_f32(
+                _lib.ptr(self.packed), self.N, self.D, _lib.ptr(self.qT), self.M, self.Mpad,
+                _lib.ptr(self.d_lo), _lib.ptr(self.d_hi), _lib.ptr(self.d_cw),
+                _lib.ptr(self.d_lw), nk.ctypes.data_as(_lib.c_float_p), len(gsub),
+                self.nsplit, _lib.ptr(sbuf), _lib.ptr(partial), _lib.stream()))
+
+    def collect(self):
+        """Scores contributed by the rows of this plan (sum over ranks = score)."""
+        scores = np.zeros(len(self.grid))
+        self.d2h_bytes = 0
+        if self.M == 0:
+            return scores
+        D = self.D
+        for g0, gsub, gt, nk, sbuf, partial in self.chunks:
+            part = partial.cpu().numpy().reshape(self.nblk, gt)[:, :len(gsub)]
+            self.d2h_bytes += self.nblk * gt * 8
+            const_g = (self.lc_ref * np.log(2.0) - np.log(self.w_scale)
+                       - 0.5 * D * np.log(2 * np.pi) - D * np.log(gsub))
+            with np.errstate(invalid="ignore"):
+                scores[g0:g0 + 32] = part.sum(axis=0) + const_g * self.sum_cw
+        return scores
+
+
+def mlcv_scores(data, weights, seed, grid, n_splits=10):
+    """Cross-validation scores of ``bw_grid[g] = grid[g] * seed`` for every g.
+
+    ``score[g] == _kde_cv_score(grid[g] * seed, data, weights, n_splits)`` of
+    the reference (kde.py:106-153), computed for the whole grid in one pass
+    over the pair space.  ``seed`` is a scalar or one bandwidth per sample.
+    Test rows are sharded over ranks when torch.distributed is initialised.
+    """
+    plan = MLCVPlan(data, weights, seed, grid, n_splits=n_splits)
+    plan.launch()
+    scores = plan.collect()
+    if _dist.rank_world()[1] > 1:
+        scores = _dist.allreduce_sum_numpy(scores)
+    return scores
+
+
+def _kde_cv_score(bw, data, weights=None, n_splits=10, modelKDE=TreeKDE):
+    """Cross-validation likelihood score (reference kde.py:106-153).
+
+    ``modelKDE`` is accepted for signature compatibility; the score is always
+    evaluated with the Gaussian kernel, as in the reference (kde.py:146).
+    """
+    if np.ndim(bw) == 1:
+        if len(bw) < len(data):
+            raise ValueError("If bw is array, must have same len as data")
+        if len(bw) > len(data):
+            print("Warning: bw longer than data.")
+    return float(mlcv_scores(data, weights, bw, np.array([1.0]), n_splits=n_splits)[0])
+
+
+def _effective_n(n_rows, weights):
+    if weights is None:
+        return n_rows
+    weights = np.asarray(weights)
+    return np.sum(weights) ** 2 / np.sum(weights ** 2)
+
+
+def _maybe_plot_scores(grid, scores):
+    """Score-vs-factor plot of the reference (kde.py:214-220); skipped when
+    matplotlib is not installed."""
+    try:
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return
+    plt.plot(grid, scores)
+    plt.xlabel("Scaling factor")
+    plt.ylabel("MLCV Figure of Merit (FoM)")
+    plt.tight_layout()
+    plt.show()
+
+
+def bw_mlcv(data, weights=None, n_splits=10, seed=None, grid=None, show=True):
+    """Maximum Likelihood Cross-Validation bandwidth (reference kde.py:156-226).
+
+    ``bw_grid[g] = grid[g] * seed`` (seed scalar or per-sample, Silverman by
+    default; default grid ``logspace(-0.1, 0.1, 10)``); returns the grid entry
+    with the best K-fold score and raises if the best one is the first or last.
+    """
+    data = np.asarray(data)
+    if seed is None:
+        seed = bw_silv(data.shape[1], _effective_n(len(data), weights))
+    if grid is None:
+        print("No grid specified. Using np.logspace(-0.1, 0.1, 10).")
+        print("If fitting fails, change the grid.")
+        grid = np.logspace(-0.1, 0.1, 10)
+    factors = np.asarray(grid, dtype=np.float64).reshape(-1)
+    scores = mlcv_scores(data, weights, seed, factors, n_splits=min(n_splits, len(data)))
+    best = int(np.argmax(scores))
+    if show:
+        _maybe_plot_scores(factors, scores)
+    if best == 0 or best == len(factors) - 1:
+        raise Exception(
+            "Maximum not found in bw range selected. Move grid and try again."
+        )
+    return factors[best] * seed
+
+
+def bw_auto(data, weights, grid=None, Nmlcv=1e4, Nbatch=1e4, Nknn=10, show=True,
+            n_splits=10):
+    """kNN seed + MLCV rescale (reference kde.py:229-297).
+
+    1. adaptive ``bw_knn`` on all samples (``Nbatch=-1``: one batch);
+    2. ``bw_mlcv`` on the first ``Nmlcv`` samples seeded with (1) (``-1``: all);
+    3. the MLCV factor is applied to the whole kNN bandwidth and corrected by
+       the Silverman ratio between N and Nmlcv samples.
+    """
+    data = np.asarray(data)
+    n_all, dim = data.shape
+    print("Fitting first with kNN method:")
+    if Nbatch == -1:
+        print("No batch size for kNN selected. Using all the particles list.")
+        Nbatch = n_all
+    knn_bw = bw_knn(data, weights=weights, k=Nknn, batch_size=Nbatch)
+    print("")
+    print("Fitting now with MLCV using the previous fitting as seed:")
+    if Nmlcv == -1:
+        print("No size for MLCV selected. Using all the particles list.")
+        Nmlcv = n_all
+    n_cv = int(Nmlcv)
+    print("If fitting takes too long, consider reducing Nmlcv.")
+    cv_bw = bw_mlcv(data[:n_cv], weights=weights, seed=knn_bw[:n_cv], grid=grid,
+                    show=show, n_splits=n_splits)
+    print("")
+    print("Extending the MLCV optimization to full kNN bandwidth:")
+    factor = cv_bw[0] / knn_bw[0]
+    factor *= bw_silv(dim, len(knn_bw)) / bw_silv(dim, len(cv_bw))
+    print("Done.")
+    return knn_bw * factor
+
+
+def optimize_bw(bw_method, vecs, ws=None, weightfun=None, maskfun=None, **kwargs):
+    """Dispatch to a bandwidth method after the reference's sample filtering
+    (kde.py:300-354): drop non-positive weights, apply ``weightfun`` to the
+    weights and ``maskfun`` to the samples."""
+    if bw_method not in bw_methods:
+        raise Exception("Invalid bw_method. Available: {}".format(list(bw_methods)))
+    vecs = np.array(vecs)
+    keep = np.ones(len(vecs), dtype=bool)
+    if ws is not None:
+        ws = np.array(ws)
+        keep = ws > 0
+    if weightfun is not None:
+        ws = ws * weightfun(vecs)
+    if maskfun is not None:
+        keep = keep & maskfun(vecs)
+    vecs = vecs[keep]
+    ws = ws[keep]  # like the reference, ws=None is not supported here
+    if bw_method == "silv":
+        return bw_silv(vecs.shape[1], _effective_n(len(vecs), ws))
+    return bw_methods[bw_method](vecs, weights=ws, **kwargs)
+
+
+bw_methods = {"auto": bw_auto, "silv": bw_silv, "knn": bw_knn, "mlcv": bw_mlcv}

@@ -1,0 +1,104 @@
+"""``resample_to_mcpl``: draw new particles from an XML source file on the GPU.
+
+Same call as the reference (``python/kdsource/resample.py:2-49``); the C loop
+behind it (``kdsource_resample_to_mcpl``, clib/src/resamplemcpl.c:17-47) is
+replaced by the batched device sampler.  The XML file is read the way
+``KDS_open`` reads it (clib/src/kdsource.c:79-280): J, optional kernel, PList,
+Geom with its metrics, scaling, BW (scalar, or a raw float32 file with one
+value per valid particle).
+"""
+
+import gzip
+import os
+import pathlib
+from xml.etree.ElementTree import parse
+
+import numpy as np
+
+from . import mcpl
+from .geom import Geometry
+from .plist import PList
+from .sampler import DEFAULT_SLOTS, DeviceSampler, make_geom_struct
+from .utils import pt2pdg
+from .writemcpl import _check_new_mcpl_filename
+
+
+def open_source(kds_sourcefile, precision="float32"):
+    """Parse an XML source file and upload its particle list: returns a
+    :class:`DeviceSampler` plus a dict of the parsed fields."""
+    path = pathlib.Path(kds_sourcefile)
+    root = parse(path).getroot()
+    if root.tag != "KDSource":
+        raise RuntimeError("Invalid format in source XML file {}".format(path))
+    kel = root.find("kernel")
+    kernel = (kel.text or "g").strip()[0] if kel is not None else "g"
+    pltree = root.find("PList")
+    # relative MCPL names are resolved against the XML file's directory first
+    name = pltree[1].text
+    if not os.path.isabs(name) and not os.path.isfile(name):
+        cand = path.parent / name
+        if cand.is_file():
+            pltree[1].text = str(cand)
+    cwd = os.getcwd()
+    plist = PList.load(pltree)
+    geom = Geometry.load(root.find("Geom"))
+    scaling = np.array(root.find("scaling").text.split(), dtype="float64")
+    bwel = root.find("BW")
+    variable = bool(int(bwel.attrib["variable"]))
+    parts, ws = plist.get(-1)
+    if len(parts) == 0:
+        raise RuntimeError("Empty particle list")
+    if variable:
+        bw = np.fromfile(bwel.text, dtype="float32")
+        if len(bw) != len(parts):
+            print("Warning: Particle list and bandwidths file have different size.")
+        if len(bw) < len(parts):
+            bw = np.resize(bw, len(parts))  # Geom_next rewinds the file, geom.c:160-177
+    else:
+        bw = float(bwel.text)
+    gs = make_geom_struct(geom, scaling, kernel)
+    sampler = DeviceSampler(parts, ws, bw, gs, pdgcode=pt2pdg(plist.pt), precision=precision)
+    info = dict(J=float(root.find("J").text), kernel=kernel, plist=plist, geom=geom,
+                scaling=scaling, bw=bw, N=len(parts), cwd=cwd)
+    return sampler, info
+
+
+def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=False,
+                     batch=1 << 22, compresslevel=1, precision="float32"):
+    """Resample `nout` particles from an XML source file into a new MCPL file
+    (always ``*.mcpl.gz``; refuses to overwrite unless `force`).
+
+    rng: an int seed (or None: seeded from os.urandom) keys the counter-based
+    Philox generator, so output particle i depends only on (seed, i); a callable
+    returning uniforms in [0,1) is honoured too (it is consumed on the host,
+    32 numbers per particle, and fed to the same kernel).
+    """
+    ksrc = pathlib.Path(kds_sourcefile)
+    nout = int(nout)
+    if not ksrc.is_file():
+        raise RuntimeError(f"Missing file: {kds_sourcefile}")
+    dst = _check_new_mcpl_filename(destination_mcpl, force=force)
+    if nout <= 0 or nout > 1e16:
+        raise RuntimeError("Invalid (or unreasonable) number of"
+                           f" particles requested: {nout}")
+    if rng is None:
+        rng = int.from_bytes(os.urandom(8), byteorder="big")
+        print("Warning: No explicit seed provided"
+              f" (choosing arbitrarily seed={rng})")
+    sampler, _ = open_source(ksrc.absolute(), precision=precision)
+    header = mcpl.build_header(nout, "KDSource resample", singleprec=True)
+    print("Resampling...")
+    with gzip.open(dst, "wb", compresslevel=compresslevel) as fh:
+        fh.write(header)
+        done = 0
+        while done < nout:
+            n = min(batch, nout - done)
+            if isinstance(rng, int):
+                rec = sampler.sample(n, seed=rng, first=done)["records"]
+            else:
+                ext = np.fromiter((rng() for _ in range(n * DEFAULT_SLOTS)), dtype=np.float64,
+                                  count=n * DEFAULT_SLOTS).reshape(n, DEFAULT_SLOTS)
+                rec = sampler.sample(n, first=done, ext_uniforms=ext)["records"]
+            fh.write(rec.tobytes())
+            done += n
+    print("Successfully sampled {} particles.".format(nout))

@@ -828,14 +828,10 @@ double orc_rand_type_scripted(char kernel, const double *uniforms, int nuni,
 
 /* fixed-point weights: c_i = floor(w_i * 2^62 / sum(w)) (at least 1 for any
  * w_i > 0), cdf = inclusive prefix sum in uint64 (exactly associative, so a
- * parallel scan on the device reproduces it bit for bit). */
-void orc_weights_cdf(const double *w, int64_t N, uint64_t *cdf) {
-  long double sum = 0;
-  double sumd = 0.0;
-  for (int64_t i = 0; i < N; i++)
-    sumd += w[i];
-  (void)sum;
-  const double scale = 4611686018427387904.0 / sumd; /* 2^62 / sum */
+ * parallel scan on the device reproduces it bit for bit).  sum_w is supplied by
+ * the caller (numpy's np.sum of the weights on both sides). */
+void orc_weights_cdf(const double *w, int64_t N, double sum_w, uint64_t *cdf) {
+  const double scale = 4611686018427387904.0 / sum_w; /* 2^62 / sum */
   uint64_t acc = 0;
   for (int64_t i = 0; i < N; i++) {
     uint64_t c = (uint64_t)(w[i] * scale);

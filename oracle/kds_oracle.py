@@ -363,7 +363,8 @@ def philox4x32_10(ctr, key):
 def weights_cdf(w):
     w = np.ascontiguousarray(w, dtype=np.float64)
     cdf = np.empty(len(w), dtype=np.uint64)
-    lib().orc_weights_cdf(_p(w, c_double_p), ctypes.c_int64(len(w)), _p(cdf, c_u64_p))
+    lib().orc_weights_cdf(_p(w, c_double_p), ctypes.c_int64(len(w)),
+                          ctypes.c_double(float(np.sum(w))), _p(cdf, c_u64_p))
     return cdf
 
 

@@ -1,0 +1,228 @@
+"""The CPU oracle against the reference's own outputs (golden vectors made by
+tests/golden/make_golden.py from the unmodified reference Python) and, when
+oracle/_ref is present, against the reference's own compiled C functions."""
+
+import numpy as np
+import pytest
+
+
+def test_bw_silv(oracle, golden_kde):
+    assert oracle.bw_silv(6, 99011.96) == float(golden_kde["bw_silv_6_99011.96"])
+    # Verification.ipynb cell 12: bw*scaling[0] = 0.2204 with importance 3 on std(u)
+    assert abs(oracle.bw_silv(6, 99011.96) - 0.2953) < 1e-4
+    assert oracle.lib().orc_bw_silv(6, 99011.96) == pytest.approx(oracle.bw_silv(6, 99011.96),
+                                                                  rel=1e-15)
+
+
+@pytest.mark.parametrize("key,kw", [
+    ("knn_k10_b600", dict(k=10, batch_size=600)),
+    ("knn_keff100_b800", dict(K_eff=100, batch_size=800)),
+    ("knn_k5_onebatch", dict(k=5, batch_size=2400)),
+])
+def test_bw_knn_bit_exact_vs_reference(oracle, golden_kde, key, kw):
+    got = oracle.bw_knn(golden_kde["data"], weights=golden_kde["weights"], **kw)
+    assert np.array_equal(got, golden_kde[key])
+
+
+def test_knn_matches_sklearn(oracle, golden_kde):
+    from sklearn.neighbors import NearestNeighbors
+
+    data = golden_kde["data"][:900]
+    ds, idx = NearestNeighbors(n_neighbors=8).fit(data).kneighbors(data)
+    d2, i2 = oracle.knn(data, 8)
+    assert np.array_equal(ds, d2)
+    assert np.array_equal(idx, i2)
+
+
+def test_kfold_and_array_split(oracle):
+    from sklearn.model_selection import KFold
+
+    for N, K in [(23, 5), (700, 10), (150, 150), (11, 3)]:
+        fb = oracle.kfold_bounds(N, K)
+        for f, (_, test) in enumerate(KFold(n_splits=K).split(np.zeros((N, 1)))):
+            assert test[0] == fb[f] and test[-1] + 1 == fb[f + 1]
+    for N, B in [(23, 4), (2400, 3), (10, 1)]:
+        off = oracle.array_split_bounds(N, B)
+        sizes = [len(c) for c in np.array_split(np.arange(N), B)]
+        assert list(np.diff(off)) == sizes
+
+
+def test_cv_scores_vs_reference(oracle, golden_kde):
+    g = golden_kde
+    n = int(g["cv_n"])
+    d, w = g["data"][:n], g["weights"][:n]
+    bw = float(g["cv_scalar_bw"])
+    assert oracle.cv_score(bw, d, w, 10) == pytest.approx(float(g["cv_score_scalar"]), rel=1e-13)
+    assert oracle.cv_score(bw, d, w, 7) == pytest.approx(float(g["cv_score_scalar_k7"]), rel=1e-13)
+    assert oracle.cv_score(bw, d, None, 10) == pytest.approx(float(g["cv_score_unweighted"]),
+                                                             rel=1e-13)
+    bwa = g["knn_k10_b600"][:n]
+    assert oracle.cv_score(bwa, d, w, 10) == pytest.approx(float(g["cv_score_array"]), rel=1e-13)
+    assert oracle.cv_score(bw, d[:150], w[:150], 150) == pytest.approx(
+        float(g["cv_score_loo"]), rel=1e-13)
+    # C restatement, whole grid at once
+    sc = oracle.mlcv_scores_c(d, w, bw, g["mlcv_grid"], 10)
+    assert np.allclose(sc, g["mlcv_scores_scalar"], rtol=1e-12, atol=0)
+    sa = oracle.mlcv_scores_c(d, w, bwa, g["mlcv_grid_array"], 10)
+    assert np.allclose(sa, g["mlcv_scores_array"], rtol=1e-12, atol=0)
+    su = oracle.mlcv_scores_c(d, None, bw, np.array([1.0]), 10)
+    assert su[0] == pytest.approx(float(g["cv_score_unweighted"]), rel=1e-12)
+
+
+def test_bw_mlcv_and_auto_vs_reference(oracle, golden_kde):
+    g = golden_kde
+    n = int(g["cv_n"])
+    d, w = g["data"][:n], g["weights"][:n]
+    bw, _ = oracle.bw_mlcv(d, w, 10, None, g["mlcv_grid"])
+    assert bw == pytest.approx(float(g["mlcv_scalar"]), rel=1e-14)
+    bwa, _ = oracle.bw_mlcv(d, w, 10, g["knn_k10_b600"][:n], g["mlcv_grid_array"])
+    assert np.allclose(bwa, g["mlcv_array"], rtol=1e-14, atol=0)
+    with pytest.raises(Exception, match="Maximum not found"):
+        oracle.bw_mlcv(d, w, grid=np.logspace(0.5, 0.8, 4))
+    assert bool(g["mlcv_edge_raises"])
+    auto = oracle.bw_auto(g["data"], g["weights"], grid=g["mlcv_grid_array"], Nmlcv=700,
+                          Nbatch=600, Nknn=10)
+    assert np.allclose(auto, g["auto"], rtol=1e-13, atol=0)
+
+
+def test_kde_sum_c_vs_numpy_and_normalisation(oracle):
+    rng = np.random.default_rng(3)
+    data = rng.normal(size=(500, 3))
+    w = rng.uniform(0.5, 1.5, 500)
+    bw = rng.uniform(0.2, 0.5, 500)
+    pts = rng.normal(size=(64, 3))
+    a = oracle.kde_sum(data, w, bw, pts)
+    b = oracle.kde_sum_c(data, w, bw, pts)
+    assert np.allclose(a, b, rtol=1e-13)
+    ac = oracle.kde_sum(data, w, 0.3, pts, cutoff=1.0)
+    bc = oracle.kde_sum_c(data, w, 0.3, pts, cutoff=1.0)
+    assert np.allclose(ac, bc, rtol=1e-13)
+    assert np.all(ac <= oracle.kde_sum(data, w, 0.3, pts) + 1e-18)
+    # analytic check: a single unit-weight source integrates to 1 (1-D grid)
+    x = np.linspace(-8, 8, 4001).reshape(-1, 1)
+    dens = oracle.kde_sum(np.zeros((1, 1)), None, 0.7, x)
+    assert np.trapezoid(dens, x[:, 0]) == pytest.approx(1.0, rel=1e-9)
+    assert dens[2000] == pytest.approx(1 / (0.7 * np.sqrt(2 * np.pi)), rel=1e-14)
+
+
+def test_treekde_radius_matches_survey_probe(oracle):
+    # SURVEY appendix D probe: bw=0.295 -> r = 1.1214 = 3.80 bw
+    assert oracle.treekde_radius(0.295) == pytest.approx(1.1214, abs=2e-3)
+
+
+def test_philox_known_answers(oracle):
+    # Random123 known-answer vectors for Philox4x32-10
+    assert oracle.philox4x32_10([0, 0, 0, 0], [0, 0]) == [
+        0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [
+        0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
+                                [0xa4093822, 0x299f31d0]) == [
+        0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+_CASES = {
+    "Energy": ([0.3], []), "Lethargy": ([0.7], [10.0]), "Wavelength": ([0.2], []),
+    "Vol": ([1.0, 2.0, 0.5], [-5, 5, -3, 3, -1, 1]),
+    "SurfXY": ([3.0, 2.0], [-5, 5, -np.inf, np.inf, 0]),
+    "SurfR": ([1.0, 20.0], [0, 8, -np.pi, np.pi, 0]),
+    "SurfR2": ([5.0, 20.0], [0, 8, -np.pi, np.pi, 0]),
+    "SurfCircle": ([1.0, 1.0], [0, 8, -np.pi, np.pi, 0]),
+    "Guide": ([5.0, 1.0, 0.1, 10.0], [3.0, 5.0, 100.0, 2000.0]),
+    "Isotrop": ([0.2, 0.2, 0.2], [0, 0, 1]), "Polar": ([5.0, 10.0], []),
+    "PolarMu": ([0.05, 20.0], []), "Time": ([0.5], []), "Decade": ([0.3], []),
+}
+
+
+def _random_part(rng, name):
+    d = rng.normal(size=3)
+    d /= np.linalg.norm(d)
+    part = np.array([rng.uniform(0.01, 9), rng.uniform(-4, 4), rng.uniform(-2.5, 2.5),
+                     rng.uniform(-0.9, 0.9), *d, rng.uniform(0.1, 5)])
+    if name == "Guide":
+        part[1:4] = [1.5, rng.uniform(-2, 2), rng.uniform(1, 90)]
+    return part
+
+
+@pytest.mark.parametrize("name", sorted(_CASES))
+def test_perturbation_maps_bit_equal_to_reference_c(oracle, name):
+    """oracle restatement == the reference's own compiled X_perturb, same uniforms."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(hash(name) % 1000)
+    sc, pa = _CASES[name]
+    for kern in "geb":
+        for _ in range(100):
+            part = _random_part(rng, name)
+            u = rng.uniform(size=64)
+            a, ua = oracle.metric_perturb_scripted(name, sc, pa, kern, 0.6, part, u)
+            b, ub = oracle.metric_perturb_scripted(name, sc, pa, kern, 0.6, part, u, use_ref=True)
+            assert ua == ub
+            assert np.array_equal(a, b)
+
+
+def test_deviates_and_rotation_bit_equal_to_reference_c(oracle):
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    rng = np.random.default_rng(9)
+    for kern in "geb":
+        for _ in range(200):
+            u = rng.uniform(size=32)
+            assert oracle.rand_type_scripted(kern, u) == oracle.rand_type_scripted(
+                kern, u, use_ref=True)
+    for _ in range(50):
+        v, rv = rng.normal(size=3), rng.normal(size=3)
+        for inv in (0, 1):
+            assert np.array_equal(oracle.rotv(v, rv, inv), oracle.rotv(v, rv, inv, use_ref=True))
+    import ctypes
+    assert oracle.ref_lib().ref_pt2pdg(ctypes.c_char(b"n")) == 2112
+
+
+def test_resample_oracle_contract(oracle):
+    """Index pick: fixed-point CDF + upper_bound; weights respected; rank-split
+    invariance of the per-particle Philox streams."""
+    parts, w = oracle.synthetic_particles(5000, seed=21, wseed=22)
+    w[:100] *= 5
+    geom = oracle.make_geom([("Lethargy", [0.9], [10.0]), ("SurfXY", [9.0, 9.5], [-np.inf, np.inf, -np.inf, np.inf, 0.0]),
+                             ("Isotrop", [0.3] * 3, [0, 0, 1])])
+    r = oracle.resample(parts, w, 0.3, geom, 40000, seed=5)
+    cdf = r["cdf"]
+    assert cdf.dtype == np.uint64 and np.all(np.diff(cdf.astype(np.float64)) > 0)
+    assert abs(float(cdf[-1]) / 2 ** 62 - 1) < 1e-9
+    counts = np.bincount(r["idx"], minlength=len(w))
+    heavy = counts[:100].sum() / 40000
+    assert heavy == pytest.approx(w[:100].sum() / w.sum(), rel=0.05)
+    # split invariance
+    a = oracle.resample(parts, w, 0.3, geom, 1000, seed=5, first=0)
+    b = oracle.resample(parts, w, 0.3, geom, 600, seed=5, first=400)
+    assert np.array_equal(a["idx"][400:], b["idx"])
+    assert np.array_equal(a["parts"][400:], b["parts"])
+    assert np.array_equal(a["rec"][400:], b["rec"])
+    # z untouched by SurfXY, time untouched, unit directions
+    assert np.all(a["parts"][:, 3] == 0) and np.all(a["parts"][:, 7] == 0)
+    assert np.allclose(np.linalg.norm(a["parts"][:, 4:7], axis=1), 1, atol=1e-12)
+    # external uniforms: pick = floor(u * total)
+    ext = np.random.default_rng(1).uniform(size=(50, 32))
+    e = oracle.resample(parts, w, 0.3, geom, 50, ext_uniforms=ext)
+    tgt = (ext[:, 0] * float(cdf[-1])).astype(np.uint64)
+    assert np.array_equal(e["idx"], np.searchsorted(cdf, tgt, side="right"))
+
+
+def test_resample_statistics_vs_reference_sampler(oracle):
+    """KS agreement of the oracle's contract with the reference's own sequential
+    sampler (KDS_rand_sample2 compiled in place)."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    from scipy.stats import ks_2samp
+
+    parts, w = oracle.synthetic_particles(20000, seed=31, wseed=32)
+    metrics = [("Lethargy", [0.9], [10.0]),
+               ("SurfXY", [9.0, 9.5], [-np.inf, np.inf, -np.inf, np.inf, 0.0]),
+               ("Isotrop", [0.3] * 3, [0, 0, 1])]
+    ref, refw, _ = oracle.ref_sampler(parts, w, 2112, metrics, "g", 0.3, 60000, seed=77)
+    assert np.all(refw == 1.0)
+    got = oracle.resample(parts, w, 0.3, oracle.make_geom(metrics), 60000, seed=78)["parts"]
+    for col in (0, 1, 2, 4, 5, 6):
+        a = np.log(ref[:, col]) if col == 0 else ref[:, col]
+        b = np.log(got[:, col]) if col == 0 else got[:, col]
+        assert ks_2samp(a, b).pvalue > 1e-3, col
