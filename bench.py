@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Benchmark of the KDSource kernel-density hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...   (CPU reference arm)
+
+Headline workload (BASELINE.json configs[1]): MLCV bandwidth optimisation on a
+1e6-particle 6-D (E,x,y,u,v,w) list, 32-point bandwidth grid, 10 folds.  One
+"step" is one full grid search = 32 * sum_f n_f (N - n_f) = 2.88e13 Gaussian
+kernel evaluations.  `value` = kernel evaluations / s over all ranks with the
+inputs resident in HBM; `e2e` is the same search through the public API
+(`kdsource_b200.kde.mlcv_scores`) from host numpy arrays, host<->device copies
+included.  With N > 1 ranks the test rows are sharded (strong scaling: the
+configuration's list size is fixed) and the G partial scores are all-reduced.
+
+Secondary numbers for the other sub-paths (evaluate, kNN, resample) ride in
+the `sub` object of the same JSON line, each with its own roofline.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "kde_kernel_pair_evals_per_s"
+UNIT = "evals/s"
+N_MLCV = 1_000_000
+G_MLCV = 32
+K_MLCV = 10
+D_MLCV = 6
+CPU_SAMPLE_N = 24_000  # bounded CPU sample of the same workload
+
+
+def synthetic_scaled(N, seed=12345, wseed=777):
+    """Synthetic correlated neutron list in scaled KDE variables."""
+    from kdsource_b200 import geom as kgeom
+
+    rng = np.random.default_rng(seed)
+    n1 = N // 2
+    u = np.concatenate((rng.normal(5, 1, n1), rng.normal(9, 1, N - n1)))
+    x = np.concatenate((rng.normal(10, 10, n1), rng.normal(-10, 10, N - n1)))
+    y = rng.normal(0, 10, N)
+    mu = np.sqrt(rng.uniform(0, 1, N))
+    phi = rng.uniform(-np.pi, np.pi, N)
+    dxy = np.sqrt(1 - mu ** 2)
+    parts = np.stack((10 * np.exp(-u), x, y, np.zeros(N), dxy * np.cos(phi), dxy * np.sin(phi),
+                      mu, np.zeros(N)), axis=1)
+    parts = parts[rng.permutation(N)]
+    w = np.maximum(np.random.default_rng(wseed).normal(1, 0.1, N), 1e-99)
+    g = kgeom.Geometry([kgeom.Lethargy(10), kgeom.SurfXY(), kgeom.Isotrop(keep_zdir=True)])
+    vecs = g.transform(parts.copy())
+    scaling = g.std(vecs=vecs, weights=w)
+    return parts, w, g, scaling, vecs / scaling
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)),
+                "power_w_max": float(np.max(pw)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+def cpu_mlcv_baseline(data, w, bw, grid, nthreads=0):
+    """Oracle port (C + OpenMP, all host threads) on a bounded sample."""
+    from oracle import kds_oracle as O
+
+    n = min(CPU_SAMPLE_N, len(data))
+    fb = O.kfold_bounds(n, K_MLCV)
+    nf = np.diff(fb)
+    evals = float(np.sum(nf * (n - nf))) * len(grid)
+    t0 = time.perf_counter()
+    O.mlcv_scores_c(data[:n], w[:n], bw, grid, K_MLCV, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return evals / dt, dt, n
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU implementation of the path on the host cores.
+    The reference's MLCV is Python + KDEpy + joblib, none of which can run on the
+    GPU box (KDEpy is not installable; /root/reference does not travel), so this
+    arm times the oracle port of the same arithmetic (C, OpenMP on all cores)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from kdsource_b200 import kde
+
+    cores = os.cpu_count() or 1
+    _, w, _, _, data = synthetic_scaled(CPU_SAMPLE_N)
+    bw = kde.bw_silv(D_MLCV, np.sum(w) ** 2 / np.sum(w ** 2))
+    grid = np.logspace(-0.3, 0.3, G_MLCV)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, n = cpu_mlcv_baseline(data, w, bw, grid)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    sample = "first {} particles of the 1e6 list, G={}, K={}".format(CPU_SAMPLE_N, G_MLCV, K_MLCV)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "mlcv_1e6x6d_g32_k10", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def time_events(t, fn, reps):
+    """Per-call CUDA-event times (ms) of fn() on the current stream."""
+    out = []
+    for _ in range(reps):
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return out
+
+
+def sub_benchmarks(t, peaks, quick):
+    """Secondary sub-paths on one GPU: evaluate, kNN, resample."""
+    import ctypes
+
+    from kdsource_b200 import _lib, kde
+    from kdsource_b200.sampler import DeviceSampler, make_geom_struct
+    from kdsource_b200.treekde import TreeKDE
+
+    L = _lib.load()
+    sub = {}
+    flush = t.empty(256 << 20, dtype=t.uint8, device="cuda")
+    # --- evaluate: N=1e5 sources (config 1), M=1e6 queries -> 1e11 pairs per launch
+    N, M = 100_000, (200_000 if quick else 1_000_000)
+    parts, w, g, scaling, data = synthetic_scaled(N)
+    _, _, _, _, q = synthetic_scaled(M, seed=54321, wseed=1)
+    bw = kde.bw_silv(D_MLCV, np.sum(w) ** 2 / np.sum(w ** 2))
+    k = TreeKDE(bw=bw).fit(data, w)
+    dev = k._device_state()
+    d_q = _lib.to_dev(q)
+
+    def ev():
+        return k.evaluate_device(d_q, M, dev)
+
+    for _ in range(3):
+        ev()
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        ts += time_events(t, ev, 1)
+    ms = float(np.median(ts))
+    pairs = float(N) * M
+    sub["evaluate"] = {
+        "workload": "N=1e5 sources x M={:g} queries, d=6, Silverman bw".format(M),
+        "pairs_per_s": pairs / (ms * 1e-3), "ms": ms,
+        "roofline": {"bound": "fp32", "achieved": pairs * 13 / (ms * 1e-3) / 1e9,
+                     "peak": peaks["ffma2"] / 1e9, "unit": "Glane-op/s",
+                     "frac": pairs * 13 / (ms * 1e-3) / peaks["ffma2"],
+                     "per_unit": "13 FP32 lane-ops + 1 MUFU per pair (d=6)", "traffic": None}}
+    # --- kNN: k=10, batches of 1e4 (reference default), fp64 exact mode
+    Nk = 200_000 if quick else 1_000_000
+    _, wk, _, _, dk = synthetic_scaled(Nk, seed=99)
+    off = kde.array_split_bounds(Nk, int(round(Nk / 10000)))
+    d_data = _lib.to_dev(dk)
+    d_off = _lib.to_dev(off, np.int64)
+    res = {}
+    for prec, use64 in (("f64", 1), ("f32", 0)):
+        scratch = _lib.empty(Nk * 6, t.float64 if use64 else t.float32)
+        d_kth = _lib.empty(Nk, t.float64)
+
+        def kn():
+            _lib.check(L.kdsb200_knn(_lib.ptr(d_data), Nk, 6, _lib.ptr(d_off), len(off) - 1,
+                                     int(np.max(np.diff(off))), 11, use64, _lib.ptr(scratch),
+                                     _lib.ptr(d_kth), None, None, _lib.stream()))
+
+        for _ in range(2):
+            kn()
+        ms = float(np.median(time_events(t, kn, 3)))
+        pk = float(np.sum(np.diff(off).astype(np.float64) ** 2))
+        res[prec] = {"pairs_per_s": pk / (ms * 1e-3), "ms": ms}
+    sub["knn"] = {"workload": "N={:g}, k=10, batch_size=1e4, d=6".format(Nk), **res}
+    # --- resample: N=1e7 adaptive-bw sources (config 4), 1e8 particles per step
+    Ns = 1_000_000 if quick else 10_000_000
+    nout = 10_000_000 if quick else 100_000_000
+    ps, ws_, gs_, sc_, _ = synthetic_scaled(Ns, seed=7)
+    bws = np.random.default_rng(3).uniform(0.2, 0.5, Ns).astype(np.float32)
+    smp = DeviceSampler(ps, ws_, bws, make_geom_struct(gs_, sc_, "g"))
+    out = _lib.empty(nout * 36, t.uint8)
+
+    def rs():
+        smp.sample_device(nout, seed=1, first=0, out=out)
+
+    for _ in range(2):
+        rs()
+    ms = float(np.median(time_events(t, rs, 3)))
+    bytes_alg = 76.0 * nout
+    sub["resample"] = {
+        "workload": "N={:g} sources, adaptive bw, {:g} particles -> MCPL-3 records".format(Ns, nout),
+        "particles_per_s": nout / (ms * 1e-3), "ms": ms,
+        "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": bytes_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "per_unit": "76 B per particle (40 read + 36 written)", "traffic": None}}
+    return sub
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as td
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from kdsource_b200 import _lib, dist, kde
+    from tools.calib import calibrate
+
+    n_mlcv = args.n or N_MLCV
+    parts, w, g, scaling, data = synthetic_scaled(n_mlcv)
+    bw = kde.bw_silv(D_MLCV, np.sum(w) ** 2 / np.sum(w ** 2))
+    grid = np.logspace(-0.3, 0.3, G_MLCV)
+    t = torch
+    cal = calibrate()
+    hbm, hbm_src = measured_peaks()
+    peaks = {"mufu": cal["mufu_ex2_lane_ops_per_s"], "ffma2": cal["ffma2_lane_ops_per_s"],
+             "ffma": cal["ffma_lane_ops_per_s"], "hbm_gbs": hbm}
+
+    plan = kde.MLCVPlan(data, w, bw, grid, n_splits=K_MLCV)
+    flush = t.empty(256 << 20, dtype=t.uint8, device="cuda")
+    for _ in range(args.warmup):
+        plan.launch()
+    t.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    dist.barrier()
+    t.cuda.synchronize()
+    step_ms = []
+    for _ in range(args.steps):
+        flush.zero_()  # L2 flush between timed steps (untimed)
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.launch()
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    dist.barrier()
+    t.cuda.synchronize()
+    clk = clocks.stop() if rank == 0 else None
+    tot_ms = float(np.sum(step_ms))
+    if world > 1:
+        tt = t.tensor([tot_ms], device="cuda", dtype=t.float64)
+        td.all_reduce(tt, op=td.ReduceOp.MAX)
+        tot_ms = float(tt.item())
+    # whole-job evaluations: all test rows x train sources x grid
+    fb = kde.kfold_bounds(n_mlcv, K_MLCV)
+    nf = np.diff(fb).astype(np.float64)
+    evals_step = float(np.sum(nf * (n_mlcv - nf))) * G_MLCV
+    value = evals_step * args.steps / (tot_ms * 1e-3)
+    scores = plan.collect()
+    if world > 1:
+        scores = dist.allreduce_sum_numpy(scores)
+
+    # end to end through the public API: host arrays in, scores out
+    e2e_t = []
+    for i in range(max(1, min(args.steps, 2))):
+        dist.barrier()
+        t.cuda.synchronize()
+        t0 = time.perf_counter()
+        sc2 = kde.mlcv_scores(data, w, bw, grid, n_splits=K_MLCV)
+        t.cuda.synchronize()
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_t))
+    if world > 1:
+        tt = t.tensor([e2e_s], device="cuda", dtype=t.float64)
+        td.all_reduce(tt, op=td.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    assert np.allclose(sc2, scores, rtol=1e-9, equal_nan=True)
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+    # roofline of the dominant kernel (mlcv_pairs_kernel): 1 MUFU.EX2 per evaluation
+    local_evals = plan.n_evals  # rows of rank 0
+    k_ms = float(np.mean(step_ms))
+    # the kernel computes every (row, source, g) slot incl. the masked fold: N, not N - n_f
+    slots = float(plan.M) * plan.N * G_MLCV
+    achieved = slots / (k_ms * 1e-3)
+    sub = {}
+    cpu = None
+    if world == 1:
+        if not args.no_sub:
+            sub = sub_benchmarks(t, peaks, args.quick)
+        v, dt, n = cpu_mlcv_baseline(data, w, bw, grid)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "first {} particles, G={}, K={} ({:.1f} s)".format(n, G_MLCV, K_MLCV, dt)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "mlcv_1e6x6d_g32_k10" if n_mlcv == N_MLCV else
+                   "mlcv_{}x6d_g32_k10".format(n_mlcv),
+                   "N": n_mlcv, "d": D_MLCV, "G": G_MLCV, "n_splits": K_MLCV,
+                   "l2": "flushed between timed steps (256 MiB write, untimed)",
+                   "sharding": "test rows over ranks, sources replicated, allreduce of G scores"},
+        "clocks": clk,
+        "e2e": {"value": evals_step / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": int(plan.h2d_bytes), "d2h_bytes_per_step":
+                int(getattr(plan, "d2h_bytes", 0)), "s_per_step": e2e_s},
+        "gpu_launches": int(plan.n_launches * args.steps),
+        "roofline": {"bound": "sfu", "achieved": achieved / 1e9, "peak": peaks["mufu"] / 1e9,
+                     "unit": "Gop/s", "frac": achieved / peaks["mufu"], "traffic": None,
+                     "kernel": "mlcv_pairs_kernel<6,32>",
+                     "per_unit": "1 MUFU.EX2 + 2 FP32 lane-ops per (row, source, g) slot",
+                     "peak_source": "calibrated live: dependent-free ex2.approx loop, "
+                                    "{} SMs".format(cal["sm"]),
+                     "useful_frac": local_evals / slots},
+        "calibration": cal,
+        "hbm_peak_source": hbm_src,
+        "scores_argmax": int(np.nanargmax(scores)),
+        "cpu_baseline": cpu,
+        "sub": sub,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="override the MLCV list size (debug)")
+    ap.add_argument("--quick", action="store_true", help="smaller secondary benchmarks")
+    ap.add_argument("--no-sub", action="store_true", help="skip secondary benchmarks")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,7 +120,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// per-particle uniform stream (see oracle/kds_oracle.c "orc_stream")
+// per-particle uniform stream: Philox counter (index, block), key = seed; block 0
+// words 0,1 form the 64-bit pick, later words give u = ((w >> 9) + 0.5) 2^-23;
+// external mode reads U[p*slots + (n % slots)] instead (slot 0 is the pick)
 template <bool EXT>
 struct Stream {
   uint32_t k0, k1, p0, p1, blk;

@@ -341,15 +341,15 @@ class SurfR(_Polar2D):
 
     def transform(self, poss):
         rhos = np.sqrt(poss[:, 0] ** 2 + poss[:, 1] ** 2)
-        psis = np.arctan2(poss[:, 1], poss[:, 0]) * _DEG
+        psis = np.arctan2(poss[:, 1], poss[:, 0]) * 180 / np.pi
         return np.stack((rhos, psis), axis=1)
 
     def inverse_transform(self, poss):
         # (the reference stacks a (N,1) z column with (N,) x/y and raises,
         # geom.py:557-562; here all three columns are 1-D)
         z_col = np.full(len(poss), float(self.z))
-        x_col = poss[:, 0] * np.cos(poss[:, 1] / _DEG)
-        y_col = poss[:, 0] * np.sin(poss[:, 1] / _DEG)
+        x_col = poss[:, 0] * np.cos(poss[:, 1] * np.pi / 180)
+        y_col = poss[:, 0] * np.sin(poss[:, 1] * np.pi / 180)
         return np.stack((x_col, y_col, z_col), axis=1)
 
     def jac(self, poss):
@@ -365,13 +365,13 @@ class SurfR2(_Polar2D):
 
     def transform(self, poss):
         rhos = poss[:, 0] ** 2 + poss[:, 1] ** 2
-        psis = np.arctan2(poss[:, 1], poss[:, 0]) * _DEG
+        psis = np.arctan2(poss[:, 1], poss[:, 0]) * 180 / np.pi
         return np.stack((rhos, psis), axis=1)
 
     def inverse_transform(self, poss):
         z_col = np.full(len(poss), float(self.z))
-        x_col = poss[:, 0] ** 0.5 * np.cos(poss[:, 1] / _DEG)
-        y_col = poss[:, 0] ** 0.5 * np.sin(poss[:, 1] / _DEG)
+        x_col = poss[:, 0] ** 0.5 * np.cos(poss[:, 1] * np.pi / 180)
+        y_col = poss[:, 0] ** 0.5 * np.sin(poss[:, 1] * np.pi / 180)
         return np.stack((x_col, y_col, z_col), axis=1)
 
     def jac(self, poss):
@@ -504,16 +504,16 @@ class Polar(Metric):
         super().__init__([4, 5, 6], ["theta", "phi"], ["deg", "deg"], "sr^2")
 
     def transform(self, dirs):
-        return np.stack((np.arccos(dirs[:, 2]) * _DEG,
-                         np.arctan2(dirs[:, 1], dirs[:, 0]) * _DEG), axis=1)
+        return np.stack((np.arccos(dirs[:, 2]) * 180 / np.pi,
+                         np.arctan2(dirs[:, 1], dirs[:, 0]) * 180 / np.pi), axis=1)
 
     def inverse_transform(self, tps):
-        thetas, phis = tps.T / _DEG
+        thetas, phis = tps.T[0] * np.pi / 180, tps.T[1] * np.pi / 180
         return np.stack((np.sin(thetas) * np.cos(phis), np.sin(thetas) * np.sin(phis),
                          np.cos(thetas)), axis=1)
 
     def jac(self, dirs):
-        return _DEG ** 2 / np.sin(np.arccos(dirs[:, 2]))
+        return (180 / np.pi) ** 2 / np.sin(np.arccos(dirs[:, 2]))
 
 
 class PolarMu(Metric):
@@ -523,12 +523,13 @@ class PolarMu(Metric):
         super().__init__([4, 5, 6], ["mu", "phi"], ["", "deg"], "sr")
 
     def transform(self, dirs):
-        return np.stack((dirs[:, 2], np.arctan2(dirs[:, 1], dirs[:, 0]) * _DEG), axis=1)
+        return np.stack((dirs[:, 2], np.arctan2(dirs[:, 1], dirs[:, 0]) * 180 / np.pi), axis=1)
 
     def inverse_transform(self, tps):
         mus, phis = tps.T
         sq = np.sqrt(1 - mus ** 2)
-        return np.stack((sq * np.cos(phis / _DEG), sq * np.sin(phis / _DEG), mus), axis=1)
+        return np.stack((sq * np.cos(phis * np.pi / 180), sq * np.sin(phis * np.pi / 180), mus),
+                        axis=1)
 
 
 _metrics = {name: globals()[name] for name in METRIC_ORDER}

@@ -68,7 +68,23 @@ def main():
     with joblib.parallel_backend("threading"):
         kde_vectors(rkde, rgeom)
     geom_vectors(rgeom)
-    print("wrote ref_kde.npz, ref_geom.npz")
+    fixture_files()
+    print("wrote ref_kde.npz, ref_geom.npz, ref_fixture_samples.mcpl.gz, ref_fixture_source.xml")
+
+
+def fixture_files():
+    """The only test fixture the reference ships: the 9-particle MCPL list and
+    XML source embedded (base64) in python/kdsource/test.py:19-45, written out
+    byte for byte by calling the reference's own accessor functions."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_test", os.path.join(REF, "test.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(HERE, "ref_fixture_samples.mcpl.gz"), "wb") as fh:
+        fh.write(mod._test_samples_mcpl_gz_data())
+    with open(os.path.join(HERE, "ref_fixture_source.xml"), "wb") as fh:
+        fh.write(mod._test_source_xml_data())
 
 
 def kde_vectors(rkde, rgeom):

@@ -1,0 +1,44 @@
+"""Run each hot kernel a few times at a small size (for ncu captures)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import synthetic_scaled  # noqa: E402
+from kdsource_b200 import _lib, kde  # noqa: E402
+from kdsource_b200.sampler import DeviceSampler, make_geom_struct  # noqa: E402
+from kdsource_b200.treekde import TreeKDE  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+t = _lib.torch()
+N = 100_000
+parts, w, g, scaling, data = synthetic_scaled(N)
+bw = kde.bw_silv(6, np.sum(w) ** 2 / np.sum(w ** 2))
+if which in ("all", "eval"):
+    M = 200_000
+    q = synthetic_scaled(M, seed=54321, wseed=1)[4]
+    k = TreeKDE(bw=bw).fit(data, w)
+    dev = k._device_state()
+    d_q = _lib.to_dev(q)
+    for _ in range(3):
+        k.evaluate_device(d_q, M, dev)
+    t.cuda.synchronize()
+if which in ("all", "mlcv"):
+    plan = kde.MLCVPlan(data, w, bw, np.logspace(-0.3, 0.3, 32), n_splits=10)
+    for _ in range(3):
+        plan.launch()
+    t.cuda.synchronize()
+    print(plan.collect()[:4])
+if which in ("all", "knn"):
+    off = kde.array_split_bounds(N, 10)
+    for prec in ("float64", "float32"):
+        for _ in range(2):
+            kde.knn_batched(data, 11, off, precision=prec)
+if which in ("all", "resample"):
+    bws = np.random.default_rng(3).uniform(0.2, 0.5, N).astype(np.float32)
+    smp = DeviceSampler(parts, w, bws, make_geom_struct(g, scaling, "g"))
+    for _ in range(3):
+        smp.sample_device(10_000_000, seed=1)
+    t.cuda.synchronize()
+print("done", which)
