@@ -109,16 +109,20 @@ uint64_t kdsb200_cdf_scratch_words(uint64_t N);
  * uint64 prefix sums (order independent, hence bit-reproducible). */
 int kdsb200_weights_cdf(const double* d_w, uint64_t N, double sum_w, uint64_t* d_scratch,
                         uint64_t* d_cdf, void* stream);
+/* Optional search accelerator: d_guide[b] (2^bits + 1 uint32) = first i with
+ * cdf[i] > (b << (62-bits)); narrows the binary search window, same result. */
+int kdsb200_cdf_guide(const uint64_t* d_cdf, uint64_t N, int bits, uint32_t* d_guide, void* stream);
 /* (N,8) fp64 particles [ekin,x,y,z,ux,uy,uz,t] -> fp32 or fp64 device store */
 int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void* d_out,
                               void* stream);
 /* Output particle n (global index first+n): Philox4x32-10 counter (index, block),
  * key = seed; pick = first i with cdf[i] > mulhi64(R64, total); then Geom_perturb.
+ * d_guide/guide_bits: table from kdsb200_cdf_guide, or NULL for the plain search.
  * d_ext_uniforms (count x slots doubles) replaces Philox (test mode).
  * Outputs (each may be NULL): 36-byte MCPL-3 single-precision records, picked
  * source index, full-precision particle (8 doubles). */
-int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf, const float* d_bw,
-                     double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
+int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
+                     const uint32_t* d_guide, int guide_bits, const float* d_bw, double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
                      uint64_t seed, uint64_t first, uint64_t count, const double* d_ext_uniforms,
                      int slots, int perturb, void* d_out36, int64_t* d_out_idx,
                      double* d_out_parts, void* stream);

@@ -86,7 +86,9 @@ _SIGNATURES = {
     "kdsb200_cdf_scratch_words": (c_u64, [c_u64]),
     "kdsb200_weights_cdf": (c_int, [c_void_p, c_u64, c_double, c_void_p, c_void_p, c_void_p]),
     "kdsb200_convert_particles": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_void_p]),
-    "kdsb200_resample": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_i64,
+    "kdsb200_cdf_guide": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_void_p]),
+    "kdsb200_resample": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_double,
+                                 c_i64,
                                  ctypes.POINTER(Geom), c_i32, c_u64, c_u64, c_u64, c_void_p,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -59,6 +59,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x for x <= 0, two lanes at once, entirely on the FMA pipe (plus one FMNMX and
+// one shift-add per lane on the ALU pipe): Cody-Waite split by the magic-number
+// trick (t = x + 1.5*2^23 leaves round(x) in the low mantissa bits), degree-5
+// minimax polynomial on [-0.5, 0.5] (max rel. error 2.3e-7 in fp32, the same as
+// MUFU.EX2's 2^-22), exponent inserted by adding round(x) << 23 to the bits.
+// Used to take part of the exponentials off the SFU when MUFU.EX2 is the limit.
+__device__ __forceinline__ f2_t ex2_poly2(f2_t x) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  const f2_t xc = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const f2_t magic = f2_pack(12582912.f, 12582912.f);
+  const f2_t nmagic = f2_pack(-12582912.f, -12582912.f);
+  const f2_t t = f2_add(xc, magic);
+  const f2_t n = f2_add(t, nmagic);
+  const f2_t mone = f2_pack(-1.f, -1.f);
+  const f2_t f = f2_fma(n, mone, xc);  // x - round(x)
+  f2_t p = f2_pack(0.0013276472f, 0.0013276472f);
+  p = f2_fma(p, f, f2_pack(0.009675541f, 0.009675541f));
+  p = f2_fma(p, f, f2_pack(0.055507131f, 0.055507131f));
+  p = f2_fma(p, f, f2_pack(0.2402212f, 0.2402212f));
+  p = f2_fma(p, f, f2_pack(0.69314694f, 0.69314694f));
+  p = f2_fma(p, f, f2_pack(1.0000001f, 1.0000001f));
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  const float r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  const float r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+  return f2_pack(r0, r1);
+}
+
 // ---- mbarrier + 1-D bulk TMA copy ----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

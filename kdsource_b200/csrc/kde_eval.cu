@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(EV_THREADS, 2)
 #pragma unroll
     for (int qi = 0; qi < EV_Q; qi++) acc[qi] = 0ull;
 
-#pragma unroll 1
+#pragma unroll 2
     for (int j = 0; j < TS; j += 4) {
       float4 r[ROWS];
 #pragma unroll
@@ -320,14 +320,32 @@ int kdsb200_pack_queries_f32(const double* d_pts, uint64_t M, uint64_t Mpad, int
 }
 
 int kdsb200_eval_nsplit(uint64_t N, uint64_t M) {
+  // Pick the source split whose CTA count fills whole waves of 2 CTAs/SM best
+  // (at least ~4 waves when the problem is large enough).
   const uint64_t qtiles = kdsb200_eval_mpad(M) / (EV_THREADS * EV_Q);
   const uint64_t ntl = n_tiles_for(N);
   if (qtiles == 0 || ntl == 0) return 1;
-  const uint64_t target = (uint64_t)sm_count() * 2 * 4;  // >= 4 waves of 2 CTAs/SM
-  uint64_t ns = (target + qtiles - 1) / qtiles;
-  if (ns > ntl) ns = ntl;
-  if (ns < 1) ns = 1;
-  return (int)ns;
+  const uint64_t slots = (uint64_t)sm_count() * 2;
+  uint64_t lo = (4 * slots + qtiles - 1) / qtiles;
+  if (lo < 1) lo = 1;
+  if (lo > ntl) lo = ntl;
+  uint64_t hi = lo * 2 + 4;
+  if (hi > ntl) hi = ntl;
+  uint64_t best = lo;
+  double best_eff = -1.0;
+  for (uint64_t ns = lo; ns <= hi; ns++) {
+    const uint64_t tps = (ntl + ns - 1) / ns;
+    const uint64_t real = (ntl + tps - 1) / tps;  // splits actually launched
+    const uint64_t ctas = real * qtiles;
+    const uint64_t waves = (ctas + slots - 1) / slots;
+    // work of the longest CTA chain relative to a perfect distribution
+    const double eff = (double)(qtiles * ntl) / ((double)waves * slots * tps);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = ns;
+    }
+  }
+  return (int)best;
 }
 
 int kdsb200_kde_eval_f32(const float* d_packed, uint64_t N, int D, const float* d_qT, uint64_t M,

@@ -126,6 +126,39 @@ __device__ __forceinline__ void merge_queue(const KnnSmem<T>& S, int r, int cnt,
   __syncwarp();
 }
 
+// whole-warp call: compact the lanes with `pred` into the row's queue, merging
+// into the sorted list whenever 32 entries have accumulated
+template <typename T>
+__device__ __noinline__ void push_candidates(KnnSmem<T> S, int r, T d2, int j, bool pred, int KP,
+                                             int kk, int lane) {
+  const unsigned mask = __ballot_sync(0xffffffffu, pred);
+  if (!mask) return;
+  const int cnt = S.qcnt[r];
+  const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+  if (pred && pos < 32) {
+    S.que_d[r * 32 + pos] = d2;
+    S.que_i[r * 32 + pos] = j;
+  }
+  int total = cnt + __popc(mask);
+  __syncwarp();
+  if (total >= 32) {
+    merge_queue<T>(S, r, 32, KP, kk, lane);
+    if (pred && pos >= 32) {
+      S.que_d[r * 32 + pos - 32] = d2;
+      S.que_i[r * 32 + pos - 32] = j;
+    }
+    total -= 32;
+  }
+  if (lane == 0) S.qcnt[r] = total;
+  __syncwarp();
+}
+
+template <typename T>
+__device__ __noinline__ void flush_queue(KnnSmem<T> S, int r, int KP, int kk, int lane) {
+  const int cnt = S.qcnt[r];
+  if (cnt > 0) merge_queue<T>(S, r, cnt, KP, kk, lane);
+}
+
 template <typename T, int D>
 __device__ __forceinline__ T dist2(const T (&q)[D], const T* x) {
   if constexpr (sizeof(T) == 8) {
@@ -208,33 +241,20 @@ __global__ void __launch_bounds__(KNN_THREADS)
       T q[D];
 #pragma unroll
       for (int k = 0; k < D; k++) q[k] = S.rowq[r * D + k];
-      T tau = S.tau[r];
+      const T tau = S.tau[r];
+      T d2[JL];
+      bool any = false;
 #pragma unroll
       for (int e = 0; e < JL; e++) {
-        const int j = cbase + e * 32 + lane;
-        const T d2 = dist2<T, D>(q, x[e]);
-        const bool pred = (j < bn) && (d2 <= tau);
-        const unsigned mask = __ballot_sync(0xffffffffu, pred);
-        if (mask) {
-          const int cnt = S.qcnt[r];
-          const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-          if (pred && pos < 32) {
-            S.que_d[r * 32 + pos] = d2;
-            S.que_i[r * 32 + pos] = j;
-          }
-          int total = cnt + __popc(mask);
-          __syncwarp();
-          if (total >= 32) {
-            merge_queue<T>(S, r, 32, KP, kk, lane);
-            if (pred && pos >= 32) {
-              S.que_d[r * 32 + pos - 32] = d2;
-              S.que_i[r * 32 + pos - 32] = j;
-            }
-            total -= 32;
-            tau = S.tau[r];
-          }
-          if (lane == 0) S.qcnt[r] = total;
-          __syncwarp();
+        d2[e] = dist2<T, D>(q, x[e]);
+        any |= (cbase + e * 32 + lane < bn) && (d2[e] <= tau);
+      }
+      // rare path (kept out of line so the hot loop stays in the instruction cache)
+      if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int e = 0; e < JL; e++) {
+          const int j = cbase + e * 32 + lane;
+          push_candidates<T>(S, r, d2[e], j, (j < bn) && (d2[e] <= tau), KP, kk, lane);
         }
       }
     }
@@ -242,14 +262,151 @@ __global__ void __launch_bounds__(KNN_THREADS)
   __syncwarp();
   // flush leftovers and write results
   for (int r = warp; r < nrows; r += KNN_WARPS) {
-    const int cnt = S.qcnt[r];
-    if (cnt > 0) merge_queue<T>(S, r, cnt, KP, kk, lane);
+    flush_queue<T>(S, r, KP, kk, lane);
     const uint64_t row = (uint64_t)(b0 + r0 + r);
     for (int e = lane; e < kk; e += 32) {
       const double dd = sqrt((double)S.list_d[r * KP + e]);
       if (out_dist) out_dist[row * kk + e] = dd;
       if (out_idx) out_idx[row * kk + e] = S.list_i[r * KP + e] == 0x7fffffff ? -1 : S.list_i[r * KP + e];
       if (e == kk - 1 && out_kth) out_kth[row] = dd;
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// small-k kernel (k+1 <= KK <= 24): one query row per thread, its KK best
+// (distance^2, index) pairs sorted in registers.  Candidates stream through a
+// double-buffered shared-memory tile (cp.async) and are read as broadcast
+// LDS.128; no cross-lane traffic at all.  Candidates arrive in index order and
+// the insertion test is strict, so equal distances keep the smaller index first
+// ((distance, index) order, as the oracle and sklearn's brute force give).
+// ---------------------------------------------------------------------------
+constexpr int KS_THREADS = 256;
+template <typename T>
+struct KsTile {
+  static constexpr int CT = sizeof(T) == 4 ? 512 : 256;  // candidates per tile
+};
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <typename T, int D, int KK>
+__global__ void __launch_bounds__(KS_THREADS)
+    knn_small_kernel(const T* __restrict__ dataT, uint64_t Nstride,
+                     const int64_t* __restrict__ batch_off, int chunks, int kk,
+                     double* __restrict__ out_kth, double* __restrict__ out_dist,
+                     int32_t* __restrict__ out_idx) {
+  constexpr int KS_CT = KsTile<T>::CT;
+  __shared__ __align__(16) T tile[2][D][KS_CT];
+  const int tid = threadIdx.x;
+  const int bidx = blockIdx.x / chunks;
+  const int64_t b0 = batch_off[bidx], b1 = batch_off[bidx + 1];
+  const int bn = (int)(b1 - b0);
+  const int r0 = (blockIdx.x % chunks) * KS_THREADS;
+  if (r0 >= bn) return;
+  const int row = r0 + tid;
+  const bool live = row < bn;
+
+  T q[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) q[k] = live ? dataT[(uint64_t)k * Nstride + b0 + row] : (T)0;
+  T bd[KK];
+  int bi[KK];
+#pragma unroll
+  for (int s = 0; s < KK; s++) {
+    bd[s] = (T)INFINITY;
+    bi[s] = -1;
+  }
+
+  auto load_tile = [&](int buf, int cbase) {
+    for (int e = tid; e < D * KS_CT; e += KS_THREADS) {
+      const int k = e / KS_CT, c = e % KS_CT;
+      if (cbase + c < bn) {
+        const T* src = dataT + (uint64_t)k * Nstride + b0 + cbase + c;
+        if (sizeof(T) == 4) cp_async4(&tile[buf][k][c], src);
+        else cp_async8(&tile[buf][k][c], src);
+      } else {
+        tile[buf][k][c] = (T)0;
+      }
+    }
+    cp_async_commit();
+  };
+
+  const int ntile = (bn + KS_CT - 1) / KS_CT;
+  load_tile(0, 0);
+  for (int t = 0; t < ntile; t++) {
+    cp_async_wait_all();
+    __syncthreads();  // tile t visible; everyone is done with the other buffer
+    if (t + 1 < ntile) load_tile((t + 1) & 1, (t + 1) * KS_CT);
+    const int buf = t & 1;
+    const int cbase = t * KS_CT;
+    const int cnt = min(KS_CT, bn - cbase);
+    constexpr int V = 16 / sizeof(T);  // candidates per LDS.128
+    for (int c = 0; c < cnt; c += V) {
+      T x[D][V];
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        if (sizeof(T) == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(&tile[buf][k][c]);
+          x[k][0] = (T)v.x; x[k][1] = (T)v.y;
+          if (V == 4) { x[k][2 % V] = (T)v.z; x[k][3 % V] = (T)v.w; }
+        } else {
+          const double2 v = *reinterpret_cast<const double2*>(&tile[buf][k][c]);
+          x[k][0] = (T)v.x; x[k][1] = (T)v.y;
+        }
+      }
+      T d2[V];
+      bool any = false;
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        T xv[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) xv[k] = x[k][v];
+        d2[v] = dist2<T, D>(q, xv);
+        any |= d2[v] < bd[KK - 1];
+      }
+      if (any) {
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          if (c + v < cnt && d2[v] < bd[KK - 1]) {
+            // sorted insert, strict comparison keeps equal distances in index order
+            T nd = d2[v];
+            int ni = cbase + c + v;
+            bool shifting = false;  // once placed, everything behind moves down one slot
+#pragma unroll
+            for (int s = 0; s < KK; s++) {
+              shifting = shifting || (nd < bd[s]);
+              if (shifting) {
+                const T td = bd[s];
+                const int ti = bi[s];
+                bd[s] = nd;
+                bi[s] = ni;
+                nd = td;
+                ni = ti;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (live) {
+    const uint64_t grow = (uint64_t)(b0 + row);
+#pragma unroll
+    for (int s = 0; s < KK; s++) {
+      if (s < kk) {
+        const double dd = sqrt((double)bd[s]);
+        if (out_dist) out_dist[grow * kk + s] = dd;
+        if (out_idx) out_idx[grow * kk + s] = bi[s];
+        if (s == kk - 1 && out_kth) out_kth[grow] = dd;
+      }
     }
   }
 }
@@ -285,6 +442,25 @@ static int launch_knn(const double* d_data, uint64_t N, const int64_t* d_batch_o
   T* dataT = reinterpret_cast<T*>(d_scratch);
   knn_transpose_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_data, N, D, N, dataT);
   KDSB_CUDA(cudaGetLastError());
+  if (kk <= 24) {
+    const int64_t ch = (max_batch + KS_THREADS - 1) / KS_THREADS;
+    if (ch * nb >= (1ll << 31)) {
+      set_error("knn: grid too large (%lld CTAs)", (long long)(ch * nb));
+      return 1;
+    }
+    const unsigned g = (unsigned)(ch * nb);
+    if (kk <= 4)
+      knn_small_kernel<T, D, 4><<<g, KS_THREADS, 0, st>>>(dataT, N, d_batch_off, (int)ch, kk,
+                                                          out_kth, out_dist, out_idx);
+    else if (kk <= 12)
+      knn_small_kernel<T, D, 12><<<g, KS_THREADS, 0, st>>>(dataT, N, d_batch_off, (int)ch, kk,
+                                                           out_kth, out_dist, out_idx);
+    else
+      knn_small_kernel<T, D, 24><<<g, KS_THREADS, 0, st>>>(dataT, N, d_batch_off, (int)ch, kk,
+                                                           out_kth, out_dist, out_idx);
+    KDSB_CUDA(cudaGetLastError());
+    return 0;
+  }
   KDSB_CUDA(cudaFuncSetAttribute(knn_kernel<T, D, JL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   const int64_t chunks = (max_batch + RC - 1) / RC;

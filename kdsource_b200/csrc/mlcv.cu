@@ -12,11 +12,16 @@
 // [excl_lo, excl_hi) of sources (contiguous KFold without shuffle, kde.py:134),
 // so leave-one-out is the interval [i, i+1).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kdsb200.h"
 
 namespace kdsb {
+
+#ifndef KDSB_MLCV_POLY_DEFAULT
+#define KDSB_MLCV_POLY_DEFAULT 4
+#endif
 
 constexpr int CV_THREADS = 256;
 constexpr int CV_STAGES = 3;
@@ -40,7 +45,18 @@ __device__ __forceinline__ void block_reduce_store(double* S2, double* __restric
   }
 }
 
-template <int D, int GT>
+// Which grid slots take the FMA-pipe exponential (the rest use MUFU.EX2).  PM is a
+// small pattern id: 0 none, 2 every 2nd, 3 every 3rd, 4 every 4th, 38 three of eight.
+template <int PM>
+__device__ __forceinline__ constexpr bool use_poly(int g) {
+  return PM == 2 ? (g % 2 == 1)
+       : PM == 3 ? (g % 3 == 2)
+       : PM == 4 ? (g % 4 == 3)
+       : PM == 38 ? (g % 8 == 2 || g % 8 == 5 || g % 8 == 7)
+       : false;
+}
+
+template <int D, int GT, int PM>
 __global__ void __launch_bounds__(CV_THREADS, 2)
     mlcv_pairs_kernel(const float* __restrict__ packed, uint32_t n_tiles, uint32_t tiles_per_split,
                       const float* __restrict__ qT, uint64_t M, uint64_t Mpad,
@@ -120,9 +136,13 @@ __global__ void __launch_bounds__(CV_THREADS, 2)
 #pragma unroll
       for (int g = 0; g < GT; g++) {
         const f2_t arg = f2_mul(u2, f2_pack(P.nk[g], P.nk[g]));
-        float x0, x1;
-        f2_unpack(arg, x0, x1);
-        acc[g] = f2_fma(c2, f2_pack(ex2_approx(x0), ex2_approx(x1)), acc[g]);
+        if (use_poly<PM>(g)) {
+          acc[g] = f2_fma(c2, ex2_poly2(arg), acc[g]);
+        } else {
+          float x0, x1;
+          f2_unpack(arg, x0, x1);
+          acc[g] = f2_fma(c2, f2_pack(ex2_approx(x0), ex2_approx(x1)), acc[g]);
+        }
       }
     }
 #pragma unroll
@@ -171,7 +191,17 @@ __global__ void __launch_bounds__(CV_THREADS)
   block_reduce_store<GT>(S2, partial + (uint64_t)blockIdx.x * GT);
 }
 
-template <int D, int GT>
+static int poly_mode() {
+  // KDSB200_MLCV_POLY selects the SFU/FMA split of the exponentials (tuning knob)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("KDSB200_MLCV_POLY");
+    mode = e ? atoi(e) : KDSB_MLCV_POLY_DEFAULT;
+  }
+  return mode;
+}
+
+template <int D, int GT, int PM>
 static int launch_mlcv(const float* packed, uint32_t ntl, uint32_t tps, int nsplit,
                        const float* qT, uint64_t M, uint64_t Mpad, const int32_t* lo,
                        const int32_t* hi, const double* coefw, const double* lwtr,
@@ -180,12 +210,12 @@ static int launch_mlcv(const float* packed, uint32_t ntl, uint32_t tps, int nspl
   for (int g = 0; g < GT; g++) P.nk[g] = g < G ? h_nk[g] : -1e30f;  // unused slots -> 2^-inf = 0
   const size_t smem = (size_t)CV_STAGES * (D + 2) * TS * sizeof(float) +
                       (size_t)GT * CV_THREADS * sizeof(double);
-  KDSB_CUDA(cudaFuncSetAttribute(mlcv_pairs_kernel<D, GT>,
+  KDSB_CUDA(cudaFuncSetAttribute(mlcv_pairs_kernel<D, GT, PM>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)(Mpad / CV_THREADS), (unsigned)nsplit);
   const int fused = nsplit == 1;
-  mlcv_pairs_kernel<D, GT><<<grid, CV_THREADS, smem, st>>>(packed, ntl, tps, qT, M, Mpad, lo, hi,
-                                                           coefw, lwtr, P, fused, sbuf, partial);
+  mlcv_pairs_kernel<D, GT, PM><<<grid, CV_THREADS, smem, st>>>(
+      packed, ntl, tps, qT, M, Mpad, lo, hi, coefw, lwtr, P, fused, sbuf, partial);
   KDSB_CUDA(cudaGetLastError());
   if (!fused) {
     const size_t fsm = (size_t)GT * CV_THREADS * sizeof(double);
@@ -198,24 +228,31 @@ static int launch_mlcv(const float* packed, uint32_t ntl, uint32_t tps, int nspl
   return 0;
 }
 
+#define KDSB_MLCV_ARGS packed, ntl, tps, nsplit, qT, M, Mpad, lo, hi, coefw, lwtr, h_nk, G, sbuf, partial, st
+
 template <int D>
 static int dispatch_gt(int GT, const float* packed, uint32_t ntl, uint32_t tps, int nsplit,
                        const float* qT, uint64_t M, uint64_t Mpad, const int32_t* lo,
                        const int32_t* hi, const double* coefw, const double* lwtr,
                        const float* h_nk, int G, double* sbuf, double* partial, cudaStream_t st) {
+  const int pm = poly_mode();
   switch (GT) {
     case 8:
-      return launch_mlcv<D, 8>(packed, ntl, tps, nsplit, qT, M, Mpad, lo, hi, coefw, lwtr, h_nk, G,
-                               sbuf, partial, st);
+      return launch_mlcv<D, 8, 0>(KDSB_MLCV_ARGS);
     case 10:
-      return launch_mlcv<D, 10>(packed, ntl, tps, nsplit, qT, M, Mpad, lo, hi, coefw, lwtr, h_nk,
-                                G, sbuf, partial, st);
+      return launch_mlcv<D, 10, 0>(KDSB_MLCV_ARGS);
     case 16:
-      return launch_mlcv<D, 16>(packed, ntl, tps, nsplit, qT, M, Mpad, lo, hi, coefw, lwtr, h_nk,
-                                G, sbuf, partial, st);
+      return pm ? launch_mlcv<D, 16, KDSB_MLCV_POLY_DEFAULT>(KDSB_MLCV_ARGS)
+                : launch_mlcv<D, 16, 0>(KDSB_MLCV_ARGS);
     case 32:
-      return launch_mlcv<D, 32>(packed, ntl, tps, nsplit, qT, M, Mpad, lo, hi, coefw, lwtr, h_nk,
-                                G, sbuf, partial, st);
+      if (D == 6) {  // tuning variants are only built for the benchmark shape
+        if (pm == 2) return launch_mlcv<6, 32, 2>(KDSB_MLCV_ARGS);
+        if (pm == 3) return launch_mlcv<6, 32, 3>(KDSB_MLCV_ARGS);
+        if (pm == 4) return launch_mlcv<6, 32, 4>(KDSB_MLCV_ARGS);
+        if (pm == 38) return launch_mlcv<6, 32, 38>(KDSB_MLCV_ARGS);
+      }
+      return pm ? launch_mlcv<D, 32, KDSB_MLCV_POLY_DEFAULT>(KDSB_MLCV_ARGS)
+                : launch_mlcv<D, 32, 0>(KDSB_MLCV_ARGS);
   }
   set_error("mlcv: unsupported grid tile %d", GT);
   return 1;

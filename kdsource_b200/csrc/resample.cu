@@ -105,6 +105,31 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   }
 }
 
+// guide table: guide[b] = first i with cdf[i] > (b << shift), b = 0..K-1.  A pick
+// target T falls in bucket b = min(T >> shift, K-1) and its index lies in
+// [guide[b], guide[b+1]] (N-1 for the last bucket), so the binary search starts
+// from a window of ~N/K entries instead of N.  Same result as the full search.
+__global__ void cdf_guide_kernel(const uint64_t* __restrict__ cdf, uint64_t N, int bits,
+                                 uint32_t* __restrict__ guide) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t K = 1ull << bits;
+  if (b > K) return;
+  if (b == K) {
+    guide[b] = (uint32_t)(N - 1);
+    return;
+  }
+  const uint64_t T = b << (62 - bits);
+  uint64_t lo = 0, hi = N;
+  while (lo < hi) {
+    const uint64_t mid = lo + ((hi - lo) >> 1);
+    if (cdf[mid] > T)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  guide[b] = (uint32_t)(lo < N ? lo : N - 1);
+}
+
 // ---- Philox4x32-10 --------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
@@ -123,37 +148,43 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // per-particle uniform stream: Philox counter (index, block), key = seed; block 0
 // words 0,1 form the 64-bit pick, later words give u = ((w >> 9) + 0.5) 2^-23;
 // external mode reads U[p*slots + (n % slots)] instead (slot 0 is the pick)
+constexpr int RS_THREADS = 256;
+constexpr int RS_RING = 16;  // Philox words kept per thread in shared memory (4 blocks)
+
 template <bool EXT>
 struct Stream {
-  uint32_t k0, k1, p0, p1, blk;
-  uint32_t buf[4];
-  int have;
+  uint32_t k0, k1, p0, p1;
+  uint32_t* ring;  // shared memory, word w of this thread at ring[(w % RS_RING) * RS_THREADS]
   const double* ext;
   int slots, next;
 
-  __device__ __forceinline__ void init(uint64_t seed, uint64_t p, const double* e, int nslots) {
+  // The first RS_RING words (Philox blocks 0..3) are generated up front by all
+  // lanes in lock-step; only a lane that runs past them generates further blocks.
+  __device__ __forceinline__ void init(uint64_t seed, uint64_t p, const double* e, int nslots,
+                                       uint32_t* ring_base) {
+    next = 0;
     if (EXT) {
       ext = e + p * (uint64_t)nslots;
       slots = nslots;
-      next = 0;
     } else {
       k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
       p0 = (uint32_t)p; p1 = (uint32_t)(p >> 32);
-      blk = 0;
-      philox4x32_10(p0, p1, 0u, 0u, k0, k1, buf);
-      have = 4;
+      ring = ring_base + threadIdx.x;
+#pragma unroll
+      for (uint32_t b = 0; b < RS_RING / 4; b++) fill(b);
     }
   }
+  __device__ __forceinline__ void fill(uint32_t blk) {
+    uint32_t o[4];
+    philox4x32_10(p0, p1, blk, 0u, k0, k1, o);
+    const int s0 = (blk * 4) % RS_RING;
+#pragma unroll
+    for (int k = 0; k < 4; k++) ring[(s0 + k) * RS_THREADS] = o[k];
+  }
   __device__ __forceinline__ uint32_t word() {
-    if (have == 0) {
-      blk += 1;
-      philox4x32_10(p0, p1, blk, 0u, k0, k1, buf);
-      have = 4;
-    }
-    // buf[4 - have] without dynamic register indexing
-    const int sel = 4 - have;
-    const uint32_t w = sel == 0 ? buf[0] : sel == 1 ? buf[1] : sel == 2 ? buf[2] : buf[3];
-    have--;
+    if (next >= RS_RING && (next & 3) == 0) fill((uint32_t)next >> 2);
+    const uint32_t w = ring[(next % RS_RING) * RS_THREADS];
+    next++;
     return w;
   }
   __device__ __forceinline__ double ext_next() {
@@ -535,21 +566,34 @@ __device__ void metric_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>&
 }
 
 template <typename R, bool EXT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
     resample_kernel(const R* __restrict__ src8, const uint64_t* __restrict__ cdf,
+                    const uint32_t* __restrict__ guide, int guide_bits,
                     const float* __restrict__ bw, double bw_scalar, int64_t N, kdsb200_geom g,
                     int32_t pdg, uint64_t seed, uint64_t first, uint64_t count,
                     const double* __restrict__ ext, int slots, int perturb,
                     unsigned char* __restrict__ out36, int64_t* __restrict__ out_idx,
                     double* __restrict__ out_parts) {
-  const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= count) return;
+  __shared__ __align__(16) uint32_t stage[RS_THREADS * 9];
+  __shared__ uint32_t ring[EXT ? 1 : RS_RING * RS_THREADS];
+  const uint64_t n0 = (uint64_t)blockIdx.x * RS_THREADS;
+  const uint64_t n = n0 + threadIdx.x;
+  const bool live = n < count;
+  uint32_t rec[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (live) {
   Stream<EXT> s;
-  s.init(seed, EXT ? n : first + n, ext, slots);
-  const uint64_t total = cdf[N - 1];
+  s.init(seed, EXT ? n : first + n, ext, slots, ring);
+  const uint64_t total = __ldg(cdf + (N - 1));
   const uint64_t T = s.pick_target(total);
-  // upper_bound: first i with cdf[i] > T
-  int64_t lo = 0, hi = N;
+  // upper_bound: first i with cdf[i] > T (window from the guide table if present)
+  int64_t lo = 0, hi = N - 1;
+  if (guide) {
+    const uint64_t K = 1ull << guide_bits;
+    uint64_t b = T >> (62 - guide_bits);
+    if (b > K - 1) b = K - 1;
+    lo = __ldg(guide + b);
+    hi = __ldg(guide + b + 1);
+  }
   while (lo < hi) {
     const int64_t mid = lo + ((hi - lo) >> 1);
     if (__ldg(cdf + mid) > T)
@@ -557,7 +601,7 @@ __global__ void __launch_bounds__(256)
     else
       lo = mid + 1;
   }
-  const int64_t i = lo < N ? lo : N - 1;
+  const int64_t i = lo;
 
   Part<R> p;
   {
@@ -605,16 +649,36 @@ __global__ void __launch_bounds__(256)
     } else {
       p0 = p.dir[0]; p1 = p.dir[1]; sg = p.dir[2];
     }
-    uint32_t* o = reinterpret_cast<uint32_t*>(out36 + n * 36);
-    o[0] = __float_as_uint((float)p.pos[0]);
-    o[1] = __float_as_uint((float)p.pos[1]);
-    o[2] = __float_as_uint((float)p.pos[2]);
-    o[3] = __float_as_uint((float)p0);
-    o[4] = __float_as_uint((float)p1);
-    o[5] = __float_as_uint((float)copysign(fabs(p.ekin), sg));
-    o[6] = __float_as_uint((float)p.time);
-    o[7] = __float_as_uint(1.0f);  // weight = 1/bias, kdsource.c:325
-    o[8] = (uint32_t)pdg;
+    rec[0] = __float_as_uint((float)p.pos[0]);
+    rec[1] = __float_as_uint((float)p.pos[1]);
+    rec[2] = __float_as_uint((float)p.pos[2]);
+    rec[3] = __float_as_uint((float)p0);
+    rec[4] = __float_as_uint((float)p1);
+    rec[5] = __float_as_uint((float)copysign(fabs(p.ekin), sg));
+    rec[6] = __float_as_uint((float)p.time);
+    rec[7] = __float_as_uint(1.0f);  // weight = 1/bias, kdsource.c:325
+    rec[8] = (uint32_t)pdg;
+  }
+  }  // live
+  if (out36) {
+    // stage the CTA's records in shared memory (stride 9 words: conflict-free) and
+    // write them out as one contiguous, 16-byte-vectorised block
+#pragma unroll
+    for (int k = 0; k < 9; k++) stage[threadIdx.x * 9 + k] = rec[k];
+    __syncthreads();
+    const uint64_t nblk = count - n0 < RS_THREADS ? count - n0 : RS_THREADS;
+    const uint32_t words = (uint32_t)nblk * 9;
+    unsigned char* base = out36 + n0 * 36;  // n0*36 is a multiple of 16
+    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+      uint4* dst = reinterpret_cast<uint4*>(base);
+      const uint4* srcv = reinterpret_cast<const uint4*>(stage);
+      for (uint32_t v = threadIdx.x; v < words / 4; v += RS_THREADS) dst[v] = srcv[v];
+      for (uint32_t wd = (words / 4) * 4 + threadIdx.x; wd < words; wd += RS_THREADS)
+        reinterpret_cast<uint32_t*>(base)[wd] = stage[wd];
+    } else {
+      for (uint32_t wd = threadIdx.x; wd < words; wd += RS_THREADS)
+        reinterpret_cast<uint32_t*>(base)[wd] = stage[wd];
+    }
   }
 }
 
@@ -651,6 +715,22 @@ int kdsb200_weights_cdf(const double* d_w, uint64_t N, double sum_w, uint64_t* d
   return 0;
 }
 
+int kdsb200_cdf_guide(const uint64_t* d_cdf, uint64_t N, int bits, uint32_t* d_guide, void* stream) {
+  if (bits < 1 || bits > 26) {
+    set_error("cdf_guide: bits=%d out of range 1..26", bits);
+    return 1;
+  }
+  if (N == 0 || N >= (1ull << 32)) {
+    set_error("cdf_guide: N must be in 1..2^32-1");
+    return 1;
+  }
+  const uint64_t K1 = (1ull << bits) + 1;
+  cdf_guide_kernel<<<(unsigned)((K1 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_cdf, N, bits,
+                                                                                  d_guide);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void* d_out,
                               void* stream) {
   const uint64_t n8 = N * 8;
@@ -665,8 +745,8 @@ int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void
   return 0;
 }
 
-int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf, const float* d_bw,
-                     double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
+int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
+                     const uint32_t* d_guide, int guide_bits, const float* d_bw, double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
                      uint64_t seed, uint64_t first, uint64_t count, const double* d_ext_uniforms,
                      int slots, int perturb, void* d_out36, int64_t* d_out_idx,
                      double* d_out_parts, void* stream) {
@@ -680,6 +760,10 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf, 
     set_error("resample: geometry order %d out of range", h_geom->order);
     return 1;
   }
+  if (d_guide && (guide_bits < 1 || guide_bits > 26)) {
+    set_error("resample: guide_bits=%d out of range 1..26", guide_bits);
+    return 1;
+  }
   if (d_ext_uniforms && slots < 1) {
     set_error("resample: external uniforms need slots >= 1");
     return 1;
@@ -687,7 +771,8 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf, 
   const unsigned blocks = (unsigned)((count + 255) / 256);
   unsigned char* o36 = (unsigned char*)d_out36;
 #define KDSB_LAUNCH(R, EXT)                                                                      \
-  resample_kernel<R, EXT><<<blocks, 256, 0, st>>>((const R*)d_src8, d_cdf, d_bw, bw_scalar, N,   \
+  resample_kernel<R, EXT><<<blocks, RS_THREADS, 0, st>>>((const R*)d_src8, d_cdf, d_guide,     \
+                                                  guide_bits, d_bw, bw_scalar, N,                \
                                                   *h_geom, pdgcode, seed, first, count,          \
                                                   d_ext_uniforms, slots, perturb, o36,           \
                                                   d_out_idx, d_out_parts)

@@ -65,6 +65,23 @@ __global__ void __launch_bounds__(256) calib_kernel(float* out, int iters, float
     float x, y;
     f2_unpack(f2_add(f2_add(p0, p1), f2_add(p2, p3)), x, y); a0 = x + y;
     f2_unpack(f2_add(f2_add(p4, p5), f2_add(p6, p7)), x, y); a1 = x + y;
+  } else if (MODE == 3) {  // FFMA2 and scalar FFMA streams interleaved (heavy + lite pipes?)
+    f2_t p0 = f2_pack(a0, a1), p1 = f2_pack(a2, a3), p2 = f2_pack(a4, a5), p3 = f2_pack(a6, a7);
+    const f2_t mm = f2_pack(m, m), cc = f2_pack(c, c);
+    float s0 = a0 + 9.f, s1 = a1 + 9.f, s2 = a2 + 9.f, s3 = a3 + 9.f;
+    float s4 = a4 + 9.f, s5 = a5 + 9.f, s6 = a6 + 9.f, s7 = a7 + 9.f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        p0 = f2_fma(p0, mm, cc); s0 = fmaf(s0, m, c); s1 = fmaf(s1, m, c);
+        p1 = f2_fma(p1, mm, cc); s2 = fmaf(s2, m, c); s3 = fmaf(s3, m, c);
+        p2 = f2_fma(p2, mm, cc); s4 = fmaf(s4, m, c); s5 = fmaf(s5, m, c);
+        p3 = f2_fma(p3, mm, cc); s6 = fmaf(s6, m, c); s7 = fmaf(s7, m, c);
+      }
+    }
+    float x, y;
+    f2_unpack(f2_add(f2_add(p0, p1), f2_add(p2, p3)), x, y);
+    a0 = x + y + s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
   } else {  // MUFU.EX2
     a0 = -1e-3f * a0; a1 = -1e-3f * a1; a2 = -1e-3f * a2; a3 = -1e-3f * a3;
     a4 = -1e-3f * a4; a5 = -1e-3f * a5; a6 = -1e-3f * a6; a7 = -1e-3f * a7;
@@ -111,6 +128,7 @@ int kdsb200_calibrate_pipe(int mode, float* d_scratch /* >= sm*8*256 floats */, 
     KDSB_CUDA(cudaEventRecord(e0, st));
     if (mode == 0) calib_kernel<0><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     else if (mode == 1) calib_kernel<1><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
+    else if (mode == 3) calib_kernel<3><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     else calib_kernel<2><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     KDSB_CUDA(cudaEventRecord(e1, st));
     KDSB_CUDA(cudaEventSynchronize(e1));

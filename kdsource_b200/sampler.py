@@ -94,6 +94,13 @@ class DeviceSampler:
         self.cdf = _lib.empty(self.N, t.int64)  # uint64 payload
         _lib.check(L.kdsb200_weights_cdf(_lib.ptr(d_w), self.N, self.sum_w, _lib.ptr(scratch),
                                          _lib.ptr(self.cdf), _lib.stream()))
+        # search window table: ~8 CDF entries per bucket, at most 2^24 buckets
+        self.guide_bits = int(min(24, max(4, np.ceil(np.log2(max(self.N, 16) / 8.0)))))
+        self.guide = None
+        if self.N < (1 << 32):
+            self.guide = _lib.empty((1 << self.guide_bits) + 1, t.int32)
+            _lib.check(L.kdsb200_cdf_guide(_lib.ptr(self.cdf), self.N, self.guide_bits,
+                                           _lib.ptr(self.guide), _lib.stream()))
         if np.ndim(bw) == 0:
             self.bw = None
             self.bw_scalar = float(bw)
@@ -129,8 +136,8 @@ class DeviceSampler:
         if want_parts:
             res["parts"] = _lib.empty(count * 8, t.float64)
         _lib.check(L.kdsb200_resample(
-            _lib.ptr(self.src), int(self.f32), _lib.ptr(self.cdf), _lib.ptr(self.bw),
-            self.bw_scalar, self.N, ctypes.byref(self.geom), self.pdgcode,
+            _lib.ptr(self.src), int(self.f32), _lib.ptr(self.cdf), _lib.ptr(self.guide),
+            self.guide_bits, _lib.ptr(self.bw), self.bw_scalar, self.N, ctypes.byref(self.geom), self.pdgcode,
             int(seed) & 0xFFFFFFFFFFFFFFFF, int(first), count, _lib.ptr(d_ext), slots,
             int(bool(perturb)), _lib.ptr(res.get("records")), _lib.ptr(res.get("idx")),
             _lib.ptr(res.get("parts")), _lib.stream()))
