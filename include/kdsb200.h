@@ -118,14 +118,16 @@ int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void
 /* Output particle n (global index first+n): Philox4x32-10 counter (index, block),
  * key = seed; pick = first i with cdf[i] > mulhi64(R64, total); then Geom_perturb.
  * d_guide/guide_bits: table from kdsb200_cdf_guide, or NULL for the plain search.
+ * seq_start >= 0 replaces the pick by the list walk i = (seq_start + first + n) % N
+ * (the w_crit <= 0 mode of KDS_rand_sample2); pass -1 for weighted sampling.
  * d_ext_uniforms (count x slots doubles) replaces Philox (test mode).
  * Outputs (each may be NULL): 36-byte MCPL-3 single-precision records, picked
  * source index, full-precision particle (8 doubles). */
 int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
                      const uint32_t* d_guide, int guide_bits, const float* d_bw, double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
-                     uint64_t seed, uint64_t first, uint64_t count, const double* d_ext_uniforms,
-                     int slots, int perturb, void* d_out36, int64_t* d_out_idx,
-                     double* d_out_parts, void* stream);
+                     uint64_t seed, uint64_t first, uint64_t count, int64_t seq_start,
+                     const double* d_ext_uniforms, int slots, int perturb, void* d_out36,
+                     int64_t* d_out_idx, double* d_out_parts, void* stream);
 
 #ifdef __cplusplus
 }

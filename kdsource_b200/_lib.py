@@ -89,7 +89,7 @@ _SIGNATURES = {
     "kdsb200_cdf_guide": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_void_p]),
     "kdsb200_resample": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_double,
                                  c_i64,
-                                 ctypes.POINTER(Geom), c_i32, c_u64, c_u64, c_u64, c_void_p,
+                                 ctypes.POINTER(Geom), c_i32, c_u64, c_u64, c_u64, c_i64, c_void_p,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
     resample_kernel(const R* __restrict__ src8, const uint64_t* __restrict__ cdf,
                     const uint32_t* __restrict__ guide, int guide_bits,
                     const float* __restrict__ bw, double bw_scalar, int64_t N, kdsb200_geom g,
-                    int32_t pdg, uint64_t seed, uint64_t first, uint64_t count,
+                    int32_t pdg, uint64_t seed, uint64_t first, uint64_t count, int64_t seq_start,
                     const double* __restrict__ ext, int slots, int perturb,
                     unsigned char* __restrict__ out36, int64_t* __restrict__ out_idx,
                     double* __restrict__ out_parts) {
@@ -601,7 +601,9 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
     else
       lo = mid + 1;
   }
-  const int64_t i = lo;
+  // seq_start >= 0: walk the list in order instead (w_crit <= 0 mode of
+  // KDS_rand_sample2, kdsource.c:286-292); the pick number is still consumed
+  const int64_t i = seq_start >= 0 ? (int64_t)(((uint64_t)seq_start + first + n) % (uint64_t)N) : lo;
 
   Part<R> p;
   {
@@ -747,9 +749,9 @@ int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void
 
 int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
                      const uint32_t* d_guide, int guide_bits, const float* d_bw, double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
-                     uint64_t seed, uint64_t first, uint64_t count, const double* d_ext_uniforms,
-                     int slots, int perturb, void* d_out36, int64_t* d_out_idx,
-                     double* d_out_parts, void* stream) {
+                     uint64_t seed, uint64_t first, uint64_t count, int64_t seq_start,
+                     const double* d_ext_uniforms, int slots, int perturb, void* d_out36,
+                     int64_t* d_out_idx, double* d_out_parts, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (count == 0) return 0;
   if (N <= 0) {
@@ -774,7 +776,7 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
   resample_kernel<R, EXT><<<blocks, RS_THREADS, 0, st>>>((const R*)d_src8, d_cdf, d_guide,     \
                                                   guide_bits, d_bw, bw_scalar, N,                \
                                                   *h_geom, pdgcode, seed, first, count,          \
-                                                  d_ext_uniforms, slots, perturb, o36,           \
+                                                  seq_start, d_ext_uniforms, slots, perturb, o36, \
                                                   d_out_idx, d_out_parts)
   if (src_is_f32) {
     if (d_ext_uniforms) KDSB_LAUNCH(float, true);

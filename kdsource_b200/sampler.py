@@ -113,7 +113,8 @@ class DeviceSampler:
         t.cuda.current_stream().synchronize()
 
     def sample_device(self, count, seed=0, first=0, ext_uniforms=None, perturb=True,
-                      want_records=True, want_idx=False, want_parts=False, out=None):
+                      want_records=True, want_idx=False, want_parts=False, out=None,
+                      seq_start=-1):
         """Launch the resample kernel for output indices first..first+count-1.
         Returns a dict of device tensors ("records" uint8 (count*36), "idx" int64,
         "parts" float64 (count*8)).  `out` may supply a preallocated records
@@ -138,7 +139,8 @@ class DeviceSampler:
         _lib.check(L.kdsb200_resample(
             _lib.ptr(self.src), int(self.f32), _lib.ptr(self.cdf), _lib.ptr(self.guide),
             self.guide_bits, _lib.ptr(self.bw), self.bw_scalar, self.N, ctypes.byref(self.geom), self.pdgcode,
-            int(seed) & 0xFFFFFFFFFFFFFFFF, int(first), count, _lib.ptr(d_ext), slots,
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(first), count, int(seq_start), _lib.ptr(d_ext),
+            slots,
             int(bool(perturb)), _lib.ptr(res.get("records")), _lib.ptr(res.get("idx")),
             _lib.ptr(res.get("parts")), _lib.stream()))
         return res
