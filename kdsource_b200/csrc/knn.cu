@@ -283,9 +283,10 @@ __global__ void __launch_bounds__(KNN_THREADS)
 // ((distance, index) order, as the oracle and sklearn's brute force give).
 // ---------------------------------------------------------------------------
 constexpr int KS_THREADS = 256;
+constexpr int KS_PEND = 8;  // pending survivors per thread between warp-wide inserts
 template <typename T>
 struct KsTile {
-  static constexpr int CT = sizeof(T) == 4 ? 512 : 256;  // candidates per tile
+  static constexpr int CT = sizeof(T) == 4 ? 512 : 128;  // candidates per tile
 };
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
@@ -298,7 +299,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <typename T, int D, int KK>
-__global__ void __launch_bounds__(KS_THREADS)
+__global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
     knn_small_kernel(const T* __restrict__ dataT, uint64_t Nstride,
                      const int64_t* __restrict__ batch_off, int chunks, int kk,
                      double* __restrict__ out_kth, double* __restrict__ out_dist,
@@ -324,6 +325,37 @@ __global__ void __launch_bounds__(KS_THREADS)
     bd[s] = (T)INFINITY;
     bi[s] = -1;
   }
+
+  // per-thread pending candidates; entries are in candidate (index) order, and the
+  // insert below is strict, so equal distances keep the smaller index first
+  __shared__ T pend_d[KS_PEND][KS_THREADS];
+  __shared__ int pend_i[KS_PEND][KS_THREADS];
+  int npend = 0;
+  auto flush_pending = [&]() {
+    for (int e = 0; e < KS_PEND; e++) {
+      if (!__any_sync(0xffffffffu, e < npend)) break;
+      if (e < npend) {
+        T nd = pend_d[e][tid];
+        int ni = pend_i[e][tid];
+        if (nd < bd[KK - 1]) {
+          bool shifting = false;  // once placed, everything behind moves down one slot
+#pragma unroll
+          for (int s = 0; s < KK; s++) {
+            shifting = shifting || (nd < bd[s]);
+            if (shifting) {
+              const T td = bd[s];
+              const int ti = bi[s];
+              bd[s] = nd;
+              bi[s] = ni;
+              nd = td;
+              ni = ti;
+            }
+          }
+        }
+      }
+    }
+    npend = 0;
+  };
 
   auto load_tile = [&](int buf, int cbase) {
     for (int e = tid; e < D * KS_CT; e += KS_THREADS) {
@@ -364,39 +396,49 @@ __global__ void __launch_bounds__(KS_THREADS)
       }
       T d2[V];
       bool any = false;
+      if constexpr (sizeof(T) == 4) {
+        // two candidates per f32x2 lane pair: (q - x)^2 accumulated with FADD2/FFMA2
+        f2_t acc01 = 0ull, acc23 = 0ull;
 #pragma unroll
-      for (int v = 0; v < V; v++) {
-        T xv[D];
+        for (int k = 0; k < D; k++) {
+          const f2_t qq = f2_pack(-q[k], -q[k]);
+          const f2_t e01 = f2_add(f2_pack(x[k][0], x[k][1]), qq);
+          const f2_t e23 = f2_add(f2_pack(x[k][2], x[k][3]), qq);
+          acc01 = k == 0 ? f2_mul(e01, e01) : f2_fma(e01, e01, acc01);
+          acc23 = k == 0 ? f2_mul(e23, e23) : f2_fma(e23, e23, acc23);
+        }
+        float a, b, cc, dd;
+        f2_unpack(acc01, a, b);
+        f2_unpack(acc23, cc, dd);
+        d2[0] = a; d2[1] = b; d2[2] = cc; d2[3] = dd;
 #pragma unroll
-        for (int k = 0; k < D; k++) xv[k] = x[k][v];
-        d2[v] = dist2<T, D>(q, xv);
-        any |= d2[v] < bd[KK - 1];
+        for (int v = 0; v < V; v++) any |= d2[v] < bd[KK - 1];
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          T xv[D];
+#pragma unroll
+          for (int k = 0; k < D; k++) xv[k] = x[k][v];
+          d2[v] = dist2<T, D>(q, xv);
+          any |= d2[v] < bd[KK - 1];
+        }
       }
       if (any) {
+        // park the survivors in this thread's pending list (shared memory); the
+        // expensive sorted insert runs later for the whole warp at once
 #pragma unroll
         for (int v = 0; v < V; v++) {
           if (c + v < cnt && d2[v] < bd[KK - 1]) {
-            // sorted insert, strict comparison keeps equal distances in index order
-            T nd = d2[v];
-            int ni = cbase + c + v;
-            bool shifting = false;  // once placed, everything behind moves down one slot
-#pragma unroll
-            for (int s = 0; s < KK; s++) {
-              shifting = shifting || (nd < bd[s]);
-              if (shifting) {
-                const T td = bd[s];
-                const int ti = bi[s];
-                bd[s] = nd;
-                bi[s] = ni;
-                nd = td;
-                ni = ti;
-              }
-            }
+            pend_d[npend][tid] = d2[v];
+            pend_i[npend][tid] = cbase + c + v;
+            npend++;
           }
         }
       }
+      if (__any_sync(0xffffffffu, npend > KS_PEND - V)) flush_pending();
     }
   }
+  flush_pending();
   if (live) {
     const uint64_t grow = (uint64_t)(b0 + row);
 #pragma unroll

@@ -151,6 +151,18 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 constexpr int RS_THREADS = 256;
 constexpr int RS_RING = 16;  // Philox words kept per thread in shared memory (4 blocks)
 
+// rare path of Stream::word(): a lane ran past the words generated up front.  Out
+// of line (by value, so the stream state stays in registers) to keep the
+// ~60-instruction generator from being replicated at every call site.
+__device__ __noinline__ void philox_refill(uint32_t p0, uint32_t p1, uint32_t blk, uint32_t k0,
+                                           uint32_t k1, uint32_t* ring) {
+  uint32_t o[4];
+  philox4x32_10(p0, p1, blk, 0u, k0, k1, o);
+  const int s0 = (blk * 4) % RS_RING;
+#pragma unroll
+  for (int k = 0; k < 4; k++) ring[(s0 + k) * RS_THREADS] = o[k];
+}
+
 template <bool EXT>
 struct Stream {
   uint32_t k0, k1, p0, p1;
@@ -181,8 +193,11 @@ struct Stream {
 #pragma unroll
     for (int k = 0; k < 4; k++) ring[(s0 + k) * RS_THREADS] = o[k];
   }
+  // rare: a lane ran past the words generated up front; kept out of line so the
+  // ~60-instruction generator is not replicated at every call site of word()
   __device__ __forceinline__ uint32_t word() {
-    if (next >= RS_RING && (next & 3) == 0) fill((uint32_t)next >> 2);
+    if (next >= RS_RING && (next & 3) == 0)
+      philox_refill(p0, p1, (uint32_t)next >> 2, k0, k1, ring);
     const uint32_t w = ring[(next % RS_RING) * RS_THREADS];
     next++;
     return w;
@@ -441,13 +456,15 @@ __device__ void guide_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>& 
   p.dir[0] = dx; p.dir[1] = dy; p.dir[2] = dz;
 }
 
-// one metric's perturbation: geom.c:192-650
-template <typename R, bool EXT>
-__device__ void metric_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>& p, R bw,
-                               char kernel) {
+// one metric's perturbation: geom.c:192-650.  TYPE >= 0 fixes the metric at compile
+// time (specialised kernels for the usual geometries carry only the code they
+// need); TYPE < 0 dispatches on m.type at run time.
+template <typename R, bool EXT, int TYPE>
+__device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_metric& m,
+                                               Part<R>& p, R bw, char kernel) {
   using M = Mth<R>;
   const R PI180 = (R)(KDS_PI / 180);
-  switch (m.type) {
+  switch (TYPE >= 0 ? TYPE : m.type) {
     case M_ENERGY:  // E_perturb geom.c:192-198
       p.ekin += bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
       if (p.ekin < 0) p.ekin *= -1;
@@ -565,7 +582,9 @@ __device__ void metric_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>&
   }
 }
 
-template <typename R, bool EXT>
+enum { SIG_GENERIC = 0, SIG_FLAT = 1, SIG_ACTIV = 2 };
+
+template <typename R, bool EXT, int SIG>
 __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
     resample_kernel(const R* __restrict__ src8, const uint64_t* __restrict__ cdf,
                     const uint32_t* __restrict__ guide, int guide_bits,
@@ -619,19 +638,29 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
     }
   }
   const R h = bw ? (R)__ldg(bw + i) : (R)bw_scalar;
-  if (perturb) {  // Geom_perturb geom.c:139-158
-    if (g.has_trasl)
+  if (perturb) {  // Geom_perturb geom.c:139-158 (specialised signatures have no trasl/rot)
+    if (SIG == SIG_GENERIC && g.has_trasl)
       for (int k = 0; k < 3; k++) p.pos[k] -= (R)g.trasl[k];
-    if (g.has_rot) {
+    if (SIG == SIG_GENERIC && g.has_rot) {
       rotv<R>(p.pos, g.rot, 1);
       rotv<R>(p.dir, g.rot, 1);
     }
-    for (int k = 0; k < g.order; k++) metric_perturb<R, EXT>(s, g.ms[k], p, h, g.kernel);
-    if (g.has_rot) {
+    if (SIG == SIG_FLAT) {          // Lethargy + SurfXY + Isotrop (GeomFlat)
+      metric_perturb<R, EXT, M_LETHARGY>(s, g.ms[0], p, h, 'g');
+      metric_perturb<R, EXT, M_SURFXY>(s, g.ms[1], p, h, 'g');
+      metric_perturb<R, EXT, M_ISOTROP>(s, g.ms[2], p, h, 'g');
+    } else if (SIG == SIG_ACTIV) {  // Energy + Vol + Isotrop (GeomActiv)
+      metric_perturb<R, EXT, M_ENERGY>(s, g.ms[0], p, h, 'g');
+      metric_perturb<R, EXT, M_VOL>(s, g.ms[1], p, h, 'g');
+      metric_perturb<R, EXT, M_ISOTROP>(s, g.ms[2], p, h, 'g');
+    } else {
+      for (int k = 0; k < g.order; k++) metric_perturb<R, EXT, -1>(s, g.ms[k], p, h, g.kernel);
+    }
+    if (SIG == SIG_GENERIC && g.has_rot) {
       rotv<R>(p.pos, g.rot, 0);
       rotv<R>(p.dir, g.rot, 0);
     }
-    if (g.has_trasl)
+    if (SIG == SIG_GENERIC && g.has_trasl)
       for (int k = 0; k < 3; k++) p.pos[k] += (R)g.trasl[k];
   }
   if (out_idx) out_idx[n] = i;
@@ -772,12 +801,23 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
   }
   const unsigned blocks = (unsigned)((count + 255) / 256);
   unsigned char* o36 = (unsigned char*)d_out36;
-#define KDSB_LAUNCH(R, EXT)                                                                      \
-  resample_kernel<R, EXT><<<blocks, RS_THREADS, 0, st>>>((const R*)d_src8, d_cdf, d_guide,     \
-                                                  guide_bits, d_bw, bw_scalar, N,                \
-                                                  *h_geom, pdgcode, seed, first, count,          \
-                                                  seq_start, d_ext_uniforms, slots, perturb, o36, \
-                                                  d_out_idx, d_out_parts)
+  // kernels specialised for the usual geometries (Gaussian kernel, no trasl/rot)
+  int sig = SIG_GENERIC;
+  if (h_geom->kernel == 'g' && !h_geom->has_trasl && !h_geom->has_rot && h_geom->order == 3 &&
+      h_geom->ms[2].type == M_ISOTROP) {
+    if (h_geom->ms[0].type == M_LETHARGY && h_geom->ms[1].type == M_SURFXY) sig = SIG_FLAT;
+    if (h_geom->ms[0].type == M_ENERGY && h_geom->ms[1].type == M_VOL) sig = SIG_ACTIV;
+  }
+#define KDSB_LAUNCH1(R, EXT, SIG)                                                                \
+  resample_kernel<R, EXT, SIG><<<blocks, RS_THREADS, 0, st>>>(                                   \
+      (const R*)d_src8, d_cdf, d_guide, guide_bits, d_bw, bw_scalar, N, *h_geom, pdgcode, seed, \
+      first, count, seq_start, d_ext_uniforms, slots, perturb, o36, d_out_idx, d_out_parts)
+#define KDSB_LAUNCH(R, EXT)                                     \
+  do {                                                          \
+    if (sig == SIG_FLAT) KDSB_LAUNCH1(R, EXT, SIG_FLAT);        \
+    else if (sig == SIG_ACTIV) KDSB_LAUNCH1(R, EXT, SIG_ACTIV); \
+    else KDSB_LAUNCH1(R, EXT, SIG_GENERIC);                     \
+  } while (0)
   if (src_is_f32) {
     if (d_ext_uniforms) KDSB_LAUNCH(float, true);
     else KDSB_LAUNCH(float, false);
@@ -785,6 +825,7 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
     if (d_ext_uniforms) KDSB_LAUNCH(double, true);
     else KDSB_LAUNCH(double, false);
   }
+#undef KDSB_LAUNCH1
 #undef KDSB_LAUNCH
   KDSB_CUDA(cudaGetLastError());
   return 0;
