@@ -86,6 +86,15 @@ int kdsb200_knn(const double* d_data, uint64_t N, int D, const int64_t* d_batch_
                 int64_t max_batch, int kk, int use_f64, void* d_scratch, double* d_kth,
                 double* d_dist, int32_t* d_idx, void* stream);
 
+/* ---- geometry: Geometry.transform / Geometry.jac (python/kdsource/geom.py:158-205)
+ * d_parts (M,8) fp64 [ekin,x,y,z,dx,dy,dz,t] -> d_vecs (M,D) fp64 = transformed
+ * variables times h_inv_scaling (NULL: 1), and d_jac (M) (may be NULL).  The
+ * geometry's translation is taken from h_geom; its rotation from h_rot_inv, the
+ * row-major inverse rotation matrix (required when h_geom->has_rot). */
+int kdsb200_geom_transform(const double* d_parts, uint64_t M, const struct kdsb200_geom_s* h_geom,
+                           const double* h_rot_inv, const double* h_inv_scaling, double* d_vecs,
+                           double* d_jac, void* stream);
+
 /* ---- resampling: KDS_rand_sample2 loop (kdsource.c:282-330, resamplemcpl.c:40-43)
  * with the metric perturbations of geom.c:192-650 ------------------------- */
 #define KDSB200_MAX_METRICS 8
@@ -96,7 +105,7 @@ typedef struct {
   int32_t nps;
   double params[8];
 } kdsb200_metric;
-typedef struct {
+typedef struct kdsb200_geom_s {
   int32_t order;
   kdsb200_metric ms[KDSB200_MAX_METRICS];
   char kernel;       /* 'g' | 'e' | 'b' */

@@ -86,6 +86,8 @@ _SIGNATURES = {
     "kdsb200_cdf_scratch_words": (c_u64, [c_u64]),
     "kdsb200_weights_cdf": (c_int, [c_void_p, c_u64, c_double, c_void_p, c_void_p, c_void_p]),
     "kdsb200_convert_particles": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_void_p]),
+    "kdsb200_geom_transform": (c_int, [c_void_p, c_u64, ctypes.POINTER(Geom), c_double_p,
+                                       c_double_p, c_void_p, c_void_p, c_void_p]),
     "kdsb200_cdf_guide": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_void_p]),
     "kdsb200_resample": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_double,
                                  c_i64,

@@ -9,6 +9,7 @@ behind :class:`kdsource_b200.treekde.TreeKDE`; bandwidth selection in
 are presentation code and are not part of this package.
 """
 
+import ctypes
 import os
 from xml.dom import minidom
 from xml.etree.ElementTree import Element, SubElement, parse, tostring
@@ -121,16 +122,51 @@ class KDSource:
         (reference kdsource.py:215-248)."""
         if self.fitted is False:
             raise Exception("Must fit before evaluating.")
-        parts = np.array(parts, dtype=np.float64)  # private copy: geom edits in place
-        vecs = self.geom.transform(parts.copy())
-        jacs = self.geom.jac(parts)
+        parts = np.ascontiguousarray(parts, dtype=np.float64)
+        if parts.ndim != 2 or parts.shape[1] not in (7, 8):
+            raise ValueError("parts must have shape (obs, 8)")
+        if parts.shape[1] == 7:  # no time column
+            parts = np.concatenate((parts, np.zeros((len(parts), 1))), axis=1)
         vol = np.prod(self.scaling)
-        evals = 1 / vol * self.kde.evaluate(vecs / self.scaling)
+        dens, jacs = self._density_and_jac(parts)
+        evals = 1 / vol * dens
         errs = np.sqrt(
             evals * self.R ** self.geom.dim / (self.N_eff * np.mean(self.kde.bw) * vol))
         evals *= self.J * jacs
         errs *= self.J * jacs
         return [evals, errs]
+
+    def _density_and_jac(self, parts, chunk=1 << 22):
+        """kde.evaluate(geom.transform(parts) / scaling) and geom.jac(parts), with
+        the transform, the scaling and the kernel sum all on the device
+        (kdsb200_geom_transform + the evaluation kernel); `parts` is not modified."""
+        from . import _lib
+        from .sampler import make_geom_struct
+
+        L = _lib.load()
+        t = _lib.torch()
+        D = self.geom.dim
+        gs = make_geom_struct(self.geom, np.ones(D), "g")
+        inv_keep, inv_p = _lib.hostvec(1.0 / np.asarray(self.scaling, dtype=np.float64))
+        rot_keep, rot_p = (None, None)
+        if self.geom.rot is not None:
+            rot_keep, rot_p = _lib.hostvec(self.geom.rot.inv().as_matrix().reshape(-1))
+        dev = self.kde._device_state()
+        M = len(parts)
+        dens = np.empty(M)
+        jacs = np.empty(M)
+        for s in range(0, M, chunk):
+            n = min(chunk, M - s)
+            d_parts = _lib.to_dev(parts[s:s + n])
+            d_vecs = _lib.empty(n * D, t.float64)
+            d_jac = _lib.empty(n, t.float64)
+            _lib.check(L.kdsb200_geom_transform(_lib.ptr(d_parts), n, ctypes.byref(gs), rot_p,
+                                                inv_p, _lib.ptr(d_vecs), _lib.ptr(d_jac),
+                                                _lib.stream()))
+            d_out = self.kde.evaluate_device(d_vecs, n, dev)
+            dens[s:s + n] = d_out.cpu().numpy()
+            jacs[s:s + n] = d_jac.cpu().numpy()
+        return dens, jacs
 
     def save(self, xmlfilename=None, bwfile=None, adjust_N=True):
         """Write the XML source file (and the float32 bandwidth file for adaptive

@@ -353,3 +353,96 @@ def test_cdf_large_and_skewed(oracle):
         [("Lethargy", [1], [10.0]), ("SurfXY", [1, 1], [-np.inf, np.inf, -np.inf, np.inf, 0]),
          ("Isotrop", [1, 1, 1], [0, 0, 1])]), 200000, seed=1, perturb=False, want=("idx",))
     assert np.array_equal(idx, ref["idx"])
+
+
+# ------------------------------------------------- geometry kernel / KDSource
+def test_geom_transform_kernel_vs_numpy(golden_geom):
+    import ctypes
+
+    from kdsource_b200 import _lib
+    from kdsource_b200 import geom as G
+    from kdsource_b200.sampler import make_geom_struct
+
+    L = _lib.load()
+    t = _lib.torch()
+    P = golden_geom["parts"]
+    geoms = [
+        G.Geometry([G.Lethargy(10), G.SurfXY(), G.Isotrop()], trasl=[1.0, -2.0, 0.5],
+                   rot=[0.1, 0.2, -0.3]),
+        G.Geometry([G.Energy(), G.Vol(), G.Polar(), G.Time()]),
+        G.Geometry([G.Wavelength(), G.SurfR(), G.PolarMu(), G.Decade()], trasl=[0.3, 0.1, 0]),
+        G.Geometry([G.Lethargy(7.5), G.SurfR2(), G.Isotrop()]),
+        G.Geometry([G.Energy(), G.SurfCircle(), G.Isotrop()]),
+    ]
+    parts_sets = [P] * 5
+    guide = G.GeomGuide(3.0, 5.0, 100.0, 2000.0)
+    geoms.append(guide)
+    parts_sets.append(golden_geom["Guide_parts"])
+    for geo, parts in zip(geoms, parts_sets):
+        D = geo.dim
+        scaling = np.linspace(0.5, 2.0, D)
+        want_v = geo.transform(parts.copy()) / scaling
+        want_j = geo.jac(parts.copy())
+        gs = make_geom_struct(geo, np.ones(D), "g")
+        d_parts = _lib.to_dev(parts)
+        d_v = _lib.empty(len(parts) * D, t.float64)
+        d_j = _lib.empty(len(parts), t.float64)
+        inv_keep, inv_p = _lib.hostvec(1.0 / scaling)
+        rot_p = None
+        if geo.rot is not None:
+            rot_keep, rot_p = _lib.hostvec(geo.rot.inv().as_matrix().reshape(-1))
+        _lib.check(L.kdsb200_geom_transform(_lib.ptr(d_parts), len(parts), ctypes.byref(gs), rot_p,
+                                            inv_p, _lib.ptr(d_v), _lib.ptr(d_j), _lib.stream()))
+        got_v = d_v.cpu().numpy().reshape(len(parts), D)
+        got_j = d_j.cpu().numpy()
+        assert np.allclose(got_v, want_v, rtol=1e-12, atol=1e-13), geo.varnames
+        assert np.allclose(got_j, want_j, rtol=1e-12), geo.varnames
+
+
+def test_kdsource_pipeline_fit_evaluate_save_load(oracle, tmp_path, monkeypatch):
+    """The reference's user-level flow on a synthetic list written to MCPL:
+    KDSource(plist, geom, bw='silv').fit(); evaluate; save; load; evaluate."""
+    import kdsource_b200.api as kds
+    from kdsource_b200 import mcpl
+
+    monkeypatch.chdir(tmp_path)
+    parts, w = oracle.synthetic_particles(30000, seed=41, wseed=42)
+    mcpl.write_mcpl_file("list.mcpl.gz", ekin=parts[:, 0], x=parts[:, 1], y=parts[:, 2],
+                         z=parts[:, 3], ux=parts[:, 4], uy=parts[:, 5], uz=parts[:, 6],
+                         time=parts[:, 7], weight=w, pdgcode=2112, srcname="synthetic")
+    pl = kds.PList("list.mcpl.gz")
+    geo = kds.geom.GeomFlat(trasl=[0.5, -0.5, 0.0])
+    s = kds.KDSource(pl, geo, bw="silv", J=2.5)
+    s.fit(importance=[3, 1, 1, 1, 1, 1])
+    assert np.ndim(s.kde.bw) == 0 and s.kde.bw == pytest.approx(kds.bw_silv(6, s.N_eff))
+    q, _ = oracle.synthetic_particles(2000, seed=43, wseed=44)
+    evals, errs = s.evaluate(q)
+    # oracle: same formula from the file's (single precision) particles
+    fparts, fw = pl.get()
+    vecs = geo.transform(fparts.copy())
+    qv = geo.transform(q.copy())
+    jac = geo.jac(q.copy())
+    ref_e, ref_err = oracle.evaluate(qv, jac, vecs / s.scaling, fw, s.kde.bw, s.scaling, 2.5,
+                                     s.N_eff, 6)
+    ok = ref_e > 1e-12 * ref_e.max()
+    assert np.max(np.abs(evals[ok] / ref_e[ok] - 1)) < 1e-5
+    assert np.max(np.abs(errs[ok] / ref_err[ok] - 1)) < 1e-5
+    assert q.shape == (2000, 8)  # caller's array untouched
+    xml = s.save("src.xml", adjust_N=False)
+    s2 = kds.load(xml)
+    e2, _ = s2.evaluate(q)
+    assert np.allclose(e2, evals, rtol=1e-6)
+    # adaptive bandwidth by kNN, saved to the float32 side file and resampled
+    s3 = kds.KDSource(pl, geo, bw="knn")
+    s3.fit(N=20000, k=10, batch_size=5000)
+    assert s3.kde.bw.shape == (20000,)
+    e3, _ = s3.evaluate(q[:500])
+    v3 = geo.transform(pl.get(20000)[0].copy()) / s3.scaling
+    r3 = oracle.kde_sum_c(v3, pl.get(20000)[1], s3.kde.bw, qv[:500] / s3.scaling)
+    r3 = r3 / np.prod(s3.scaling) * jac[:500]  # J = 1
+    ok = r3 > 1e-12 * r3.max()
+    assert np.max(np.abs(e3[ok] / r3[ok] - 1)) < 1e-5
+    xml3 = s3.save("src3.xml", adjust_N=True)
+    kds.resample_to_mcpl(xml3, "res3.mcpl.gz", 5000, rng=3)
+    pb = mcpl.MCPLFile("res3.mcpl.gz", blocklength=5000).read_block()
+    assert len(pb) == 5000 and np.all(pb.weight == 1) and np.all(pb.z == 0)
