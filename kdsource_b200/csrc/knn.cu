@@ -380,18 +380,18 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
     const int buf = t & 1;
     const int cbase = t * KS_CT;
     const int cnt = min(KS_CT, bn - cbase);
-    constexpr int V = 16 / sizeof(T);  // candidates per LDS.128
+    constexpr int V = 4;  // candidates per step (one LDS.128 per coordinate in fp32, two in fp64)
     for (int c = 0; c < cnt; c += V) {
       T x[D][V];
 #pragma unroll
       for (int k = 0; k < D; k++) {
-        if (sizeof(T) == 4) {
+        if constexpr (sizeof(T) == 4) {
           const float4 v = *reinterpret_cast<const float4*>(&tile[buf][k][c]);
-          x[k][0] = (T)v.x; x[k][1] = (T)v.y;
-          if (V == 4) { x[k][2 % V] = (T)v.z; x[k][3 % V] = (T)v.w; }
+          x[k][0] = v.x; x[k][1] = v.y; x[k][2] = v.z; x[k][3] = v.w;
         } else {
-          const double2 v = *reinterpret_cast<const double2*>(&tile[buf][k][c]);
-          x[k][0] = (T)v.x; x[k][1] = (T)v.y;
+          const double2 v0 = *reinterpret_cast<const double2*>(&tile[buf][k][c]);
+          const double2 v1 = *reinterpret_cast<const double2*>(&tile[buf][k][c + 2]);
+          x[k][0] = v0.x; x[k][1] = v0.y; x[k][2] = v1.x; x[k][3] = v1.y;
         }
       }
       T d2[V];

@@ -10,6 +10,7 @@
 // sequentially); the perturbation maps, deviate maps (clib/src/utils.c:9-67) and
 // uniform-consumption order follow the reference.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kdsb200.h"
@@ -246,6 +247,25 @@ struct Mth<double> {
   static __device__ __forceinline__ double pow10_(double x) { return pow(10.0, x); }
 };
 
+// FAST (fp32 only): MUFU-based approximations (lg2/ex2/rcp/rsq/sin/cos, abs. error
+// ~2^-21) for the transcendental steps of the deviate and direction maps.  The
+// accept/reject decisions stay exact, so the uniform consumption is unchanged and
+// the perturbed coordinates stay within ~1e-6 of the variable's scale.
+template <typename R, bool FAST>
+struct Mf {
+  static __device__ __forceinline__ R exp_(R x) { return Mth<R>::exp_(x); }
+  static __device__ __forceinline__ R log_(R x) { return Mth<R>::log_(x); }
+  static __device__ __forceinline__ R sqrt_(R x) { return Mth<R>::sqrt_(x); }
+  static __device__ __forceinline__ R div_(R a, R b) { return a / b; }
+};
+template <>
+struct Mf<float, true> {
+  static __device__ __forceinline__ float exp_(float x) { return __expf(x); }
+  static __device__ __forceinline__ float log_(float x) { return __logf(x); }
+  static __device__ __forceinline__ float sqrt_(float x) { return __fsqrt_rn(x); }
+  static __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
+};
+
 template <typename R, bool EXT>
 __device__ __forceinline__ R uniform(Stream<EXT>& s) {
   if (EXT) return (R)s.ext_next();
@@ -255,7 +275,7 @@ __device__ __forceinline__ R uniform(Stream<EXT>& s) {
 // kds_rand_norm: Marsaglia polar method, second value discarded (utils.c:9-29).
 // Accept/reject is decided exactly (integers for Philox, fp64 for external
 // uniforms) so fp32 and fp64 modes consume the same number of uniforms.
-template <typename R, bool EXT>
+template <typename R, bool EXT, bool FAST>
 __device__ R rand_norm(Stream<EXT>& s) {
   if (EXT) {
     double t, g1, g2;
@@ -283,6 +303,10 @@ __device__ R rand_norm(Stream<EXT>& s) {
     }
     const float tf = (float)ti * (1.0f / 70368744177664.0f);
     const float g1 = (float)G1 * (1.0f / 8388608.0f);
+    if (FAST) {
+      // g1 * sqrt(-2 ln t / t) = g1 * sqrt(-2 ln2 * lg2 t) * rsqrt(t)
+      return (R)(g1 * __fsqrt_rn(-1.3862943611f * __log2f(tf)) * rsqrtf(tf));
+    }
     const float lt = ti > (1ll << 45)
                          ? log1pf(-(float)((1ll << 46) - ti) * (1.0f / 70368744177664.0f))
                          : logf(tf);
@@ -301,9 +325,9 @@ __device__ R rand_epan(Stream<EXT>& s) {
 }
 
 // kds_rand_type (utils.c:55-67)
-template <typename R, bool EXT>
+template <typename R, bool EXT, bool FAST>
 __device__ R rand_type(Stream<EXT>& s, char kernel) {
-  if (kernel == 'g') return rand_norm<R, EXT>(s);
+  if (kernel == 'g') return rand_norm<R, EXT, FAST>(s);
   if (kernel == 'e') return rand_epan<R, EXT>(s);
   if (kernel == 'b') return uniform<R, EXT>(s) * (R)2 - (R)1;
   return (R)0;
@@ -345,9 +369,10 @@ __device__ void rotv(R* v, const double* rv, int inverse) {
 }
 
 // _vMF_perturb (geom.c:557-573)
-template <typename R, bool EXT>
+template <typename R, bool EXT, bool FAST>
 __device__ void vmf_perturb(Stream<EXT>& s, R bw, R& dx, R& dy, R& dz) {
   using M = Mth<R>;
+  using F = Mf<R, FAST>;
   const R xi = uniform<R, EXT>(s);
   R w, uv;
   if (sizeof(R) == 8) {
@@ -356,9 +381,9 @@ __device__ void vmf_perturb(Stream<EXT>& s, R bw, R& dx, R& dy, R& dz) {
     uv = M::sqrt_(1 - w * w);
   } else {
     // same map, arranged so 1 - w*w does not cancel in fp32
-    const R m = -bw * bw * M::log_(xi + (1 - xi) * M::exp_(-2 / (bw * bw)));
+    const R m = -bw * bw * F::log_(xi + (1 - xi) * F::exp_(F::div_((R)-2, bw * bw)));
     w = 1 - m;
-    uv = M::sqrt_(fmax(m * (2 - m), (R)0));
+    uv = F::sqrt_(fmax(m * (2 - m), (R)0));
   }
   const R u01 = uniform<R, EXT>(s);
   R sphi, cphi;
@@ -366,6 +391,11 @@ __device__ void vmf_perturb(Stream<EXT>& s, R bw, R& dx, R& dy, R& dz) {
     const R phi = (R)(2. * KDS_PI) * u01;
     sphi = M::sin_(phi);
     cphi = M::cos_(phi);
+  } else if (FAST) {
+    // angle folded to [-pi, pi) before the MUFU sine/cosine
+    const float ang = 6.2831853072f * ((float)u01 - ((float)u01 >= 0.5f ? 1.0f : 0.0f));
+    sphi = __sinf(ang);
+    cphi = __cosf(ang);
   } else {
     float sf, cf;
     sincospif(2.0f * (float)u01, &sf, &cf);
@@ -374,18 +404,21 @@ __device__ void vmf_perturb(Stream<EXT>& s, R bw, R& dx, R& dy, R& dz) {
   }
   const R u = uv * cphi, v = uv * sphi;
   const R dx0 = dx, dy0 = dy, dz0 = dz;
+  const R cross = v * dx0 - u * dy0;
   if (dz0 > 0) {
-    dx = u * dz0 + w * dx0 - (v * dx0 - u * dy0) * dy0 / (1 + dz0);
-    dy = v * dz0 + w * dy0 + (v * dx0 - u * dy0) * dx0 / (1 + dz0);
+    const R den = 1 + dz0;
+    dx = u * dz0 + w * dx0 - F::div_(cross * dy0, den);
+    dy = v * dz0 + w * dy0 + F::div_(cross * dx0, den);
   } else {
-    dx = u * dz0 + w * dx0 + (v * dx0 - u * dy0) * dy0 / (1 - dz0);
-    dy = v * dz0 + w * dy0 - (v * dx0 - u * dy0) * dx0 / (1 - dz0);
+    const R den = 1 - dz0;
+    dx = u * dz0 + w * dx0 + F::div_(cross * dy0, den);
+    dy = v * dz0 + w * dy0 - F::div_(cross * dx0, den);
   }
   dz = w * dz0 - u * dx0 - v * dy0;
 }
 
 // Guide_perturb (geom.c:386-555)
-template <typename R, bool EXT>
+template <typename R, bool EXT, bool FAST>
 __device__ void guide_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>& p, R bw,
                               char kernel) {
   using M = Mth<R>;
@@ -418,14 +451,14 @@ __device__ void guide_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>& 
     case 2: t = (R)1.5 * yh + xw - y; mu = -dx; phi = M::atan2_(dy, dz); lo = yh + xw; hi = 2 * yh + xw; break;
     default: t = 2 * yh + (R)1.5 * xw + x; mu = -dy; phi = M::atan2_(-dx, dz); lo = 2 * yh + xw; hi = 2 * yh + 2 * xw; break;
   }
-  z += bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+  z += bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel);
   reflect<R>(z, (R)0, zmax);
-  t += bw * (R)m.scaling[1] * rand_type<R, EXT>(s, kernel);
+  t += bw * (R)m.scaling[1] * rand_type<R, EXT, FAST>(s, kernel);
   reflect<R>(t, lo, hi);
   if (isinf(m.scaling[2]))
     mu = -1 + 2 * uniform<R, EXT>(s);
   else {
-    mu2 = mu + bw * (R)m.scaling[2] * rand_type<R, EXT>(s, kernel);
+    mu2 = mu + bw * (R)m.scaling[2] * rand_type<R, EXT, FAST>(s, kernel);
     if (mu >= 0)
       reflect<R>(mu2, (R)0, (R)1);
     else
@@ -435,7 +468,7 @@ __device__ void guide_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>& 
   if (isinf(m.scaling[3]))
     phi = (R)(2. * KDS_PI) * uniform<R, EXT>(s);
   else
-    phi += bw * (R)m.scaling[3] * (R)(KDS_PI / 180) * rand_type<R, EXT>(s, kernel);
+    phi += bw * (R)m.scaling[3] * (R)(KDS_PI / 180) * rand_type<R, EXT, FAST>(s, kernel);
   const R sq = M::sqrt_(1 - mu * mu), cp = M::cos_(phi), sp = M::sin_(phi);
   switch (mirror) {
     case 0: x = xw / 2; y = t - (R)0.5 * yh; dx = mu; dz = sq * cp; dy = -sq * sp; break;
@@ -459,45 +492,45 @@ __device__ void guide_perturb(Stream<EXT>& s, const kdsb200_metric& m, Part<R>& 
 // one metric's perturbation: geom.c:192-650.  TYPE >= 0 fixes the metric at compile
 // time (specialised kernels for the usual geometries carry only the code they
 // need); TYPE < 0 dispatches on m.type at run time.
-template <typename R, bool EXT, int TYPE>
+template <typename R, bool EXT, int TYPE, bool FAST>
 __device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_metric& m,
                                                Part<R>& p, R bw, char kernel) {
   using M = Mth<R>;
   const R PI180 = (R)(KDS_PI / 180);
   switch (TYPE >= 0 ? TYPE : m.type) {
     case M_ENERGY:  // E_perturb geom.c:192-198
-      p.ekin += bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      p.ekin += bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel);
       if (p.ekin < 0) p.ekin *= -1;
       break;
     case M_LETHARGY: {  // Let_perturb geom.c:200-210
-      R E = p.ekin * M::exp_(bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel));
+      R E = p.ekin * Mf<R, FAST>::exp_(bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel));
       while (E > (R)m.params[0])
-        E = p.ekin * M::exp_(bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel));
+        E = p.ekin * Mf<R, FAST>::exp_(bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel));
       p.ekin = E;
     } break;
     case M_WAVELENGTH: {  // wl_perturb geom.c:212-221
       const R wl = (R)9.045 / M::sqrt_(p.ekin * (R)1e9);
-      const R wl2 = wl + bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      const R wl2 = wl + bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel);
       p.ekin = (R)81.82e-9 / (wl2 * wl2);
       if (p.ekin < 0) p.ekin *= -1;
     } break;
     case M_TIME:  // t_perturb geom.c:223-227
-      p.time += bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      p.time += bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel);
       break;
     case M_DECADE:  // Dec_perturb geom.c:228-233
-      p.time *= M::pow10_(bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel));
+      p.time *= M::pow10_(bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel));
       break;
     case M_VOL:  // Vol_perturb geom.c:235-265
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        p.pos[a] += bw * (R)m.scaling[a] * rand_type<R, EXT>(s, kernel);
+        p.pos[a] += bw * (R)m.scaling[a] * rand_type<R, EXT, FAST>(s, kernel);
         reflect<R>(p.pos[a], (R)m.params[2 * a], (R)m.params[2 * a + 1]);
       }
       break;
     case M_SURFXY:  // SurfXY_perturb geom.c:266-287
 #pragma unroll
       for (int a = 0; a < 2; a++) {
-        p.pos[a] += bw * (R)m.scaling[a] * rand_type<R, EXT>(s, kernel);
+        p.pos[a] += bw * (R)m.scaling[a] * rand_type<R, EXT, FAST>(s, kernel);
         reflect<R>(p.pos[a], (R)m.params[2 * a], (R)m.params[2 * a + 1]);
       }
       break;
@@ -509,8 +542,8 @@ __device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_met
       R rho = p.pos[0] * p.pos[0] + p.pos[1] * p.pos[1];
       if (!sq) rho = M::sqrt_(rho);
       const R psi = M::atan2_(p.pos[1], p.pos[0]);
-      R rho2 = rho + bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
-      R psi2 = psi + bw * (R)m.scaling[1] * PI180 * rand_type<R, EXT>(s, kernel);
+      R rho2 = rho + bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel);
+      R psi2 = psi + bw * (R)m.scaling[1] * PI180 * rand_type<R, EXT, FAST>(s, kernel);
       reflect<R>(rho2, rmin, rmax);
       reflect<R>(psi2, (R)m.params[2], (R)m.params[3]);
       if (sq) rho2 = M::sqrt_(rho2);
@@ -518,8 +551,8 @@ __device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_met
       p.pos[1] = rho2 * M::sin_(psi2);
     } break;
     case M_SURFCIRCLE: {  // SurfCircle_perturb geom.c:355-385
-      const R x = p.pos[0] + bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
-      const R y = p.pos[1] + bw * (R)m.scaling[1] * rand_type<R, EXT>(s, kernel);
+      const R x = p.pos[0] + bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel);
+      const R y = p.pos[1] + bw * (R)m.scaling[1] * rand_type<R, EXT, FAST>(s, kernel);
       R rho2 = M::sqrt_(x * x + y * y);
       R psi2 = M::atan2_(y, x);
       reflect<R>(rho2, (R)m.params[0], (R)m.params[1]);
@@ -528,7 +561,7 @@ __device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_met
       p.pos[1] = rho2 * M::sin_(psi2);
     } break;
     case M_GUIDE:
-      guide_perturb<R, EXT>(s, m, p, bw, kernel);
+      guide_perturb<R, EXT, FAST>(s, m, p, bw, kernel);
       break;
     case M_ISOTROP: {  // Isotrop_perturb geom.c:575-600 (kernel ignored)
       const R sc = bw * (R)m.scaling[0];
@@ -540,7 +573,7 @@ __device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_met
         p.dir[1] = dxy * M::sin_(phi);
       } else if (sc > 0) {
         const R dx = p.dir[0], dy = p.dir[1], dz = p.dir[2];
-        vmf_perturb<R, EXT>(s, sc, p.dir[0], p.dir[1], p.dir[2]);
+        vmf_perturb<R, EXT, FAST>(s, sc, p.dir[0], p.dir[1], p.dir[2]);
         if ((int)m.params[0] && (dx * p.dir[0] < 0)) p.dir[0] *= -1;
         if ((int)m.params[1] && (dy * p.dir[1] < 0)) p.dir[1] *= -1;
         if ((int)m.params[2] && (dz * p.dir[2] < 0)) p.dir[2] *= -1;
@@ -549,8 +582,8 @@ __device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_met
     case M_POLAR: {  // Polar_perturb geom.c:602-620 (reflected theta is overwritten there too)
       R theta = M::acos_(p.dir[2]);
       R phi = M::atan2_(p.dir[1], p.dir[0]);
-      theta = theta + bw * (R)m.scaling[0] * PI180 * rand_type<R, EXT>(s, kernel);
-      phi += bw * (R)m.scaling[1] * PI180 * rand_type<R, EXT>(s, kernel);
+      theta = theta + bw * (R)m.scaling[0] * PI180 * rand_type<R, EXT, FAST>(s, kernel);
+      phi += bw * (R)m.scaling[1] * PI180 * rand_type<R, EXT, FAST>(s, kernel);
       p.dir[0] = M::sin_(theta) * M::cos_(phi);
       p.dir[1] = M::sin_(theta) * M::sin_(phi);
       p.dir[2] = M::cos_(theta);
@@ -558,7 +591,7 @@ __device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_met
     case M_POLARMU: {  // PolarMu_perturb geom.c:622-650
       R mu = p.dir[2];
       R phi = M::atan2_(p.dir[1], p.dir[0]);
-      R mu2 = mu + bw * (R)m.scaling[0] * rand_type<R, EXT>(s, kernel);
+      R mu2 = mu + bw * (R)m.scaling[0] * rand_type<R, EXT, FAST>(s, kernel);
       if (mu >= 0) {
         while ((mu2 < 0) || (mu2 > 1)) {
           if (mu2 < 0) mu2 *= -1;
@@ -571,7 +604,7 @@ __device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_met
         }
       }
       mu = mu2;
-      phi += bw * (R)m.scaling[1] * PI180 * rand_type<R, EXT>(s, kernel);
+      phi += bw * (R)m.scaling[1] * PI180 * rand_type<R, EXT, FAST>(s, kernel);
       const R sq = M::sqrt_(1 - mu * mu);
       p.dir[0] = sq * M::cos_(phi);
       p.dir[1] = sq * M::sin_(phi);
@@ -584,7 +617,7 @@ __device__ __forceinline__ void metric_perturb(Stream<EXT>& s, const kdsb200_met
 
 enum { SIG_GENERIC = 0, SIG_FLAT = 1, SIG_ACTIV = 2 };
 
-template <typename R, bool EXT, int SIG>
+template <typename R, bool EXT, int SIG, bool FAST>
 __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
     resample_kernel(const R* __restrict__ src8, const uint64_t* __restrict__ cdf,
                     const uint32_t* __restrict__ guide, int guide_bits,
@@ -646,15 +679,15 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
       rotv<R>(p.dir, g.rot, 1);
     }
     if (SIG == SIG_FLAT) {          // Lethargy + SurfXY + Isotrop (GeomFlat)
-      metric_perturb<R, EXT, M_LETHARGY>(s, g.ms[0], p, h, 'g');
-      metric_perturb<R, EXT, M_SURFXY>(s, g.ms[1], p, h, 'g');
-      metric_perturb<R, EXT, M_ISOTROP>(s, g.ms[2], p, h, 'g');
+      metric_perturb<R, EXT, M_LETHARGY, FAST>(s, g.ms[0], p, h, 'g');
+      metric_perturb<R, EXT, M_SURFXY, FAST>(s, g.ms[1], p, h, 'g');
+      metric_perturb<R, EXT, M_ISOTROP, FAST>(s, g.ms[2], p, h, 'g');
     } else if (SIG == SIG_ACTIV) {  // Energy + Vol + Isotrop (GeomActiv)
-      metric_perturb<R, EXT, M_ENERGY>(s, g.ms[0], p, h, 'g');
-      metric_perturb<R, EXT, M_VOL>(s, g.ms[1], p, h, 'g');
-      metric_perturb<R, EXT, M_ISOTROP>(s, g.ms[2], p, h, 'g');
+      metric_perturb<R, EXT, M_ENERGY, FAST>(s, g.ms[0], p, h, 'g');
+      metric_perturb<R, EXT, M_VOL, FAST>(s, g.ms[1], p, h, 'g');
+      metric_perturb<R, EXT, M_ISOTROP, FAST>(s, g.ms[2], p, h, 'g');
     } else {
-      for (int k = 0; k < g.order; k++) metric_perturb<R, EXT, -1>(s, g.ms[k], p, h, g.kernel);
+      for (int k = 0; k < g.order; k++) metric_perturb<R, EXT, -1, FAST>(s, g.ms[k], p, h, g.kernel);
     }
     if (SIG == SIG_GENERIC && g.has_rot) {
       rotv<R>(p.pos, g.rot, 0);
@@ -674,7 +707,7 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
     const R ax = fabs(p.dir[0]), ay = fabs(p.dir[1]), az = fabs(p.dir[2]);
     R p0, p1, sg;
     if (az < fmax(ax, ay)) {
-      const R invz = p.dir[2] != 0 ? 1 / p.dir[2] : (R)INFINITY;
+      const R invz = p.dir[2] != 0 ? Mf<R, FAST>::div_((R)1, p.dir[2]) : (R)INFINITY;
       if (ax >= ay) { p0 = invz; p1 = p.dir[1]; sg = p.dir[0]; }
       else { p0 = p.dir[0]; p1 = invz; sg = p.dir[1]; }
     } else {
@@ -808,8 +841,20 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
     if (h_geom->ms[0].type == M_LETHARGY && h_geom->ms[1].type == M_SURFXY) sig = SIG_FLAT;
     if (h_geom->ms[0].type == M_ENERGY && h_geom->ms[1].type == M_VOL) sig = SIG_ACTIV;
   }
+  // fp32 Philox kernels of the specialised signatures use the MUFU fast-math maps
+  // unless KDSB200_RESAMPLE_PRECISE is set
+  static int precise = -1;
+  if (precise < 0) precise = getenv("KDSB200_RESAMPLE_PRECISE") ? 1 : 0;
+  const bool fast = !precise && src_is_f32 && !d_ext_uniforms && sig != SIG_GENERIC;
 #define KDSB_LAUNCH1(R, EXT, SIG)                                                                \
-  resample_kernel<R, EXT, SIG><<<blocks, RS_THREADS, 0, st>>>(                                   \
+  if (fast && sizeof(R) == 4 && !EXT && SIG != SIG_GENERIC)                                      \
+    resample_kernel<float, false, SIG == SIG_GENERIC ? SIG_FLAT : SIG, true>                     \
+        <<<blocks, RS_THREADS, 0, st>>>(                                                         \
+            (const float*)d_src8, d_cdf, d_guide, guide_bits, d_bw, bw_scalar, N, *h_geom,       \
+            pdgcode, seed, first, count, seq_start, d_ext_uniforms, slots, perturb, o36,         \
+            d_out_idx, d_out_parts);                                                             \
+  else                                                                                           \
+    resample_kernel<R, EXT, SIG, false><<<blocks, RS_THREADS, 0, st>>>(                          \
       (const R*)d_src8, d_cdf, d_guide, guide_bits, d_bw, bw_scalar, N, *h_geom, pdgcode, seed, \
       first, count, seq_start, d_ext_uniforms, slots, perturb, o36, d_out_idx, d_out_parts)
 #define KDSB_LAUNCH(R, EXT)                                     \

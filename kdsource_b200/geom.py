@@ -255,7 +255,8 @@ class Wavelength(Metric):
         return 81.82e-9 / ls ** 2
 
     def jac(self, ekins):
-        return 9.045 / (2 * np.sqrt(ekins ** 3))
+        # (the reference omits the reshape, geom.py:375-376, which breaks Geometry.jac)
+        return 9.045 / (2 * np.sqrt(ekins.reshape(-1) ** 3))
 
 
 class Time(Metric):
