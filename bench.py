@@ -363,9 +363,15 @@ def run_ours(args):
     sfu_peak = peaks["mufu"] / (1.0 - poly_x)
     local_evals = plan.n_evals  # rows of rank 0
     k_ms = float(np.mean(step_ms))
-    # the kernel computes every (row, source, g) slot incl. the masked fold: N, not N - n_f
-    slots = float(plan.M) * plan.N * G_MLCV
+    # slots the kernel executes: tiles inside a CTA's own fold are skipped, partial tiles
+    # and padding rows/sources are not
+    slots = plan.n_slots
     achieved = slots / (k_ms * 1e-3)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_mlcv.json")
+    if os.path.exists(tp) and world == 1 and n_mlcv == N_MLCV:
+        with open(tp) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
     sub = {}
     cpu = None
     if world == 1:
@@ -389,7 +395,7 @@ def run_ours(args):
                 int(getattr(plan, "d2h_bytes", 0)), "s_per_step": e2e_s},
         "gpu_launches": int(plan.n_launches * args.steps),
         "roofline": {"bound": "sfu", "achieved": achieved / 1e9, "peak": sfu_peak / 1e9,
-                     "unit": "Gop/s", "frac": achieved / sfu_peak, "traffic": None,
+                     "unit": "Gop/s", "frac": achieved / sfu_peak, "traffic": traffic,
                      "kernel": "mlcv_pairs_kernel<6,32,{}>".format(poly_mode),
                      "per_unit": "1 exponential + 2 FP32 lane-ops per (row, source, g) slot; "
                                  "{:.3g} of the exponentials run on the FMA pipe".format(poly_x),

@@ -75,20 +75,13 @@ __global__ void __launch_bounds__(CV_THREADS, 2)
   const int tid = threadIdx.x;
   const uint32_t t0 = blockIdx.y * tiles_per_split;
   const uint32_t t1 = min(n_tiles, t0 + tiles_per_split);
-  const uint32_t nt = t1 > t0 ? t1 - t0 : 0;
+  const uint32_t nt_all = t1 > t0 ? t1 - t0 : 0;
 
   if (tid == 0) {
     for (int s = 0; s < CV_STAGES; s++) mbar_init(&full[s], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    for (uint32_t p = 0; p < (uint32_t)(CV_STAGES - 1) && p < nt; p++) {
-      mbar_expect_tx(&full[p], TILE_BYTES);
-      tma_load_1d(tiles + p * TILE_FLOATS, packed + (uint64_t)(t0 + p) * TILE_FLOATS, TILE_BYTES,
-                  &full[p]);
-    }
-  }
 
   const uint64_t m = (uint64_t)blockIdx.x * CV_THREADS + tid;
   float q[D];
@@ -98,6 +91,43 @@ __global__ void __launch_bounds__(CV_THREADS, 2)
 #pragma unroll
   for (int g = 0; g < GT; g++) S2[g * CV_THREADS + tid] = 0.0;
 
+  // Source tiles that lie inside the excluded interval of EVERY row of this CTA
+  // (the rows' own fold, for all CTAs that do not straddle a fold boundary)
+  // contribute nothing and are skipped: [skip_a, skip_b) in tile units.  Padding
+  // rows (m >= M, empty interval) do not take part in the intersection.
+  __shared__ int cta_lo, cta_hi;
+  if (tid == 0) {
+    cta_lo = 0;
+    cta_hi = 0x7fffffff;
+  }
+  __syncthreads();
+  if (m < M) {
+    atomicMax(&cta_lo, lo);
+    atomicMin(&cta_hi, hi);
+  }
+  __syncthreads();
+  uint32_t skip_a = 0, skip_b = 0;
+  if (cta_hi > cta_lo) {
+    const uint32_t a = ((uint32_t)cta_lo + TS - 1) / TS, b = (uint32_t)cta_hi / TS;
+    const uint32_t a2 = max(a, t0), b2 = min(b, t1);
+    if (b2 > a2) {
+      skip_a = a2 - t0;
+      skip_b = b2 - t0;
+    }
+  }
+  const uint32_t nskip = skip_b - skip_a;
+  const uint32_t nt = nt_all - nskip;
+  // logical tile index (0..nt) -> physical tile of this split
+  auto phys = [&](uint32_t l) { return l < skip_a ? l : l + nskip; };
+
+  if (tid == 0) {
+    for (uint32_t p = 0; p < (uint32_t)(CV_STAGES - 1) && p < nt; p++) {
+      mbar_expect_tx(&full[p], TILE_BYTES);
+      tma_load_1d(tiles + p * TILE_FLOATS, packed + (uint64_t)(t0 + phys(p)) * TILE_FLOATS,
+                  TILE_BYTES, &full[p]);
+    }
+  }
+
   for (uint32_t it = 0; it < nt; it++) {
     const uint32_t s = it % CV_STAGES;
     const uint32_t parity = (it / CV_STAGES) & 1u;
@@ -105,13 +135,13 @@ __global__ void __launch_bounds__(CV_THREADS, 2)
       const uint32_t ps = (it + CV_STAGES - 1) % CV_STAGES;
       mbar_expect_tx(&full[ps], TILE_BYTES);
       tma_load_1d(tiles + ps * TILE_FLOATS,
-                  packed + (uint64_t)(t0 + it + CV_STAGES - 1) * TILE_FLOATS, TILE_BYTES,
+                  packed + (uint64_t)(t0 + phys(it + CV_STAGES - 1)) * TILE_FLOATS, TILE_BYTES,
                   &full[ps]);
     }
     mbar_wait(&full[s], parity);
     const float* tile = tiles + s * TILE_FLOATS;
     // excluded interval relative to this tile, clamped to [0, TS]
-    const int tbase = (int)((t0 + it) * TS);
+    const int tbase = (int)((t0 + phys(it)) * TS);
     const int xlo = max(lo - tbase, 0), xhi = min(hi - tbase, TS);
 
     f2_t acc[GT];

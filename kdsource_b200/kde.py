@@ -223,6 +223,19 @@ class MLCVPlan:
         #: kernel evaluations (exponentials that enter a score) per launch() call
         tr = float(N) - nf[f_loc]
         self.n_evals = float(np.sum(tr)) * len(self.grid)
+        #: (row, source, g) slots the kernel executes: per CTA of 256 rows, all source
+        #: tiles except those inside the excluded interval shared by all its rows
+        TS = 512
+        ntiles = (N + TS - 1) // TS
+        lo_pad = np.full(Mpad, -1, dtype=np.int64)
+        hi_pad = np.full(Mpad, np.iinfo(np.int64).max, dtype=np.int64)
+        lo_pad[:M] = fb[f_loc]
+        hi_pad[:M] = fb[f_loc + 1]
+        cta_lo = lo_pad.reshape(-1, 256).max(axis=1)
+        cta_hi = hi_pad.reshape(-1, 256).min(axis=1)
+        skipped = np.clip(cta_hi // TS - (cta_lo + TS - 1) // TS, 0, None)
+        skipped[cta_hi <= cta_lo] = 0
+        self.n_slots = float(np.sum(ntiles - skipped)) * TS * 256 * len(self.grid)
 
     def launch(self):
         if self.M == 0:

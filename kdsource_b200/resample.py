@@ -8,9 +8,10 @@ Geom with its metrics, scaling, BW (scalar, or a raw float32 file with one
 value per valid particle).
 """
 
-import gzip
 import os
 import pathlib
+import shutil
+import zlib
 from xml.etree.ElementTree import parse
 
 import numpy as np
@@ -63,8 +64,15 @@ def open_source(kds_sourcefile, precision="float32"):
     return sampler, info
 
 
+def _gzip_member(data, level):
+    """One complete gzip member (concatenated members form a valid .gz file, which
+    gzip/zlib readers -- and libmcpl's gzread -- decode as one stream)."""
+    co = zlib.compressobj(level, zlib.DEFLATED, 31)
+    return co.compress(data) + co.flush()
+
+
 def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=False,
-                     batch=1 << 22, compresslevel=1, precision="float32"):
+                     batch=1 << 22, compresslevel=1, precision="float32", threads=None):
     """Resample `nout` particles from an XML source file into a new MCPL file
     (always ``*.mcpl.gz``; refuses to overwrite unless `force`).
 
@@ -72,12 +80,26 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
     Philox generator, so output particle i depends only on (seed, i); a callable
     returning uniforms in [0,1) is honoured too (it is consumed on the host,
     32 numbers per particle, and fed to the same kernel).
+
+    The GPU produces MCPL-3 records in batches; the host compresses them as
+    independent gzip members on `threads` worker threads (default: all cores)
+    while the next batch is generated.  With torch.distributed initialised each
+    rank produces a contiguous share of the particles and rank 0 assembles the
+    file; the result does not depend on the number of ranks.
     """
+    from concurrent.futures import ThreadPoolExecutor
+
+    from . import dist as _dist
+
     ksrc = pathlib.Path(kds_sourcefile)
     nout = int(nout)
     if not ksrc.is_file():
         raise RuntimeError(f"Missing file: {kds_sourcefile}")
-    dst = _check_new_mcpl_filename(destination_mcpl, force=force)
+    rank, world = _dist.rank_world()
+    if rank == 0:
+        dst = _check_new_mcpl_filename(destination_mcpl, force=force)
+    else:
+        dst = _check_new_mcpl_filename(destination_mcpl, force=True)
     if nout <= 0 or nout > 1e16:
         raise RuntimeError("Invalid (or unreasonable) number of"
                            f" particles requested: {nout}")
@@ -85,20 +107,52 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
         rng = int.from_bytes(os.urandom(8), byteorder="big")
         print("Warning: No explicit seed provided"
               f" (choosing arbitrarily seed={rng})")
+        if world > 1:
+            raise RuntimeError("multi-rank resampling needs an explicit integer seed")
+    if world > 1 and not isinstance(rng, int):
+        raise RuntimeError("multi-rank resampling needs an explicit integer seed")
     sampler, _ = open_source(ksrc.absolute(), precision=precision)
-    header = mcpl.build_header(nout, "KDSource resample", singleprec=True)
+    lo, hi = _dist.shard_range(nout, rank, world)
+    nthreads = threads or os.cpu_count() or 1
+    part_name = str(dst) + ".part{}".format(rank) if world > 1 else None
     print("Resampling...")
-    with gzip.open(dst, "wb", compresslevel=compresslevel) as fh:
-        fh.write(header)
-        done = 0
-        while done < nout:
-            n = min(batch, nout - done)
+    with open(part_name or dst, "wb") as fh, ThreadPoolExecutor(nthreads) as pool:
+        if rank == 0:
+            fh.write(_gzip_member(mcpl.build_header(nout, "KDSource resample", singleprec=True),
+                                  compresslevel))
+        pending = []  # futures of the previous batch, written while the next one is generated
+
+        def drain():
+            for fut in pending:
+                fh.write(fut.result())
+            pending.clear()
+
+        done = lo
+        while done < hi:
+            n = min(batch, hi - done)
             if isinstance(rng, int):
                 rec = sampler.sample(n, seed=rng, first=done)["records"]
             else:
                 ext = np.fromiter((rng() for _ in range(n * DEFAULT_SLOTS)), dtype=np.float64,
                                   count=n * DEFAULT_SLOTS).reshape(n, DEFAULT_SLOTS)
                 rec = sampler.sample(n, first=done, ext_uniforms=ext)["records"]
-            fh.write(rec.tobytes())
+            drain()
+            raw = rec.reshape(-1)
+            step = max(36 * 4096, (len(raw) // nthreads + 35) // 36 * 36)
+            for s0 in range(0, len(raw), step):
+                pending.append(pool.submit(_gzip_member, raw[s0:s0 + step].tobytes(),
+                                           compresslevel))
             done += n
-    print("Successfully sampled {} particles.".format(nout))
+        drain()
+    if world > 1:
+        _dist.barrier()
+        if rank == 0:
+            with open(dst, "wb") as out:
+                for r in range(world):
+                    pn = str(dst) + ".part{}".format(r)
+                    with open(pn, "rb") as src:
+                        shutil.copyfileobj(src, out, 1 << 24)
+                    os.unlink(pn)
+        _dist.barrier()
+    if rank == 0:
+        print("Successfully sampled {} particles.".format(nout))

@@ -72,7 +72,10 @@ class TreeKDE:
     def __call__(self, points):
         return self.evaluate(points)
 
-    def evaluate(self, points, chunk=1 << 22):
+    def evaluate(self, points, chunk=1 << 22, shard=True):
+        """Densities at `points` ((obs, dims)).  With torch.distributed initialised
+        and ``shard=True`` the query points are split contiguously over the ranks
+        (sources replicated) and the result is assembled on every rank."""
         if self.data is None:
             raise ValueError("Must call fit before evaluating.")
         if self.kernel != "gaussian":
@@ -84,12 +87,19 @@ class TreeKDE:
             pts = pts.reshape(-1, self.data.shape[1])
         if pts.shape[1] != self.data.shape[1]:
             raise ValueError("points must have shape (obs, {})".format(self.data.shape[1]))
-        out = np.empty(len(pts), dtype=np.float64)
+        from . import dist as _dist
+
+        rank, world = _dist.rank_world()
+        lo, hi = _dist.shard_range(len(pts), rank, world) if shard else (0, len(pts))
+        out = np.zeros(len(pts), dtype=np.float64)
         dev = self._device_state()
-        for s in range(0, len(pts), chunk):
-            d_pts = _lib.to_dev(pts[s:s + chunk])
-            d_out = self.evaluate_device(d_pts, len(pts[s:s + chunk]), dev)
-            out[s:s + chunk] = d_out.cpu().numpy()
+        for s in range(lo, hi, chunk):
+            e = min(s + chunk, hi)
+            d_pts = _lib.to_dev(pts[s:e])
+            d_out = self.evaluate_device(d_pts, e - s, dev)
+            out[s:e] = d_out.cpu().numpy()
+        if shard and world > 1:
+            out = _dist.allreduce_sum_numpy(out)
         return out
 
     # -- device side ----------------------------------------------------------

@@ -30,5 +30,38 @@ lo, hi = dist.shard_range(100000, rank, world)
 mine = smp.sample(hi - lo, seed=5, first=lo)["records"]
 allrec = smp.sample(100000, seed=5, first=0)["records"]
 assert np.array_equal(mine, allrec[lo:hi])
-print("rank", rank, "of", world, "ok: mlcv sharded == full, knn", bw[:3], "resample split ok")
+from kdsource_b200.treekde import TreeKDE  # noqa: E402
+import tempfile  # noqa: E402
+from kdsource_b200 import mcpl  # noqa: E402
+from kdsource_b200.resample import resample_to_mcpl  # noqa: E402
+import kdsource_b200.api as kds  # noqa: E402
+
+k = TreeKDE(bw=0.35).fit(data, w)
+q = data[:5001] + 0.01
+sharded = k.evaluate(q)
+whole = k.evaluate(q, shard=False)
+assert np.allclose(sharded, whole, rtol=1e-12)
+# multi-rank resample_to_mcpl: same file as a single-rank run (compared after decompression)
+tmp = "/tmp/kds_multi"
+os.makedirs(tmp, exist_ok=True)
+if rank == 0:
+    mcpl.write_mcpl_file(tmp + "/list.mcpl.gz", ekin=parts[:, 0], x=parts[:, 1], y=parts[:, 2],
+                         z=parts[:, 3], ux=parts[:, 4], uy=parts[:, 5], uz=parts[:, 6],
+                         time=parts[:, 7], weight=w, pdgcode=2112)
+dist.barrier()
+pl = kds.PList(tmp + "/list.mcpl.gz")
+src = kds.KDSource(pl, g, bw=0.3)
+src.fit()
+if rank == 0:
+    src.save(tmp + "/src.xml", adjust_N=False)
+dist.barrier()
+resample_to_mcpl(tmp + "/src.xml", tmp + "/multi.mcpl.gz", 300001, rng=9, force=True)
+if rank == 0:
+    import gzip
+    a = gzip.open(tmp + "/multi.mcpl.gz").read()
+    smp2, _ = __import__("kdsource_b200.resample", fromlist=["open_source"]).open_source(tmp + "/src.xml")
+    ref = mcpl.build_header(300001, "KDSource resample") + smp2.sample(300001, seed=9)["records"].tobytes()
+    assert a == ref, (len(a), len(ref))
+dist.barrier()
+print("rank", rank, "of", world, "ok: mlcv sharded == full, knn", bw[:3], "resample split ok, evaluate sharded ok, multi-rank mcpl ok")
 td.destroy_process_group()
