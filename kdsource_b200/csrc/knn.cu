@@ -283,7 +283,11 @@ __global__ void __launch_bounds__(KNN_THREADS)
 // ((distance, index) order, as the oracle and sklearn's brute force give).
 // ---------------------------------------------------------------------------
 constexpr int KS_THREADS = 256;
-constexpr int KS_PEND = 8;  // pending survivors per thread between warp-wide inserts
+template <typename T>
+struct KsPend {
+  // pending survivors per thread between warp-wide inserts
+  static constexpr int N = sizeof(T) == 4 ? 16 : 8;
+};
 template <typename T>
 struct KsTile {
   static constexpr int CT = sizeof(T) == 4 ? 512 : 128;  // candidates per tile
@@ -305,7 +309,13 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
                      double* __restrict__ out_kth, double* __restrict__ out_dist,
                      int32_t* __restrict__ out_idx) {
   constexpr int KS_CT = KsTile<T>::CT;
-  __shared__ __align__(16) T tile[2][D][KS_CT];
+  constexpr int KS_PEND = KsPend<T>::N;
+  extern __shared__ __align__(16) unsigned char ks_smem[];
+  T(*tile)[D][KS_CT] = reinterpret_cast<T(*)[D][KS_CT]>(ks_smem);
+  T(*pend_d)[KS_THREADS] =
+      reinterpret_cast<T(*)[KS_THREADS]>(ks_smem + sizeof(T) * 2 * D * KS_CT);
+  int(*pend_i)[KS_THREADS] = reinterpret_cast<int(*)[KS_THREADS]>(
+      ks_smem + sizeof(T) * 2 * D * KS_CT + sizeof(T) * KS_PEND * KS_THREADS);
   const int tid = threadIdx.x;
   const int bidx = blockIdx.x / chunks;
   const int64_t b0 = batch_off[bidx], b1 = batch_off[bidx + 1];
@@ -328,8 +338,6 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
 
   // per-thread pending candidates; entries are in candidate (index) order, and the
   // insert below is strict, so equal distances keep the smaller index first
-  __shared__ T pend_d[KS_PEND][KS_THREADS];
-  __shared__ int pend_i[KS_PEND][KS_THREADS];
   int npend = 0;
   auto flush_pending = [&]() {
     for (int e = 0; e < KS_PEND; e++) {
@@ -491,15 +499,19 @@ static int launch_knn(const double* d_data, uint64_t N, const int64_t* d_batch_o
       return 1;
     }
     const unsigned g = (unsigned)(ch * nb);
-    if (kk <= 4)
-      knn_small_kernel<T, D, 4><<<g, KS_THREADS, 0, st>>>(dataT, N, d_batch_off, (int)ch, kk,
-                                                          out_kth, out_dist, out_idx);
-    else if (kk <= 12)
-      knn_small_kernel<T, D, 12><<<g, KS_THREADS, 0, st>>>(dataT, N, d_batch_off, (int)ch, kk,
-                                                           out_kth, out_dist, out_idx);
-    else
-      knn_small_kernel<T, D, 24><<<g, KS_THREADS, 0, st>>>(dataT, N, d_batch_off, (int)ch, kk,
-                                                           out_kth, out_dist, out_idx);
+    const size_t ksm = sizeof(T) * 2 * D * KsTile<T>::CT +
+                       (sizeof(T) + sizeof(int)) * KsPend<T>::N * KS_THREADS;
+#define KDSB_KS(KKV)                                                                        \
+  do {                                                                                      \
+    KDSB_CUDA(cudaFuncSetAttribute(knn_small_kernel<T, D, KKV>,                             \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm)); \
+    knn_small_kernel<T, D, KKV><<<g, KS_THREADS, ksm, st>>>(dataT, N, d_batch_off, (int)ch, \
+                                                            kk, out_kth, out_dist, out_idx); \
+  } while (0)
+    if (kk <= 4) KDSB_KS(4);
+    else if (kk <= 12) KDSB_KS(12);
+    else KDSB_KS(24);
+#undef KDSB_KS
     KDSB_CUDA(cudaGetLastError());
     return 0;
   }
