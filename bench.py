@@ -357,9 +357,11 @@ def run_ours(args):
         return
     # roofline of the dominant kernel (mlcv_pairs_kernel): one exponential per (row,
     # source, g) slot.  A fraction x of the slots evaluates 2^x on the FMA pipe
-    # (ex2_poly2), so the SFU bound is mufu_rate / (1 - x).
-    poly_mode = int(os.environ.get("KDSB200_MLCV_POLY", "4"))
-    poly_x = {0: 0.0, 2: 0.5, 3: 10.0 / 32, 4: 0.25, 38: 0.375}.get(poly_mode, 0.25)
+    # (ex2_poly2_scaled), so the SFU bound is mufu_rate / (1 - x).
+    L = _lib.load()
+    gtile = int(L.kdsb200_mlcv_gtile(G_MLCV))
+    poly_slots = int(L.kdsb200_mlcv_poly_slots(G_MLCV))
+    poly_x = poly_slots / float(gtile)
     sfu_peak = peaks["mufu"] / (1.0 - poly_x)
     local_evals = plan.n_evals  # rows of rank 0
     k_ms = float(np.mean(step_ms))
@@ -396,7 +398,7 @@ def run_ours(args):
         "gpu_launches": int(plan.n_launches * args.steps),
         "roofline": {"bound": "sfu", "achieved": achieved / 1e9, "peak": sfu_peak / 1e9,
                      "unit": "Gop/s", "frac": achieved / sfu_peak, "traffic": traffic,
-                     "kernel": "mlcv_pairs_kernel<6,32,{}>".format(poly_mode),
+                     "kernel": "mlcv_pairs_kernel<6,{},PM> with {}/{} polynomial slots".format(gtile, poly_slots, gtile),
                      "per_unit": "1 exponential + 2 FP32 lane-ops per (row, source, g) slot; "
                                  "{:.3g} of the exponentials run on the FMA pipe".format(poly_x),
                      "peak_source": "calibrated live: ex2.approx loop {:.4g} Gop/s on {} SMs, "

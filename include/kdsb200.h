@@ -63,6 +63,9 @@ int kdsb200_kde_eval_f64(const double* d_data, const double* d_w, const double* 
 int kdsb200_mlcv_gtile(int G);          /* grid slots the kernel computes for G factors */
 uint64_t kdsb200_mlcv_mpad(uint64_t M); /* test-point count padded to the CTA tile */
 int kdsb200_mlcv_nsplit(uint64_t N, uint64_t M);
+/* how many of the gtile(G) slots evaluate 2^x on the FMA pipe instead of MUFU.EX2
+ * (for roofline accounting; the result does not depend on it beyond 1e-6) */
+int kdsb200_mlcv_poly_slots(int G);
 /* Sources packed with mode 1.  Test points d_qT [D][Mpad]; per test point the
  * excluded source interval [lo,hi) (its fold; [i,i+1) for leave-one-out), the
  * coefficient coefw = w_i / (n_fold * K) and lwtr = ln(sum of train weights).

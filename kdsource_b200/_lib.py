@@ -78,6 +78,7 @@ _SIGNATURES = {
     "kdsb200_mlcv_gtile": (c_int, [c_int]),
     "kdsb200_mlcv_mpad": (c_u64, [c_u64]),
     "kdsb200_mlcv_nsplit": (c_int, [c_u64, c_u64]),
+    "kdsb200_mlcv_poly_slots": (c_int, [c_int]),
     "kdsb200_mlcv_scores_f32": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_u64, c_u64, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_float_p, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p]),

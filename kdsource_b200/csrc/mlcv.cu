@@ -301,6 +301,20 @@ int kdsb200_mlcv_gtile(int G) {
   return 32;
 }
 
+int kdsb200_mlcv_poly_slots(int G) {
+  // grid slots (of kdsb200_mlcv_gtile(G)) whose exponential runs on the FMA pipe
+  const int GT = kdsb200_mlcv_gtile(G);
+  int pm = poly_mode();
+  if (GT < 16 || pm == 0) return 0;
+  if (GT == 16) pm = KDSB_MLCV_POLY_DEFAULT;  // only the default pattern is built for 16
+  if (pm != 2 && pm != 3 && pm != 4 && pm != 38) pm = KDSB_MLCV_POLY_DEFAULT;
+  int n = 0;
+  for (int g = 0; g < GT; g++)
+    n += pm == 2 ? (g % 2 == 1) : pm == 3 ? (g % 3 == 2) : pm == 4 ? (g % 4 == 3)
+                                : (g % 8 == 2 || g % 8 == 5 || g % 8 == 7);
+  return n;
+}
+
 uint64_t kdsb200_mlcv_mpad(uint64_t M) { return (M + CV_THREADS - 1) / CV_THREADS * CV_THREADS; }
 
 int kdsb200_mlcv_nsplit(uint64_t N, uint64_t M) {
