@@ -191,8 +191,11 @@ def time_events(t, fn, reps):
     return out
 
 
-def sub_benchmarks(t, peaks, quick):
-    """Secondary sub-paths on one GPU: evaluate, kNN, resample."""
+def sub_benchmarks(t, peaks, quick, cpu=True):
+    """Secondary sub-paths on one GPU: evaluate, kNN, resample; each with the device
+    rate + roofline, the end-to-end rate through the host API and (cpu=True) the CPU
+    reference of that sub-path on a bounded sample."""
+    cores = os.cpu_count() or 1
     import ctypes
 
     from kdsource_b200 import _lib, kde
@@ -229,6 +232,25 @@ def sub_benchmarks(t, peaks, quick):
                      "peak": peaks["ffma2"] / 1e9, "unit": "Glane-op/s",
                      "frac": pairs * 13 / (ms * 1e-3) / peaks["ffma2"],
                      "per_unit": "13 FP32 lane-ops + 1 MUFU per pair (d=6)", "traffic": None}}
+    if cpu:
+        from oracle import kds_oracle as O
+
+        mq = 20_000  # bounded sample: 1e5 sources x 2e4 queries = 2e9 pairs
+        t0 = time.perf_counter()
+        O.kde_sum_c(data, w, bw, q[:mq], nthreads=cores)
+        dt = time.perf_counter() - t0
+        sub["evaluate"]["cpu_baseline"] = {
+            "value": N * mq / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": "dense fp64 sum, 1e5 sources x {} queries ({:.1f} s)".format(mq, dt)}
+    # e2e through KDSource-level API: host (M,6) fp64 in, densities out
+    Me = min(M, 400_000)
+    t.cuda.synchronize()
+    t0 = time.perf_counter()
+    k.evaluate(q[:Me])
+    dt = time.perf_counter() - t0
+    sub["evaluate"]["e2e"] = {"value": N * Me / dt, "unit": "pairs/s",
+                              "h2d_bytes_per_step": Me * 6 * 8, "d2h_bytes_per_step": Me * 8,
+                              "api": "TreeKDE.evaluate(host array), M={}".format(Me)}
     # --- kNN: k=10, batches of 1e4 (reference default), fp64 exact mode
     Nk = 200_000 if quick else 1_000_000
     _, wk, _, _, dk = synthetic_scaled(Nk, seed=99)
@@ -250,7 +272,29 @@ def sub_benchmarks(t, peaks, quick):
         ms = float(np.median(time_events(t, kn, 3)))
         pk = float(np.sum(np.diff(off).astype(np.float64) ** 2))
         res[prec] = {"pairs_per_s": pk / (ms * 1e-3), "ms": ms}
-    sub["knn"] = {"workload": "N={:g}, k=10, batch_size=1e4, d=6".format(Nk), **res}
+    # fp64 pipe: d subtractions + d multiplies + (d-1) additions per pair, no FMA
+    # contraction (bit-exact with numpy/sklearn): 3d-1 DP ops per pair
+    sub["knn"] = {"workload": "N={:g}, k=10, batch_size=1e4, d=6".format(Nk), **res,
+                  "per_unit": "17 fp64 ops (f64 mode) / 12 fp32 lane-ops (f32 mode) per pair"}
+    t0 = time.perf_counter()
+    kth, _, _ = kde.knn_batched(dk, 11, off)
+    dt = time.perf_counter() - t0
+    sub["knn"]["e2e"] = {"value": pk / dt, "unit": "pairs/s", "h2d_bytes_per_step": Nk * 6 * 8,
+                         "d2h_bytes_per_step": Nk * 8, "api": "kde.knn_batched(host array)"}
+    if cpu:
+        from sklearn.neighbors import NearestNeighbors
+
+        nb_s = 20  # bounded sample: the first 20 batches, sklearn as kde.py:93-97 calls it
+        t0 = time.perf_counter()
+        for b in range(nb_s):
+            blk = dk[off[b]:off[b + 1]]
+            NearestNeighbors(n_neighbors=11, n_jobs=-1).fit(blk).kneighbors(blk)
+        dt = time.perf_counter() - t0
+        sub["knn"]["cpu_baseline"] = {
+            "value": float(np.sum(np.diff(off[:nb_s + 1]).astype(np.float64) ** 2)) / dt,
+            "unit": "pairs/s (dense-equivalent)", "cores": cores, "kind": "reference",
+            "sample": "sklearn NearestNeighbors(k+1, n_jobs=-1) kd-tree on the first {} batches "
+                      "({:.1f} s)".format(nb_s, dt)}
     # --- resample: N=1e7 adaptive-bw sources (config 4), 1e8 particles per step
     Ns = 1_000_000 if quick else 10_000_000
     nout = 10_000_000 if quick else 100_000_000
@@ -273,7 +317,84 @@ def sub_benchmarks(t, peaks, quick):
                      "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": bytes_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "per_unit": "76 B per particle (40 read + 36 written)", "traffic": None}}
+    if cpu:
+        sub["resample"]["cpu_baseline"] = cpu_resample_baseline(ps, ws_, bws, sc_, cores)
+    sub["resample"]["e2e"] = resample_e2e(ps, ws_, bws, gs_, sc_, quick)
     return sub
+
+
+def cpu_resample_baseline(ps, ws_, bws, sc_, cores):
+    """The reference's own C sampler (clib/src compiled in place -> oracle/_ref) over
+    an in-memory list with an inlined xorshift generator, single thread (the
+    reference has no threaded sampler); oracle port if _ref was not built."""
+    import tempfile
+
+    from oracle import kds_oracle as O
+
+    n = 10_000_000
+    Nl = min(len(ps), 1_000_000)
+    metrics = [("Lethargy", sc_[:1], [10.0]),
+               ("SurfXY", sc_[1:3], [-np.inf, np.inf, -np.inf, np.inf, 0.0]),
+               ("Isotrop", sc_[3:6], [0, 0, 1])]
+    if O.ref_lib() is not None:
+        with tempfile.NamedTemporaryFile(suffix="_bws") as fh:
+            bws[:Nl].astype(np.float32).tofile(fh)
+            fh.flush()
+            t0 = time.perf_counter()
+            O.ref_sampler(ps[:Nl], ws_[:Nl], 2112, metrics, "g", 1.0, n, seed=5, bwfile=fh.name)
+            dt = time.perf_counter() - t0
+        kind = "reference"
+        what = "KDS_rand_sample2 loop of the reference C library"
+    else:
+        t0 = time.perf_counter()
+        O.resample(ps[:Nl], ws_[:Nl], bws[:Nl], O.make_geom(metrics), n, seed=5)
+        dt = time.perf_counter() - t0
+        kind = "port"
+        what = "oracle C restatement"
+    return {"value": n / dt, "unit": "particles/s", "cores": 1, "kind": kind,
+            "sample": "{}: {} particles from a {}-particle in-memory list, no file output "
+                      "({:.1f} s)".format(what, n, Nl, dt)}
+
+
+def resample_e2e(ps, ws_, bws, gs_, sc_, quick):
+    """kdsource-resample end to end: XML + MCPL list on disk -> resample_to_mcpl ->
+    gzip-compressed MCPL-3 file (the call of python/kdsource/resample.py:2-49)."""
+    import shutil
+    import tempfile
+
+    import kdsource_b200.api as kds
+    from kdsource_b200 import mcpl
+
+    Nl = min(len(ps), 1_000_000)
+    nout = 2_000_000 if quick else 20_000_000
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.mkdtemp(prefix="kdsb_bench_", dir=base)
+    cwd = os.getcwd()
+    try:
+        os.chdir(tmp)
+        pp = ps[:Nl]
+        mcpl.write_mcpl_file("list.mcpl.gz", ekin=pp[:, 0], x=pp[:, 1], y=pp[:, 2], z=pp[:, 3],
+                             ux=pp[:, 4], uy=pp[:, 5], uz=pp[:, 6], time=pp[:, 7],
+                             weight=ws_[:Nl], pdgcode=2112, srcname="synthetic")
+        src = kds.KDSource(kds.PList("list.mcpl.gz"), gs_, bw=bws[:Nl].astype(np.float64))
+        src.fit(scaling=sc_)
+        xml = src.save("src.xml", adjust_N=False)
+        res = {}
+        for level in (1, 0):
+            t0 = time.perf_counter()
+            kds.resample_to_mcpl(xml, "out.mcpl.gz", nout, rng=1, force=True,
+                                 compresslevel=level)
+            dt = time.perf_counter() - t0
+            res["gzip{}".format(level)] = {"particles_per_s": nout / dt, "s": dt,
+                                            "file_bytes": os.path.getsize("out.mcpl.gz")}
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"value": res["gzip1"]["particles_per_s"], "unit": "particles/s",
+            "api": "resample_to_mcpl(xml, out.mcpl.gz, {}) incl. XML/MCPL read, upload, "
+                   "D2H and gzip level 1 to {}".format(nout, base or "tmp"),
+            "d2h_bytes_per_step": 36 * nout, "h2d_bytes_per_step": Nl * 76,
+            "stored_gzip_level0": res["gzip0"], "gzip_level1": res["gzip1"]}
 
 
 def run_ours(args):
@@ -378,7 +499,10 @@ def run_ours(args):
     cpu = None
     if world == 1:
         if not args.no_sub:
-            sub = sub_benchmarks(t, peaks, args.quick)
+            import contextlib
+
+            with contextlib.redirect_stdout(sys.stderr):  # the API prints progress lines
+                sub = sub_benchmarks(t, peaks, args.quick)
         v, dt, n = cpu_mlcv_baseline(data, w, bw, grid)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "first {} particles, G={}, K={} ({:.1f} s)".format(n, G_MLCV, K_MLCV, dt)}

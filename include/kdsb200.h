@@ -53,7 +53,21 @@ int kdsb200_eval_nsplit(uint64_t N, uint64_t M);
 int kdsb200_kde_eval_f32(const float* d_packed, uint64_t N, int D, const float* d_qT, uint64_t M,
                          uint64_t Mpad, double cutoff, double out_scale, int nsplit,
                          double* d_partial, double* d_out, void* stream);
+/* Same with a kernel selector -- the kernel names the reference hands to KDEpy
+ * (kdsource.py:60-65): 0 gaussian (as above), 1 epa, 2 box.  For 1 and 2 the sources
+ * are packed with mode 1 and the bandwidth replaced by the support radius
+ * R_i = h_i*sqrt(5) (epa) / h_i*sqrt(3) (box), KDEpy's unit-variance scaling; then
+ * out[m] = out_scale * sum_i c_i * max(0, 1-u) (epa) or c_i*[u<1] (box),
+ * u = |q_m-x_i|^2/R_i^2; `cutoff` is ignored (the support is finite). */
+int kdsb200_kde_eval_kernel_f32(const float* d_packed, uint64_t N, int D, const float* d_qT,
+                                uint64_t M, uint64_t Mpad, int kernel, double cutoff,
+                                double out_scale, int nsplit, double* d_partial, double* d_out,
+                                void* stream);
 /* fp64 mode (1e-12 parity).  d_scratch: 2N + nsplit*M doubles. */
+int kdsb200_kde_eval_kernel_f64(const double* d_data, const double* d_w, const double* d_bw,
+                                double bw_scalar, uint64_t N, int D, double w_scale,
+                                const double* d_pts, uint64_t M, int kernel, double cutoff,
+                                int nsplit, double* d_scratch, double* d_out, void* stream);
 int kdsb200_kde_eval_f64(const double* d_data, const double* d_w, const double* d_bw,
                          double bw_scalar, uint64_t N, int D, double w_scale,
                          const double* d_pts, uint64_t M, double cutoff, int nsplit,

@@ -67,7 +67,12 @@ constexpr int EV_THREADS = 256;
 constexpr int EV_Q = 4;
 constexpr int EV_STAGES = 3;
 
-template <int D, bool CUT>
+// KERN: 0 Gaussian (rows as above); 1 Epanechnikov, 2 box -- KDEpy's radially
+// symmetric finite-support kernels (kernel names of python/kdsource/kdsource.py:60-65):
+// sources packed with mode 1 and h replaced by the support radius R_i, so u = |q-x|^2/R_i^2
+// and the last row is the linear coefficient c_i; epa adds c_i*max(0, 1-u), box adds c_i
+// where u < 1.
+template <int D, bool CUT, int KERN>
 __global__ void __launch_bounds__(EV_THREADS, 2)
     kde_eval_kernel(const float* __restrict__ packed, uint32_t n_tiles, uint32_t tiles_per_split,
                     const float* __restrict__ qT, uint64_t Mpad, float cut2, double out_scale,
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(EV_THREADS, 2)
       }
 #pragma unroll
       for (int qi = 0; qi < EV_Q; qi++) {
-        f2_t tA = CUT ? 0ull : l01, tB = CUT ? 0ull : l23;
+        f2_t tA = (CUT || KERN) ? 0ull : l01, tB = (CUT || KERN) ? 0ull : l23;
 #pragma unroll
         for (int k = 0; k < D; k++) {
           const f2_t qq = f2_pack(q[qi][k], q[qi][k]);
@@ -151,7 +156,24 @@ __global__ void __launch_bounds__(EV_THREADS, 2)
           tB = f2_fma(dB, dB, tB);
         }
         float eA0, eA1, eB0, eB1;
-        if (CUT) {
+        if (KERN) {
+          float u0, u1, u2, u3, g0, g1, g2, g3;
+          f2_unpack(tA, u0, u1);
+          f2_unpack(tB, u2, u3);
+          f2_unpack(l01, g0, g1);
+          f2_unpack(l23, g2, g3);
+          if (KERN == 1) {
+            eA0 = g0 * fmaxf(1.f - u0, 0.f);
+            eA1 = g1 * fmaxf(1.f - u1, 0.f);
+            eB0 = g2 * fmaxf(1.f - u2, 0.f);
+            eB1 = g3 * fmaxf(1.f - u3, 0.f);
+          } else {
+            eA0 = u0 < 1.f ? g0 : 0.f;
+            eA1 = u1 < 1.f ? g1 : 0.f;
+            eB0 = u2 < 1.f ? g2 : 0.f;
+            eB1 = u3 < 1.f ? g3 : 0.f;
+          }
+        } else if (CUT) {
           float u0, u1, u2, u3, m0, m1, m2, m3, g0, g1, g2, g3;
           f2_unpack(tA, u0, u1);
           f2_unpack(tB, u2, u3);
@@ -199,21 +221,22 @@ __global__ void reduce_splits_kernel(const double* __restrict__ partial, int nsp
 
 template <int D>
 static int launch_eval(const float* packed, uint32_t n_tiles, uint32_t tps, int nsplit,
-                       const float* qT, uint64_t Mpad, float cut2, double out_scale, double* out,
-                       cudaStream_t st) {
+                       const float* qT, uint64_t Mpad, float cut2, int kern, double out_scale,
+                       double* out, cudaStream_t st) {
   const size_t smem = (size_t)EV_STAGES * (D + 2) * TS * sizeof(float);
   dim3 grid((unsigned)(Mpad / (EV_THREADS * EV_Q)), (unsigned)nsplit);
-  if (cut2 > 0.f) {
-    KDSB_CUDA(cudaFuncSetAttribute(kde_eval_kernel<D, true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kde_eval_kernel<D, true><<<grid, EV_THREADS, smem, st>>>(packed, n_tiles, tps, qT, Mpad, cut2,
-                                                             out_scale, out);
-  } else {
-    KDSB_CUDA(cudaFuncSetAttribute(kde_eval_kernel<D, false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kde_eval_kernel<D, false><<<grid, EV_THREADS, smem, st>>>(packed, n_tiles, tps, qT, Mpad,
-                                                              cut2, out_scale, out);
-  }
+#define KDSB_EV(CUTV, KV)                                                                   \
+  do {                                                                                      \
+    KDSB_CUDA(cudaFuncSetAttribute(kde_eval_kernel<D, CUTV, KV>,                            \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kde_eval_kernel<D, CUTV, KV><<<grid, EV_THREADS, smem, st>>>(packed, n_tiles, tps, qT,   \
+                                                                 Mpad, cut2, out_scale, out); \
+  } while (0)
+  if (kern == 1) KDSB_EV(false, 1);
+  else if (kern == 2) KDSB_EV(false, 2);
+  else if (cut2 > 0.f) KDSB_EV(true, 0);
+  else KDSB_EV(false, 0);
+#undef KDSB_EV
   KDSB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -224,11 +247,13 @@ static int launch_eval(const float* packed, uint32_t n_tiles, uint32_t tps, int 
 constexpr int E64_THREADS = 128;
 constexpr int E64_TILE = 256;
 
+// kern 0: coef*exp(-r2*ih2), ih2 = 1/(2h^2); kern 1/2: ih2 = 1/R^2 (support radius),
+// coef*max(0, 1 - r2*ih2) / coef where r2*ih2 < 1
 template <int D>
 __global__ void __launch_bounds__(E64_THREADS)
     kde_eval_f64_kernel(const double* __restrict__ data, const double* __restrict__ coef,
                         const double* __restrict__ ih2, uint64_t N, uint64_t n_per_split,
-                        const double* __restrict__ pts, uint64_t M, double cut2,
+                        const double* __restrict__ pts, uint64_t M, double cut2, int kern,
                         double* __restrict__ out, uint64_t Mstride) {
   __shared__ double sx[E64_TILE * D];
   __shared__ double sc[E64_TILE];
@@ -256,21 +281,41 @@ __global__ void __launch_bounds__(E64_THREADS)
         const double t = q[k] - sx[j * D + k];
         r2 += t * t;
       }
-      if (r2 <= cut2) acc += sc[j] * exp(-r2 * sh[j]);
+      if (kern == 0) {
+        if (r2 <= cut2) acc += sc[j] * exp(-r2 * sh[j]);
+      } else {
+        const double u = r2 * sh[j];
+        if (u < 1.0) acc += kern == 1 ? sc[j] * (1.0 - u) : sc[j];
+      }
     }
   }
   if (m < M) out[(uint64_t)blockIdx.y * Mstride + m] = acc;
 }
 
+// log of the volume of the D-dimensional unit ball
+__host__ __device__ inline double log_unit_ball(int D) {
+  return 0.5 * D * 1.1447298858494001741434273513531 - lgamma(0.5 * D + 1.0);
+}
+
 __global__ void coef_f64_kernel(const double* __restrict__ w, const double* __restrict__ bw,
-                                double bw_scalar, uint64_t N, int D, double w_scale,
+                                double bw_scalar, uint64_t N, int D, double w_scale, int kern,
                                 double* __restrict__ coef, double* __restrict__ ih2) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const double h = bw ? bw[i] : bw_scalar;
-  const double lognorm = -0.5 * D * 1.8378770664093454835606594728112;  // log(2 pi)
-  coef[i] = (w ? w[i] : 1.0) * w_scale * exp(lognorm - D * log(h));
-  ih2[i] = 0.5 / (h * h);
+  const double wi = (w ? w[i] : 1.0) * w_scale;
+  if (kern == 0) {
+    const double lognorm = -0.5 * D * 1.8378770664093454835606594728112;  // log(2 pi)
+    coef[i] = wi * exp(lognorm - D * log(h));
+    ih2[i] = 0.5 / (h * h);
+  } else {
+    // KDEpy scales finite-support kernels to unit variance: R = h / sqrt(var),
+    // var = 1/5 (epa), 1/3 (box)
+    const double R = h * (kern == 1 ? 2.2360679774997896964 : 1.7320508075688772935);
+    const double norm = (kern == 1 ? 0.5 * (D + 2) : 1.0) * exp(-log_unit_ball(D));
+    coef[i] = wi * norm * exp(-D * log(R));
+    ih2[i] = 1.0 / (R * R);
+  }
 }
 
 }  // namespace kdsb
@@ -351,8 +396,20 @@ int kdsb200_eval_nsplit(uint64_t N, uint64_t M) {
 int kdsb200_kde_eval_f32(const float* d_packed, uint64_t N, int D, const float* d_qT, uint64_t M,
                          uint64_t Mpad, double cutoff, double out_scale, int nsplit,
                          double* d_partial, double* d_out, void* stream) {
+  return kdsb200_kde_eval_kernel_f32(d_packed, N, D, d_qT, M, Mpad, 0, cutoff, out_scale, nsplit,
+                                     d_partial, d_out, stream);
+}
+
+int kdsb200_kde_eval_kernel_f32(const float* d_packed, uint64_t N, int D, const float* d_qT,
+                                uint64_t M, uint64_t Mpad, int kernel, double cutoff,
+                                double out_scale, int nsplit, double* d_partial, double* d_out,
+                                void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) return 0;
+  if (kernel < 0 || kernel > 2) {
+    set_error("kde_eval: kernel=%d must be 0 (gaussian), 1 (epa) or 2 (box)", kernel);
+    return 1;
+  }
   if (Mpad % (EV_THREADS * EV_Q) != 0 || Mpad < M) {
     set_error("kde_eval_f32: Mpad=%llu must be a multiple of %d and >= M",
               (unsigned long long)Mpad, EV_THREADS * EV_Q);
@@ -378,7 +435,8 @@ int kdsb200_kde_eval_f32(const float* d_packed, uint64_t N, int D, const float* 
   switch (D) {
 #define KDSB_CASE(d)                                                                         \
   case d:                                                                                    \
-    rc = launch_eval<d>(d_packed, ntl, tps, nsplit, d_qT, Mpad, cut2, out_scale, target, st); \
+    rc = launch_eval<d>(d_packed, ntl, tps, nsplit, d_qT, Mpad, cut2, kernel, out_scale, target, \
+                        st);                                                                 \
     break;
     KDSB_CASE(1)
     KDSB_CASE(2)
@@ -407,13 +465,25 @@ int kdsb200_kde_eval_f64(const double* d_data, const double* d_w, const double* 
                          const double* d_pts, uint64_t M, double cutoff, int nsplit,
                          double* d_scratch /* 2N + nsplit*M doubles */, double* d_out,
                          void* stream) {
+  return kdsb200_kde_eval_kernel_f64(d_data, d_w, d_bw, bw_scalar, N, D, w_scale, d_pts, M, 0,
+                                     cutoff, nsplit, d_scratch, d_out, stream);
+}
+
+int kdsb200_kde_eval_kernel_f64(const double* d_data, const double* d_w, const double* d_bw,
+                                double bw_scalar, uint64_t N, int D, double w_scale,
+                                const double* d_pts, uint64_t M, int kernel, double cutoff,
+                                int nsplit, double* d_scratch, double* d_out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0 || N == 0) return 0;
+  if (kernel < 0 || kernel > 2) {
+    set_error("kde_eval: kernel=%d must be 0 (gaussian), 1 (epa) or 2 (box)", kernel);
+    return 1;
+  }
   double* coef = d_scratch;
   double* ih2 = d_scratch + N;
   double* partial = d_scratch + 2 * N;
   coef_f64_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_w, d_bw, bw_scalar, N, D,
-                                                               w_scale, coef, ih2);
+                                                               w_scale, kernel, coef, ih2);
   KDSB_CUDA(cudaGetLastError());
   if (nsplit < 1) nsplit = 1;
   const uint64_t nps = (N + nsplit - 1) / nsplit;
@@ -425,7 +495,7 @@ int kdsb200_kde_eval_f64(const double* d_data, const double* d_w, const double* 
 #define KDSB_CASE(d)                                                                       \
   case d:                                                                                  \
     kde_eval_f64_kernel<d><<<grid, E64_THREADS, 0, st>>>(d_data, coef, ih2, N, nps, d_pts, \
-                                                         M, cut2, target, M);              \
+                                                         M, cut2, kernel, target, M);      \
     break;
     KDSB_CASE(1)
     KDSB_CASE(2)

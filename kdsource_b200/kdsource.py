@@ -151,12 +151,17 @@ class KDSource:
         rot_keep, rot_p = (None, None)
         if self.geom.rot is not None:
             rot_keep, rot_p = _lib.hostvec(self.geom.rot.inv().as_matrix().reshape(-1))
+        from . import dist as _dist
+
         dev = self.kde._device_state()
         M = len(parts)
-        dens = np.empty(M)
-        jacs = np.empty(M)
-        for s in range(0, M, chunk):
-            n = min(chunk, M - s)
+        # query points are split contiguously over the ranks (sources replicated)
+        rank, world = _dist.rank_world()
+        lo, hi = _dist.shard_range(M, rank, world)
+        dens = np.zeros(M)
+        jacs = np.zeros(M)
+        for s in range(lo, hi, chunk):
+            n = min(chunk, hi - s)
             d_parts = _lib.to_dev(parts[s:s + n])
             d_vecs = _lib.empty(n * D, t.float64)
             d_jac = _lib.empty(n, t.float64)
@@ -166,6 +171,9 @@ class KDSource:
             d_out = self.kde.evaluate_device(d_vecs, n, dev)
             dens[s:s + n] = d_out.cpu().numpy()
             jacs[s:s + n] = d_jac.cpu().numpy()
+        if world > 1:
+            dens = _dist.allreduce_sum_numpy(dens)
+            jacs = _dist.allreduce_sum_numpy(jacs)
         return dens, jacs
 
     def save(self, xmlfilename=None, bwfile=None, adjust_N=True):

@@ -137,13 +137,16 @@ class PList:
         SubElement(pltree, "x2z").text = str(int(self.x2z))
 
     @staticmethod
-    def load(pltree):
-        """Build a PList from a <PList> element (reference plist.py:413-429)."""
+    def load(pltree, set_params=True):
+        """Build a PList from a <PList> element (reference plist.py:413-429).
+        ``set_params=False`` skips the pass over the whole file that computes
+        N / N_eff (the sampler does not need them)."""
         def vec(el):
             return np.array(el.text.split(), dtype="float64") if el.text else None
 
         return PList(pltree[1].text, pt=pltree[0].text, trasl=vec(pltree[2]),
-                     rot=vec(pltree[3]), switch_x2z=bool(int(pltree[4].text)))
+                     rot=vec(pltree[3]), switch_x2z=bool(int(pltree[4].text)),
+                     set_params=set_params)
 
 
 def savessv(*args, **kwargs):

@@ -41,7 +41,7 @@ def open_source(kds_sourcefile, precision="float32"):
         if cand.is_file():
             pltree[1].text = str(cand)
     cwd = os.getcwd()
-    plist = PList.load(pltree)
+    plist = PList.load(pltree, set_params=False)
     geom = Geometry.load(root.find("Geom"))
     scaling = np.array(root.find("scaling").text.split(), dtype="float64")
     bwel = root.find("BW")

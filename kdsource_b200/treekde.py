@@ -11,6 +11,12 @@ Semantics: ``out[m] = sum_i w_i/sum(w) (2 pi)^(-d/2) h_i^-d exp(-|q_m - x_i|^2 /
 (2 h_i^2))``.  ``cutoff=None`` is the exact sum (KDEpy NaiveKDE semantics);
 ``cutoff="treekde"`` applies the hard support radius KDEpy's TreeKDE derives
 from the largest bandwidth; a float is an explicit radius.
+
+``kernel="epa"`` / ``"box"`` (the other two names the reference passes to KDEpy,
+kdsource.py:60-65) are KDEpy's radially symmetric finite-support kernels scaled
+to unit variance: support radius ``R_i = h_i sqrt(5)`` (epa) or ``h_i sqrt(3)``
+(box), ``K = (d+2)/(2 V_d R^d) (1 - r^2/R^2)`` resp. ``1/(V_d R^d)`` inside the
+ball (``V_d`` = volume of the unit d-ball).
 """
 
 import ctypes
@@ -20,6 +26,16 @@ import numpy as np
 from . import _lib
 
 _LOG2E = 1.4426950408889634
+_KERNEL_ID = {"gaussian": 0, "epa": 1, "box": 2}
+_SUPPORT_SCALE = {"epa": np.sqrt(5.0), "box": np.sqrt(3.0)}  # 1/sqrt(var), KDEpy kernel table
+
+
+def unit_ball_volume(d):
+    from math import gamma, pi
+
+    return pi ** (d / 2.0) / gamma(d / 2.0 + 1.0)
+
+
 _KERNEL_ALIASES = {"g": "gaussian", "gaussian": "gaussian", "e": "epa", "epa": "epa",
                    "b": "box", "box": "box"}
 
@@ -78,10 +94,6 @@ class TreeKDE:
         (sources replicated) and the result is assembled on every rank."""
         if self.data is None:
             raise ValueError("Must call fit before evaluating.")
-        if self.kernel != "gaussian":
-            raise NotImplementedError(
-                "only the gaussian kernel is evaluated on the GPU (kernel={!r})".format(
-                    self.kernel))
         pts = np.ascontiguousarray(points, dtype=np.float64)
         if pts.ndim == 1:
             pts = pts.reshape(-1, self.data.shape[1])
@@ -127,6 +139,7 @@ class TreeKDE:
         d = self._dev
         if (d is not None and d["data_ref"] is self.data and d["weights_ref"] is self.weights
                 and d["dtype"] == self.dtype and d["cutoff_spec"] == self.cutoff
+                and d["kernel"] == self.kernel
                 and d["bw_scalar_snap"] == bw_scalar
                 and ((bw_arr is None) == (d["bw_snap"] is None))
                 and (bw_arr is None or np.array_equal(bw_arr, d["bw_snap"]))):
@@ -145,7 +158,9 @@ class TreeKDE:
             center = np.average(self.data, axis=0, weights=w)
         else:
             center = self.data.mean(axis=0)
-        dev = {"N": N, "D": D, "center": center, "cutoff": self._cutoff_radius(hmax),
+        gauss = self.kernel == "gaussian"
+        dev = {"N": N, "D": D, "center": center, "kernel": self.kernel,
+               "cutoff": self._cutoff_radius(hmax) if gauss else 0.0,
                "data_ref": self.data, "weights_ref": self.weights, "dtype": self.dtype,
                "cutoff_spec": self.cutoff, "bw_scalar_snap": bw_scalar,
                "bw_snap": None if bw_arr is None else bw_arr.copy()}
@@ -153,7 +168,7 @@ class TreeKDE:
         d_w = _lib.to_dev(w) if w is not None else None
         d_bw = _lib.to_dev(bw_arr) if bw_arr is not None else None
         w_scale = 1.0 / sumw
-        if self.dtype == "float32":
+        if self.dtype == "float32" and gauss:
             lc_ref = np.log2(wmax * w_scale) - D * np.log2(hmin)
             packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
             cen_keep, cen_p = _lib.hostvec(center)
@@ -162,6 +177,20 @@ class TreeKDE:
                 w_scale, lc_ref, 0, _lib.ptr(packed), _lib.stream()))
             dev["packed"] = packed
             dev["out_scale"] = float(2.0 ** lc_ref * (2 * np.pi) ** (-D / 2))
+        elif self.dtype == "float32":
+            # finite-support kernels: linear coefficients w_i R_i^-D / 2^lc_ref (mode 1)
+            # with the support radius R_i in place of the bandwidth
+            sc = _SUPPORT_SCALE[self.kernel]
+            d_R = _lib.to_dev(bw_arr * sc) if bw_arr is not None else None
+            lc_ref = np.log2(wmax * w_scale) - D * np.log2(hmin * sc)
+            packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
+            cen_keep, cen_p = _lib.hostvec(center)
+            _lib.check(L.kdsb200_pack_sources_f32(
+                _lib.ptr(d_data), _lib.ptr(d_w), _lib.ptr(d_R), bw_scalar * sc, N, D, cen_p,
+                w_scale, lc_ref, 1, _lib.ptr(packed), _lib.stream()))
+            norm = (0.5 * (D + 2) if self.kernel == "epa" else 1.0) / unit_ball_volume(D)
+            dev["packed"] = packed
+            dev["out_scale"] = float(2.0 ** lc_ref * norm)
         else:
             dev.update(d_data=d_data, d_w=d_w, d_bw=d_bw, bw_scalar=bw_scalar,
                        w_scale=w_scale)
@@ -187,16 +216,18 @@ class TreeKDE:
                                                   _lib.ptr(qT), _lib.stream()))
             nsplit = L.kdsb200_eval_nsplit(N, M)
             partial = _lib.empty(nsplit * Mpad, t.float64)
-            _lib.check(L.kdsb200_kde_eval_f32(
-                _lib.ptr(dev["packed"]), N, D, _lib.ptr(qT), M, Mpad, dev["cutoff"],
-                dev["out_scale"], nsplit, _lib.ptr(partial), _lib.ptr(d_out), _lib.stream()))
+            _lib.check(L.kdsb200_kde_eval_kernel_f32(
+                _lib.ptr(dev["packed"]), N, D, _lib.ptr(qT), M, Mpad, _KERNEL_ID[dev["kernel"]],
+                dev["cutoff"], dev["out_scale"], nsplit, _lib.ptr(partial), _lib.ptr(d_out),
+                _lib.stream()))
         else:
             nsplit = max(1, min(64, (4 * 148 * 128) // max(M, 1)))
             scratch = _lib.empty(2 * N + nsplit * M, t.float64)
-            _lib.check(L.kdsb200_kde_eval_f64(
+            _lib.check(L.kdsb200_kde_eval_kernel_f64(
                 _lib.ptr(dev["d_data"]), _lib.ptr(dev["d_w"]), _lib.ptr(dev["d_bw"]),
-                dev["bw_scalar"], N, D, dev["w_scale"], _lib.ptr(d_pts), M, dev["cutoff"],
-                nsplit, _lib.ptr(scratch), _lib.ptr(d_out), _lib.stream()))
+                dev["bw_scalar"], N, D, dev["w_scale"], _lib.ptr(d_pts), M,
+                _KERNEL_ID[dev["kernel"]], dev["cutoff"], nsplit, _lib.ptr(scratch),
+                _lib.ptr(d_out), _lib.stream()))
         return d_out
 
 

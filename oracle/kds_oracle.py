@@ -117,14 +117,42 @@ def normalise_weights(weights, N):
     return w / w.sum()
 
 
-def kde_sum(data, weights, bw, points, cutoff=None, chunk=256):
-    """Gaussian kernel sum (KDEpy Naive/TreeKDE.evaluate with norm=2), the
-    arithmetic behind python/kdsource/kdsource.py:239 and kde.py:146-151:
+def kde_sum(data, weights, bw, points, cutoff=None, chunk=256, kernel="gaussian"):
+    """Kernel sum (KDEpy Naive/TreeKDE.evaluate with norm=2), the arithmetic behind
+    python/kdsource/kdsource.py:239 and kde.py:146-151:
 
         out[m] = sum_i w_i/sum(w) (2 pi)^(-d/2) h_i^-d exp(-|q_m-x_i|^2/(2 h_i^2))
 
-    ``cutoff``: hard support radius (None = exact sum).
+    ``cutoff``: hard support radius (None = exact sum).  ``kernel`` "epa"/"box"
+    (kdsource.py:60-65): KDEpy's radial finite-support kernels, published form
+    (KDEpy is not in the tree -- restated from its documentation, pinned against
+    scikit-learn's KernelDensity in tests/test_oracle.py): bandwidth = standard
+    deviation of the 1-D kernel, so the support radius is R = h/sqrt(var) with
+    var = 1/5 (epa), 1/3 (box); K = (d+2)/(2 V_d R^d)(1 - r^2/R^2) resp. 1/(V_d R^d)
+    for r < R, V_d the volume of the unit d-ball.
     """
+    if kernel in ("epa", "e", "box", "b"):
+        from math import gamma
+
+        data = np.asarray(data, dtype=np.float64)
+        pts = np.asarray(points, dtype=np.float64)
+        N, d = data.shape
+        epa = kernel[0] == "e"
+        wn = normalise_weights(weights, N)
+        R = np.broadcast_to(np.asarray(bw, dtype=np.float64), (N,)) * np.sqrt(5.0 if epa else 3.0)
+        Vd = np.pi ** (d / 2) / gamma(d / 2 + 1)
+        coef = wn * ((d + 2) / 2 if epa else 1.0) / (Vd * R ** d)
+        out = np.empty(len(pts))
+        for s in range(0, len(pts), chunk):
+            q = pts[s:s + chunk]
+            r2 = np.zeros((len(q), N))
+            for k in range(d):
+                t = q[:, k:k + 1] - data[None, :, k]
+                r2 += t * t
+            u = r2 / R ** 2
+            K = np.where(u < 1.0, coef * (1.0 - u) if epa else coef, 0.0)
+            out[s:s + chunk] = K.sum(axis=1)
+        return out
     data = np.asarray(data, dtype=np.float64)
     pts = np.asarray(points, dtype=np.float64)
     N, d = data.shape

@@ -81,6 +81,41 @@ def test_evaluate_cutoff_and_dims(oracle):
     assert one[0] == pytest.approx((2 * np.pi) ** -3 * 0.4 ** -6, rel=1e-6)
 
 
+@pytest.mark.parametrize("kernel", ["epa", "box"])
+def test_evaluate_finite_support_kernels(oracle, scaled, kernel):
+    """KDEpy's radial Epanechnikov / box kernels (kdsource.py:60-65), scalar and
+    per-particle bandwidths: fp64 mode 1e-12, fp32 mode 1e-5 where the kernel is
+    continuous (epa); the box kernel is a step, so a pair within fp32 rounding of
+    the support radius may fall on either side -- bounded by a few coefficients."""
+    from kdsource_b200.treekde import TreeKDE
+
+    data, w, q = scaled["data"][:8000], scaled["w"][:8000], scaled["q"][:1500]
+    rng = np.random.default_rng(5)
+    for bw in (0.45, rng.uniform(0.35, 0.7, len(data))):
+        ref = oracle.kde_sum(data, w, bw, q, kernel=kernel)
+        assert np.count_nonzero(ref) > 500
+        g64 = TreeKDE(kernel=kernel, bw=bw, dtype="float64").fit(data, w).evaluate(q)
+        ok = ref > 0
+        assert np.max(np.abs(g64[ok] / ref[ok] - 1)) < 1e-12
+        assert np.all(g64[~ok] == 0)
+        g32 = TreeKDE(kernel=kernel, bw=bw).fit(data, w).evaluate(q)
+        if kernel == "epa":
+            big = ref > 1e-3 * ref.max()
+            assert np.max(np.abs(g32[big] / ref[big] - 1)) < 1e-5
+            assert np.max(np.abs(g32 - ref)) < 1e-6 * ref.max()
+        else:
+            step = np.max(oracle.kde_sum(data[:1], None, np.min(bw), data[:1], kernel="box")) * (
+                np.max(w) / np.sum(w))
+            assert np.max(np.abs(g32 - ref)) <= 3 * step
+            assert np.mean(np.abs(g32 - ref) <= 1e-5 * np.abs(ref)) > 0.99
+    # dimensions 1..8 and the KDSource-level error estimate constants
+    for d in (1, 2, 4, 8):
+        X, Q = rng.normal(size=(2000, d)), rng.normal(size=(300, d))
+        ref = oracle.kde_sum(X, None, 0.6, Q, kernel=kernel)
+        got = TreeKDE(kernel=kernel, bw=0.6, dtype="float64").fit(X).evaluate(Q)
+        assert np.allclose(got, ref, rtol=1e-12, atol=0), d
+
+
 def test_evaluate_linearity_at_scale(oracle):
     """Size-independent property: density of A u B = weighted mix of densities."""
     from kdsource_b200.treekde import TreeKDE

@@ -125,6 +125,22 @@ def test_kde_sum_vs_independent_libraries(oracle):
         ref_u = np.exp(KernelDensity(kernel="gaussian", bandwidth=h, rtol=0, atol=0)
                        .fit(data).score_samples(pts))
         assert np.allclose(oracle.kde_sum_c(data, None, h, pts), ref_u, rtol=1e-10)
+        # finite-support kernels: sklearn's bandwidth is the support radius
+        for kern, skname, sc in (("epa", "epanechnikov", np.sqrt(5.0)), ("box", "tophat", np.sqrt(3.0))):
+            hk = 0.8
+            kd = KernelDensity(kernel=skname, bandwidth=hk * sc, rtol=0, atol=0)
+            with np.errstate(divide="ignore"):
+                ref = np.exp(kd.fit(data, sample_weight=w).score_samples(pts))
+            ours = oracle.kde_sum(data, w, hk, pts, kernel=kern)
+            inside = ref > 1e-200  # sklearn reports empty balls as exp(-huge), not 0
+            assert np.allclose(ours[inside], ref[inside], rtol=1e-10)
+            assert np.all(ours[~inside] == 0) and np.count_nonzero(inside) > 20
+    # normalisation of the finite-support kernels: integrate over a 2-D grid
+    gx = np.linspace(-3, 3, 601)
+    gpts = np.stack(np.meshgrid(gx, gx, indexing="ij"), axis=-1).reshape(-1, 2)
+    for kern in ("epa", "box"):
+        dens = oracle.kde_sum(np.zeros((1, 2)), None, 0.9, gpts, kernel=kern)
+        assert dens.sum() * (gx[1] - gx[0]) ** 2 == pytest.approx(1.0, rel=5e-3)
     # scipy: covariance = factor^2 * weighted data covariance; whiten so it is h^2 I
     data = rng.normal(size=(600, 2))
     w = rng.uniform(0.5, 1.5, 600)

@@ -52,6 +52,11 @@ dist.barrier()
 pl = kds.PList(tmp + "/list.mcpl.gz")
 src = kds.KDSource(pl, g, bw=0.3)
 src.fit()
+# KDSource.evaluate shards the query points; same densities as the unsharded kernel sum
+qp = parts[:4001].copy()
+ev, er = src.evaluate(qp)
+dens = src.kde.evaluate(g.transform(qp.copy()) / src.scaling, shard=False)
+assert np.allclose(ev, dens / np.prod(src.scaling) * src.J * g.jac(qp.copy()), rtol=1e-12)
 if rank == 0:
     src.save(tmp + "/src.xml", adjust_N=False)
 dist.barrier()
