@@ -1,0 +1,516 @@
+// gzip on the GPU for the resampler's output.
+//
+// The reference writes its resampled list through libmcpl and closes it with
+// mcpl_closeandgzip_outfile (clib/src/resamplemcpl.c:30-46): the product is always a
+// gzip file.  At 1.6e10 particles/s the records exist in HBM long before a host could
+// deflate them (zlib level 1 on 16 cores: ~1e7 particles/s), so the compression runs
+// on the device too: the record stream is cut into members of `member_bytes`, each
+// member becomes one complete gzip member (RFC 1952) holding a single dynamic-Huffman
+// deflate block (RFC 1951) of literals only -- no LZ77 matches; MCPL-3 records are
+// floats, the gain of level-1 zlib over an order-0 Huffman code is a few percent --
+// and the members are laid out back to back.  Concatenated gzip members are a valid
+// gzip file for zlib's gzread (libmcpl), gzip(1) and Python's gzip module.
+//
+//   pass 1 (gz_size_kernel)   per member: code-length sum per thread, CRC-32
+//   pass 2 (gz_scan_kernel)   member sizes -> byte offsets (all multiples of 4: the
+//                             gzip FNAME field carries 0-3 filler characters)
+//   pass 3 (gz_encode_kernel) header, bit-packed codes, end-of-block, CRC-32, ISIZE
+//
+// One Huffman table serves every member: it is built on the host
+// (kdsb200_gz_build_table) from a byte histogram of the first records
+// (kdsb200_gz_histogram), with every symbol kept encodable.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "kdsb200.h"
+
+namespace kdsb {
+
+constexpr int GZ_THREADS = 256;
+constexpr uint32_t CRC_POLY = 0xEDB88320u;  // reflected CRC-32 (IEEE 802.3), as gzip uses
+
+// device image of the table (uploaded at the start of every compress call)
+struct GzDev {
+  uint32_t entry[257];   // len << 16 | bit-reversed code
+  uint32_t hdr_bits;
+  uint32_t hdr[64];
+  uint32_t crc_tab[256];
+  uint32_t crc_mat[6][32];  // advance-by-(chunk << j)-zero-bytes operators, j = 0..5
+  uint32_t init_full, init_last;  // M_n(0xffffffff) for a full / the last member
+};
+
+// ---- host: Huffman code lengths, canonical codes, deflate block header --------
+static void huffman_lengths(const uint64_t* freq, int n, int maxlen, uint8_t* len) {
+  std::vector<uint64_t> f(freq, freq + n);
+  for (;;) {
+    // plain O(n^2) two-smallest merging; n <= 257
+    struct Node { uint64_t w; int l, r; };
+    std::vector<Node> nodes;
+    std::vector<int> live;
+    for (int i = 0; i < n; i++)
+      if (f[i] > 0) {
+        nodes.push_back({f[i], -1 - i, 0});
+        live.push_back((int)nodes.size() - 1);
+      }
+    for (int i = 0; i < n; i++) len[i] = 0;
+    if (live.size() == 1) {
+      len[-1 - nodes[live[0]].l] = 1;
+      return;
+    }
+    while (live.size() > 1) {
+      auto by_w = [&](int a, int b) { return nodes[a].w < nodes[b].w || (nodes[a].w == nodes[b].w && a < b); };
+      std::sort(live.begin(), live.end(), by_w);
+      const int a = live[0], b = live[1];
+      nodes.push_back({nodes[a].w + nodes[b].w, a, b});
+      live.erase(live.begin(), live.begin() + 2);
+      live.push_back((int)nodes.size() - 1);
+    }
+    // depth of every leaf
+    std::vector<std::pair<int, int>> stack{{live[0], 0}};
+    int deepest = 0;
+    while (!stack.empty()) {
+      auto [id, d] = stack.back();
+      stack.pop_back();
+      if (nodes[id].l < 0) {
+        len[-1 - nodes[id].l] = (uint8_t)d;
+        deepest = std::max(deepest, d);
+      } else {
+        stack.push_back({nodes[id].l, d + 1});
+        stack.push_back({nodes[id].r, d + 1});
+      }
+    }
+    if (deepest <= maxlen) return;
+    for (int i = 0; i < n; i++)  // flatten the distribution and retry
+      if (f[i] > 0) f[i] = (f[i] + 1) / 2;
+  }
+}
+
+static void canonical_codes(const uint8_t* len, int n, uint32_t* code_rev) {
+  uint32_t bl_count[16] = {0}, next[16] = {0};
+  for (int i = 0; i < n; i++) bl_count[len[i]]++;
+  bl_count[0] = 0;
+  uint32_t c = 0;
+  for (int b = 1; b < 16; b++) {
+    c = (c + bl_count[b - 1]) << 1;
+    next[b] = c;
+  }
+  for (int i = 0; i < n; i++) {
+    code_rev[i] = 0;
+    if (!len[i]) continue;
+    uint32_t v = next[len[i]]++, r = 0;
+    for (int b = 0; b < len[i]; b++) r |= ((v >> b) & 1u) << (len[i] - 1 - b);  // MSB-first -> LSB-first
+    code_rev[i] = r;
+  }
+}
+
+struct BitWriter {
+  uint32_t* w;
+  uint32_t nbits = 0, cap;
+  BitWriter(uint32_t* words, uint32_t cap_bits) : w(words), cap(cap_bits) {}
+  bool put(uint32_t v, int n) {
+    for (int b = 0; b < n; b++, nbits++) {
+      if (nbits >= cap) return false;
+      if ((v >> b) & 1u) w[nbits >> 5] |= 1u << (nbits & 31);
+    }
+    return true;
+  }
+};
+
+// GF(2) operators on the CRC register: column c of M = image of bit c
+static void mat_square(const uint32_t* m, uint32_t* out) {
+  for (int c = 0; c < 32; c++) {
+    uint32_t v = m[c], r = 0;
+    for (int b = 0; v; b++, v >>= 1)
+      if (v & 1u) r ^= m[b];
+    out[c] = r;
+  }
+}
+static uint32_t mat_apply(const uint32_t* m, uint32_t v) {
+  uint32_t r = 0;
+  for (int b = 0; v; b++, v >>= 1)
+    if (v & 1u) r ^= m[b];
+  return r;
+}
+// operator "append n zero bytes" by square-and-multiply on the one-zero-bit operator
+static void crc_advance_matrix(uint64_t nbytes, uint32_t* out) {
+  uint32_t sq[32], acc[32], tmp[32];
+  sq[0] = CRC_POLY;  // one zero bit: r -> (r >> 1) ^ (r & 1 ? poly : 0)
+  for (int c = 1; c < 32; c++) sq[c] = 1u << (c - 1);
+  for (int c = 0; c < 32; c++) acc[c] = 1u << c;  // identity
+  uint64_t nb = nbytes * 8;
+  while (nb) {
+    if (nb & 1) {
+      for (int c = 0; c < 32; c++) tmp[c] = mat_apply(sq, acc[c]);
+      memcpy(acc, tmp, sizeof(acc));
+    }
+    mat_square(sq, tmp);
+    memcpy(sq, tmp, sizeof(sq));
+    nb >>= 1;
+  }
+  memcpy(out, acc, sizeof(acc));
+}
+
+// ---- device ---------------------------------------------------------------------
+__global__ void gz_hist_kernel(const unsigned char* __restrict__ data, uint64_t nbytes,
+                               unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i + 4 <= nbytes;
+       i += (uint64_t)gridDim.x * blockDim.x * 4) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(data + i);
+    atomicAdd(&h[w & 255u], 1u);
+    atomicAdd(&h[(w >> 8) & 255u], 1u);
+    atomicAdd(&h[(w >> 16) & 255u], 1u);
+    atomicAdd(&h[w >> 24], 1u);
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+// chunk of thread t in a member of nb bytes: right-aligned frames of `chunk` bytes, so
+// only leading threads are empty / partial (leading zero bytes leave a zero CRC
+// register unchanged, which keeps the combination tree uniform)
+__device__ __forceinline__ void gz_chunk(uint32_t nb, uint32_t chunk, int t, uint32_t& lo,
+                                         uint32_t& hi) {
+  const int64_t h = (int64_t)nb - (int64_t)(GZ_THREADS - 1 - t) * chunk;
+  if (h <= 0) {
+    lo = hi = 0;
+    return;
+  }
+  hi = (uint32_t)h;
+  lo = h > (int64_t)chunk ? (uint32_t)(h - chunk) : 0u;
+}
+
+__device__ __forceinline__ uint32_t gz_mat_apply(const uint32_t* m, uint32_t v) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int b = 0; b < 32; b++) r ^= ((v >> b) & 1u) ? m[b] : 0u;
+  return r;
+}
+
+__global__ void __launch_bounds__(GZ_THREADS)
+    gz_size_kernel(const unsigned char* __restrict__ data, uint64_t nbytes, uint32_t member_bytes,
+                   const GzDev* __restrict__ T, uint32_t* __restrict__ thread_bits,
+                   uint32_t* __restrict__ member_bits, uint32_t* __restrict__ member_crc) {
+  __shared__ uint32_t s_len[256], s_crc[256], s_mat[6][32], s_red[GZ_THREADS / 32],
+      s_wcrc[GZ_THREADS / 32];
+  const int t = threadIdx.x;
+  s_len[t] = T->entry[t] >> 16;
+  s_crc[t] = T->crc_tab[t];
+  if (t < 192) s_mat[t / 32][t % 32] = T->crc_mat[t / 32][t % 32];
+  __syncthreads();
+  const uint64_t m = blockIdx.x;
+  const uint64_t base = m * member_bytes;
+  const uint32_t nb = (uint32_t)min((uint64_t)member_bytes, nbytes - base);
+  uint32_t lo, hi;
+  gz_chunk(nb, member_bytes / GZ_THREADS, t, lo, hi);
+  uint32_t bits = 0, crc = 0;
+  const unsigned char* p = data + base;
+  for (uint32_t o = lo; o < hi; o += 4) {  // chunks are multiples of 4 bytes
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + o));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t b = (w >> (8 * k)) & 255u;
+      bits += s_len[b];
+      crc = s_crc[(crc ^ b) & 255u] ^ (crc >> 8);
+    }
+  }
+  thread_bits[m * GZ_THREADS + t] = bits;
+  // total bits of the member
+  uint32_t s = bits;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  // CRC of the concatenation: c = M_j(left) ^ right, level by level
+  const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const uint32_t left = __shfl_up_sync(0xffffffffu, crc, 1 << j);
+    if (((lane + 1) & ((2 << j) - 1)) == 0) crc = gz_mat_apply(s_mat[j], left) ^ crc;
+  }
+  if (lane == 0) s_red[warp] = s;
+  if (lane == 31) s_wcrc[warp] = crc;
+  __syncthreads();
+  if (t == 0) {
+    uint32_t tot = 0, c = 0;
+    for (int w = 0; w < GZ_THREADS / 32; w++) {
+      tot += s_red[w];
+      c = gz_mat_apply(s_mat[5], c) ^ s_wcrc[w];
+    }
+    member_bits[m] = tot;
+    const bool last = base + nb >= nbytes;
+    member_crc[m] = c ^ (last ? T->init_last : T->init_full) ^ 0xffffffffu;
+  }
+}
+
+// member m: 10-byte gzip header + k filler characters + NUL + deflate + CRC32 + ISIZE,
+// k chosen so the member is a multiple of 4 bytes
+__device__ __forceinline__ uint32_t gz_member_size(uint32_t bits, uint32_t hdr_bits,
+                                                   uint32_t eob_len, uint32_t& k) {
+  const uint32_t D = (hdr_bits + bits + eob_len + 7) / 8;
+  k = (4u - ((19u + D) & 3u)) & 3u;
+  return 19u + k + D;
+}
+
+__global__ void __launch_bounds__(GZ_THREADS)
+    gz_scan_kernel(const uint32_t* __restrict__ member_bits, uint64_t n_members,
+                   const GzDev* __restrict__ T, uint64_t* __restrict__ member_off,
+                   uint64_t* __restrict__ total) {
+  __shared__ uint64_t wsum[GZ_THREADS / 32];
+  __shared__ uint64_t carry_s;
+  const uint32_t hb = T->hdr_bits, eob = T->entry[256] >> 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint64_t b0 = 0; b0 < n_members; b0 += GZ_THREADS) {
+    const uint64_t i = b0 + threadIdx.x;
+    uint32_t k;
+    const uint64_t v = i < n_members ? gz_member_size(member_bits[i], hb, eob, k) : 0;
+    uint64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint64_t woff = 0, tot = 0;
+    for (int w = 0; w < GZ_THREADS / 32; w++) {
+      if (w < warp) woff += wsum[w];
+      tot += wsum[w];
+    }
+    const uint64_t carry = carry_s;
+    if (i < n_members) member_off[i] = carry + woff + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+
+__device__ __forceinline__ void gz_or_byte(uint32_t* words, uint32_t byte_pos, uint32_t v) {
+  atomicOr(words + (byte_pos >> 2), v << (8 * (byte_pos & 3u)));
+}
+
+__global__ void __launch_bounds__(GZ_THREADS)
+    gz_encode_kernel(const unsigned char* __restrict__ data, uint64_t nbytes, uint32_t member_bytes,
+                     const GzDev* __restrict__ T, const uint32_t* __restrict__ thread_bits,
+                     const uint32_t* __restrict__ member_bits,
+                     const uint32_t* __restrict__ member_crc,
+                     const uint64_t* __restrict__ member_off, uint64_t capacity,
+                     unsigned char* __restrict__ out) {
+  __shared__ uint32_t s_ent[257], s_scan[GZ_THREADS / 32];
+  const int t = threadIdx.x;
+  s_ent[t] = T->entry[t];
+  if (t == 0) s_ent[256] = T->entry[256];
+  const uint64_t m = blockIdx.x;
+  const uint64_t base = m * member_bytes;
+  const uint32_t nb = (uint32_t)min((uint64_t)member_bytes, nbytes - base);
+  const uint32_t hb = T->hdr_bits, eob_len = T->entry[256] >> 16;
+  uint32_t k;
+  const uint32_t msize = gz_member_size(member_bits[m], hb, eob_len, k);
+  const uint64_t off = member_off[m];
+  if (off + msize > capacity) return;  // reported by the host from the scan total
+  uint32_t* words = reinterpret_cast<uint32_t*>(out + off);  // off % 4 == 0
+  // exclusive prefix of the threads' bit counts
+  const uint32_t mybits = thread_bits[m * GZ_THREADS + t];
+  const int lane = t & 31, warp = t >> 5;
+  uint32_t inc = mybits;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) s_scan[warp] = inc;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < warp; w++) woff += s_scan[w];
+  const uint32_t B0 = 8u * (11u + k);  // first deflate bit
+  const uint32_t start = B0 + hb + woff + inc - mybits;
+
+  // gzip header (thread 0), block header bits (threads 0..), trailer (thread 1)
+  if (t == 0) {
+    atomicOr(words + 0, 0x08088b1fu);  // ID1 ID2 CM=8 FLG=FNAME; MTIME = 0
+    gz_or_byte(words, 9, 0xffu);       // XFL = 0, OS = 255 (unknown)
+    for (uint32_t c = 0; c < k; c++) gz_or_byte(words, 10 + c, 0x6bu);  // filler 'k', then NUL
+  }
+  {
+    const uint32_t s = B0 & 31u, nw = (s + hb + 31u) / 32u, hw = (hb + 31u) / 32u;
+    for (uint32_t j = t; j < nw; j += GZ_THREADS) {
+      uint32_t v = j < hw ? T->hdr[j] << s : 0u;
+      if (s && j > 0) v |= T->hdr[j - 1] >> (32u - s);
+      if (v) atomicOr(words + (B0 >> 5) + j, v);
+    }
+  }
+  if (t == 1) {
+    const uint32_t tb = (B0 + hb + member_bits[m] + eob_len + 7u) / 8u;
+    const uint32_t crc = member_crc[m];
+    for (int c = 0; c < 4; c++) {
+      gz_or_byte(words, tb + c, (crc >> (8 * c)) & 255u);
+      gz_or_byte(words, tb + 4 + c, (nb >> (8 * c)) & 255u);
+    }
+  }
+  // codes of this thread's chunk; interior words are exclusively this thread's
+  uint32_t lo, hi;
+  gz_chunk(nb, member_bytes / GZ_THREADS, t, lo, hi);
+  uint64_t acc = 0;
+  uint32_t nbit = start & 31u;
+  uint32_t* wp = words + (start >> 5);
+  bool first = true;
+  const unsigned char* p = data + base;
+  auto emit = [&](uint32_t e) {
+    acc |= (uint64_t)(e & 0xffffu) << nbit;
+    nbit += e >> 16;
+    if (nbit >= 32u) {
+      if (first) {
+        atomicOr(wp, (uint32_t)acc);
+        first = false;
+      } else {
+        *wp = (uint32_t)acc;
+      }
+      wp++;
+      acc >>= 32;
+      nbit -= 32u;
+    }
+  };
+  for (uint32_t o = lo; o < hi; o += 4) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + o));
+    emit(s_ent[w & 255u]);
+    emit(s_ent[(w >> 8) & 255u]);
+    emit(s_ent[(w >> 16) & 255u]);
+    emit(s_ent[w >> 24]);
+  }
+  if (t == GZ_THREADS - 1) emit(s_ent[256]);  // end of block
+  if (nbit) atomicOr(wp, (uint32_t)acc);
+}
+
+}  // namespace kdsb
+
+using namespace kdsb;
+
+extern "C" {
+
+int kdsb200_gz_histogram(const void* d_data, uint64_t nbytes, uint64_t* d_hist256, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  KDSB_CUDA(cudaMemsetAsync(d_hist256, 0, 256 * sizeof(uint64_t), st));
+  if (nbytes < 4) return 0;
+  const uint64_t words = nbytes / 4;
+  const unsigned blocks = (unsigned)std::min<uint64_t>((words + 255) / 256, (uint64_t)sm_count() * 8);
+  gz_hist_kernel<<<blocks, 256, 0, st>>>((const unsigned char*)d_data, nbytes,
+                                         (unsigned long long*)d_hist256);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kdsb200_gz_build_table(const uint64_t* h_hist256, kdsb200_gz_table* out) {
+  memset(out, 0, sizeof(*out));
+  uint64_t freq[257];
+  for (int i = 0; i < 256; i++) freq[i] = h_hist256[i] + 1;  // every byte stays encodable
+  freq[256] = 1;                                             // end of block
+  huffman_lengths(freq, 257, 15, out->len);
+  canonical_codes(out->len, 257, out->code);
+  // code lengths of the 257 literal/length codes + one distance code of length 0
+  // ("no distance codes", RFC 1951 3.2.7), each sent as a plain code-length symbol
+  uint8_t seq[258];
+  memcpy(seq, out->len, 257);
+  seq[257] = 0;
+  uint64_t clfreq[19] = {0};
+  for (int i = 0; i < 258; i++) clfreq[seq[i]]++;
+  uint8_t cllen[19];
+  uint32_t clcode[19];
+  huffman_lengths(clfreq, 19, 7, cllen);
+  canonical_codes(cllen, 19, clcode);
+  static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  int hclen = 19;
+  while (hclen > 4 && cllen[order[hclen - 1]] == 0) hclen--;
+  BitWriter bw(out->hdr, 64 * 32);
+  bool ok = bw.put(1, 1) && bw.put(2, 2) && bw.put(0, 5) && bw.put(0, 5) && bw.put(hclen - 4, 4);
+  for (int i = 0; i < hclen && ok; i++) ok = bw.put(cllen[order[i]], 3);
+  for (int i = 0; i < 258 && ok; i++) ok = bw.put(clcode[seq[i]], cllen[seq[i]]);
+  if (!ok) {
+    set_error("gz_build_table: block header does not fit %d bits", 64 * 32);
+    return 1;
+  }
+  out->hdr_bits = bw.nbits;
+  return 0;
+}
+
+uint32_t kdsb200_gz_member_bytes(void) { return 36u * 2048u; }
+
+uint64_t kdsb200_gz_scratch_bytes(uint64_t nbytes, uint32_t member_bytes) {
+  const uint64_t nm = (nbytes + member_bytes - 1) / member_bytes;
+  // table image | thread_bits | member_bits | member_crc | member_off | total
+  return 8192 + nm * (GZ_THREADS * 4 + 4 + 4 + 8) + 64;
+}
+
+int kdsb200_gz_compress(const void* d_data, uint64_t nbytes, uint32_t member_bytes,
+                        const kdsb200_gz_table* h_table, void* d_scratch, void* d_out,
+                        uint64_t out_capacity, uint64_t* d_total, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nbytes == 0) {
+    KDSB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st));
+    return 0;
+  }
+  if (member_bytes == 0 || member_bytes % (GZ_THREADS * 4) != 0 || nbytes % 4 != 0) {
+    set_error("gz_compress: member_bytes must be a multiple of %d and nbytes of 4", GZ_THREADS * 4);
+    return 1;
+  }
+  if (member_bytes > (1u << 24)) {
+    set_error("gz_compress: member_bytes too large");
+    return 1;
+  }
+  if ((reinterpret_cast<uintptr_t>(d_data) & 3) || (reinterpret_cast<uintptr_t>(d_out) & 3) ||
+      (reinterpret_cast<uintptr_t>(d_scratch) & 7) || (out_capacity & 3)) {
+    set_error("gz_compress: buffers must be 4-byte aligned (scratch 8), capacity a multiple of 4");
+    return 1;
+  }
+  const uint64_t nm = (nbytes + member_bytes - 1) / member_bytes;
+  if (nm > 0x7fffffffull) {
+    set_error("gz_compress: too many members");
+    return 1;
+  }
+  // device image of the table (pinned staging is not needed for 8 KB)
+  static thread_local GzDev img;
+  for (int i = 0; i < 257; i++) img.entry[i] = ((uint32_t)h_table->len[i] << 16) | h_table->code[i];
+  img.hdr_bits = h_table->hdr_bits;
+  memcpy(img.hdr, h_table->hdr, sizeof(img.hdr));
+  for (uint32_t n = 0; n < 256; n++) {
+    uint32_t c = n;
+    for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? CRC_POLY : 0u);
+    img.crc_tab[n] = c;
+  }
+  const uint32_t chunk = member_bytes / GZ_THREADS;
+  for (int j = 0; j < 6; j++) crc_advance_matrix((uint64_t)chunk << j, img.crc_mat[j]);
+  uint32_t mat[32];
+  crc_advance_matrix(member_bytes, mat);
+  img.init_full = mat_apply(mat, 0xffffffffu);
+  crc_advance_matrix(nbytes - (nm - 1) * member_bytes, mat);
+  img.init_last = mat_apply(mat, 0xffffffffu);
+  static_assert(sizeof(GzDev) <= 8192, "table image must fit its scratch slot");
+
+  unsigned char* sc = (unsigned char*)d_scratch;
+  GzDev* dT = (GzDev*)sc;
+  uint32_t* thread_bits = (uint32_t*)(sc + 8192);
+  uint32_t* member_bits = thread_bits + nm * GZ_THREADS;
+  uint32_t* member_crc = member_bits + nm;
+  uint64_t* member_off = (uint64_t*)(sc + 8192 + ((nm * (GZ_THREADS * 4 + 8) + 7) / 8) * 8);
+  KDSB_CUDA(cudaMemcpyAsync(dT, &img, sizeof(GzDev), cudaMemcpyHostToDevice, st));
+  KDSB_CUDA(cudaStreamSynchronize(st));  // `img` is reused by the next call of this thread
+  gz_size_kernel<<<(unsigned)nm, GZ_THREADS, 0, st>>>((const unsigned char*)d_data, nbytes,
+                                                      member_bytes, dT, thread_bits, member_bits,
+                                                      member_crc);
+  KDSB_CUDA(cudaGetLastError());
+  gz_scan_kernel<<<1, GZ_THREADS, 0, st>>>(member_bits, nm, dT, member_off, d_total);
+  KDSB_CUDA(cudaGetLastError());
+  KDSB_CUDA(cudaMemsetAsync(d_out, 0, out_capacity, st));
+  gz_encode_kernel<<<(unsigned)nm, GZ_THREADS, 0, st>>>(
+      (const unsigned char*)d_data, nbytes, member_bytes, dT, thread_bits, member_bits, member_crc,
+      member_off, out_capacity, (unsigned char*)d_out);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,278 @@
+// Streaming .gz writer for device-resident data: the I/O side of the resampler.
+//
+// Replaces the mcpl_add_particle loop + mcpl_closeandgzip_outfile of
+// clib/src/resamplemcpl.c:40-46.  Device buffers are compressed on the GPU
+// (gzip.cu), copied to one of two pinned host buffers and written by a worker thread
+// (parallel pwrite of slices) while the caller already produces the next batch, so the
+// generator, the PCIe copy and the file system work concurrently.  Small host-side
+// pieces (the MCPL header) go through zlib as a gzip member of their own.
+#include <fcntl.h>
+#include <string.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "kdsb200.h"
+
+namespace kdsb {
+
+struct GzJob {
+  int slot;
+  uint64_t bytes, file_off;
+  cudaEvent_t ev;
+};
+
+}  // namespace kdsb
+
+struct kdsb200_gz_writer_s {
+  int fd = -1;
+  cudaStream_t st = nullptr;
+  uint64_t cap = 0, file_off = 0;
+  uint32_t member = 0;
+  bool have_table = false;
+  kdsb200_gz_table table;
+  unsigned char* d_out[2] = {nullptr, nullptr};
+  unsigned char* h_out[2] = {nullptr, nullptr};
+  unsigned char* d_scratch = nullptr;
+  uint64_t* d_total = nullptr;
+  uint64_t* d_hist = nullptr;
+  uint64_t* h_small = nullptr;  // pinned: [0] total, [1..256] histogram
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int next_slot = 0, write_threads = 4;
+  // worker
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<kdsb::GzJob> queue;
+  bool busy[2] = {false, false};
+  bool stop = false, failed = false;
+  std::string err;
+};
+
+namespace kdsb {
+
+static bool pwrite_all(int fd, const unsigned char* p, uint64_t n, uint64_t off) {
+  while (n) {
+    const ssize_t w = pwrite(fd, p, n > (1u << 30) ? (1u << 30) : n, (off_t)off);
+    if (w <= 0) return false;
+    p += w;
+    off += (uint64_t)w;
+    n -= (uint64_t)w;
+  }
+  return true;
+}
+
+static void writer_loop(kdsb200_gz_writer_s* w) {
+  for (;;) {
+    GzJob job;
+    {
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv.wait(lk, [&] { return w->stop || !w->queue.empty(); });
+      if (w->queue.empty()) return;
+      job = w->queue.front();
+      w->queue.erase(w->queue.begin());
+    }
+    bool ok = cudaEventSynchronize(job.ev) == cudaSuccess;
+    if (ok) {
+      const int nt = job.bytes > (8u << 20) ? w->write_threads : 1;
+      const uint64_t per = ((job.bytes + nt - 1) / nt + 4095) / 4096 * 4096;
+      std::vector<std::thread> ths;
+      std::vector<char> oks(nt, 1);
+      for (int i = 0; i < nt; i++) {
+        const uint64_t lo = std::min<uint64_t>(job.bytes, per * i);
+        const uint64_t hi = std::min<uint64_t>(job.bytes, per * (i + 1));
+        if (hi <= lo) continue;
+        ths.emplace_back([=, &oks] {
+          oks[i] = pwrite_all(w->fd, w->h_out[job.slot] + lo, hi - lo, job.file_off + lo);
+        });
+      }
+      for (auto& t : ths) t.join();
+      for (char c : oks) ok = ok && c;
+    }
+    {
+      std::lock_guard<std::mutex> lk(w->mu);
+      w->busy[job.slot] = false;
+      if (!ok && !w->failed) {
+        w->failed = true;
+        w->err = "gz_writer: copy or write failed";
+      }
+    }
+    w->cv.notify_all();
+  }
+}
+
+}  // namespace kdsb
+
+using namespace kdsb;
+
+extern "C" {
+
+kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_bytes,
+                                          void* stream) {
+  if (max_batch_bytes == 0 || (max_batch_bytes & 3)) {
+    set_error("gz_writer_open: max_batch_bytes must be a positive multiple of 4");
+    return nullptr;
+  }
+  kdsb200_gz_writer_s* w = new kdsb200_gz_writer_s();
+  w->fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (w->fd < 0) {
+    set_error("gz_writer_open: cannot create %s", path);
+    delete w;
+    return nullptr;
+  }
+  w->st = (cudaStream_t)stream;
+  w->member = kdsb200_gz_member_bytes();
+  // Huffman coding never needs more than 15 bits per byte, but a table built from the
+  // first batch keeps the typical output below the input; leave generous headroom
+  w->cap = (max_batch_bytes + max_batch_bytes / 4 + (1u << 20) + 3) / 4 * 4;
+  const uint64_t scratch = kdsb200_gz_scratch_bytes(max_batch_bytes, w->member);
+  bool ok = true;
+  for (int s = 0; s < 2 && ok; s++) {
+    ok = ok && cudaMalloc(&w->d_out[s], w->cap) == cudaSuccess;
+    ok = ok && cudaMallocHost(&w->h_out[s], w->cap) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&w->ev[s], cudaEventDisableTiming) == cudaSuccess;
+  }
+  ok = ok && cudaMalloc(&w->d_scratch, scratch) == cudaSuccess;
+  ok = ok && cudaMalloc(&w->d_total, 8) == cudaSuccess;
+  ok = ok && cudaMalloc(&w->d_hist, 256 * 8) == cudaSuccess;
+  ok = ok && cudaMallocHost(&w->h_small, 257 * 8) == cudaSuccess;
+  if (!ok) {
+    set_error("gz_writer_open: out of device or pinned memory (batch of %llu bytes)",
+              (unsigned long long)max_batch_bytes);
+    uint64_t dummy;
+    kdsb200_gz_writer_close(w, &dummy);
+    return nullptr;
+  }
+  w->worker = std::thread(writer_loop, w);
+  return w;
+}
+
+static int writer_check(kdsb200_gz_writer* w) {
+  std::lock_guard<std::mutex> lk(w->mu);
+  if (w->failed) {
+    set_error("%s", w->err.c_str());
+    return 1;
+  }
+  return 0;
+}
+
+int kdsb200_gz_writer_put_host(kdsb200_gz_writer* w, const void* h_data, uint64_t nbytes) {
+  if (writer_check(w)) return 1;
+  z_stream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (deflateInit2(&zs, 6, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
+    set_error("gz_writer_put_host: deflateInit2 failed");
+    return 1;
+  }
+  std::vector<unsigned char> buf(deflateBound(&zs, (uLong)nbytes) + 64);
+  zs.next_in = (Bytef*)h_data;
+  zs.avail_in = (uInt)nbytes;
+  zs.next_out = buf.data();
+  zs.avail_out = (uInt)buf.size();
+  const int rc = deflate(&zs, Z_FINISH);
+  const uint64_t n = zs.total_out;
+  deflateEnd(&zs);
+  if (rc != Z_STREAM_END) {
+    set_error("gz_writer_put_host: deflate failed (%d)", rc);
+    return 1;
+  }
+  // ordered with the device batches by the running file offset
+  if (!pwrite_all(w->fd, buf.data(), n, w->file_off)) {
+    set_error("gz_writer_put_host: write failed");
+    return 1;
+  }
+  w->file_off += n;
+  return 0;
+}
+
+int kdsb200_gz_writer_put_device(kdsb200_gz_writer* w, const void* d_data, uint64_t nbytes) {
+  if (writer_check(w)) return 1;
+  if (nbytes == 0) return 0;
+  const uint64_t max_in = (w->cap - (1u << 20)) / 5 * 4;
+  if (nbytes > max_in || (nbytes & 3)) {
+    set_error("gz_writer_put_device: batch of %llu bytes (limit %llu, multiple of 4)",
+              (unsigned long long)nbytes, (unsigned long long)max_in);
+    return 1;
+  }
+  if (!w->have_table) {  // one Huffman table for the whole file, from the first batch
+    const uint64_t sample = nbytes < (64u << 20) ? nbytes : (64u << 20);
+    if (kdsb200_gz_histogram(d_data, sample, w->d_hist, w->st)) return 1;
+    KDSB_CUDA(cudaMemcpyAsync(w->h_small + 1, w->d_hist, 256 * 8, cudaMemcpyDeviceToHost, w->st));
+    KDSB_CUDA(cudaStreamSynchronize(w->st));
+    if (kdsb200_gz_build_table(w->h_small + 1, &w->table)) return 1;
+    w->have_table = true;
+  }
+  const int slot = w->next_slot;
+  w->next_slot ^= 1;
+  {
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cv.wait(lk, [&] { return !w->busy[slot] || w->failed; });
+    if (w->failed) {
+      set_error("%s", w->err.c_str());
+      return 1;
+    }
+  }
+  if (kdsb200_gz_compress(d_data, nbytes, w->member, &w->table, w->d_scratch, w->d_out[slot],
+                          w->cap, w->d_total, w->st))
+    return 1;
+  KDSB_CUDA(cudaMemcpyAsync(w->h_small, w->d_total, 8, cudaMemcpyDeviceToHost, w->st));
+  KDSB_CUDA(cudaStreamSynchronize(w->st));
+  const uint64_t total = w->h_small[0];
+  if (total > w->cap) {
+    set_error("gz_writer_put_device: compressed batch (%llu bytes) exceeds the buffer (%llu)",
+              (unsigned long long)total, (unsigned long long)w->cap);
+    return 1;
+  }
+  KDSB_CUDA(cudaMemcpyAsync(w->h_out[slot], w->d_out[slot], total, cudaMemcpyDeviceToHost, w->st));
+  KDSB_CUDA(cudaEventRecord(w->ev[slot], w->st));
+  {
+    std::lock_guard<std::mutex> lk(w->mu);
+    w->busy[slot] = true;
+    w->queue.push_back({slot, total, w->file_off, w->ev[slot]});
+  }
+  w->cv.notify_all();
+  w->file_off += total;
+  return 0;
+}
+
+int kdsb200_gz_writer_close(kdsb200_gz_writer* w, uint64_t* bytes_written) {
+  if (!w) return 0;
+  if (w->worker.joinable()) {
+    {
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv.wait(lk, [&] { return (w->queue.empty() && !w->busy[0] && !w->busy[1]) || w->failed; });
+      w->stop = true;
+    }
+    w->cv.notify_all();
+    w->worker.join();
+  }
+  int rc = 0;
+  if (w->failed) {
+    set_error("%s", w->err.c_str());
+    rc = 1;
+  }
+  if (bytes_written) *bytes_written = w->file_off;
+  if (w->fd >= 0 && close(w->fd) != 0 && !rc) {
+    set_error("gz_writer_close: close failed");
+    rc = 1;
+  }
+  for (int s = 0; s < 2; s++) {
+    if (w->d_out[s]) cudaFree(w->d_out[s]);
+    if (w->h_out[s]) cudaFreeHost(w->h_out[s]);
+    if (w->ev[s]) cudaEventDestroy(w->ev[s]);
+  }
+  if (w->d_scratch) cudaFree(w->d_scratch);
+  if (w->d_total) cudaFree(w->d_total);
+  if (w->d_hist) cudaFree(w->d_hist);
+  if (w->h_small) cudaFreeHost(w->h_small);
+  delete w;
+  return rc;
+}
+
+}  // extern "C"

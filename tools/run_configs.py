@@ -1,0 +1,311 @@
+"""Run the BASELINE.json configurations at (or near) full size and print one JSON
+record per configuration.  Single process, or one process per GPU under torchrun:
+
+    python tools/run_configs.py --configs 1,2,3,4 [--scale 1.0]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 \
+        tools/run_configs.py --configs 3,5
+
+`--scale s` multiplies the *query / output* counts (not the list sizes) so a
+configuration can be bounded to the GPU-minutes available; every record states
+the sizes it actually ran.  Timings are wall-clock around the public API call
+(host arrays in, host arrays out), max over ranks.  Parity spot checks use the
+CPU oracle on a bounded sample (test infrastructure, not the measured path).
+"""
+import argparse
+import contextlib
+import json
+import os
+import shutil
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as td  # noqa: E402
+
+from bench import synthetic_scaled  # noqa: E402
+from kdsource_b200 import _lib, dist, kde  # noqa: E402
+from kdsource_b200.sampler import DeviceSampler, make_geom_struct  # noqa: E402
+from kdsource_b200.treekde import TreeKDE  # noqa: E402
+
+
+def sync_max(dt):
+    torch.cuda.synchronize()
+    rank, world = dist.rank_world()
+    if world == 1:
+        return dt
+    t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_ranks(x):
+    rank, world = dist.rank_world()
+    if world == 1:
+        return float(x)
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    td.all_reduce(t, op=td.ReduceOp.SUM)
+    return float(t.item())
+
+
+def timed(fn):
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    return out, sync_max(time.perf_counter() - t0)
+
+
+def mem_available_gb():
+    try:
+        with open("/proc/meminfo") as fh:
+            for ln in fh:
+                if ln.startswith("MemAvailable"):
+                    return int(ln.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def config1(args):
+    """Verification example: 1e5-particle list, Silverman bw, evaluate on a 1e4 grid,
+    through KDSource (MCPL file -> fit -> evaluate)."""
+    import kdsource_b200.api as kds
+    from kdsource_b200 import mcpl
+    from oracle import kds_oracle as O
+
+    rank, world = dist.rank_world()
+    parts, w, g, _, _ = synthetic_scaled(100_000)
+    qparts = synthetic_scaled(10_000, seed=54321, wseed=1)[0]
+    tmp = tempfile.mkdtemp(prefix="kdsb_c1_")
+    try:
+        fn = os.path.join(tmp, "list{}.mcpl.gz".format(rank))
+        mcpl.write_mcpl_file(fn, ekin=parts[:, 0], x=parts[:, 1], y=parts[:, 2], z=parts[:, 3],
+                             ux=parts[:, 4], uy=parts[:, 5], uz=parts[:, 6], time=parts[:, 7],
+                             weight=w, pdgcode=2112, srcname="synthetic")
+        s = kds.KDSource(kds.PList(fn), g, bw="silv")
+        _, t_fit = timed(lambda: s.fit())
+        s.evaluate(qparts[:256])  # warm-up (context, first launch)
+        (ev, er), t_eval = timed(lambda: s.evaluate(qparts))
+        fparts, fw = s.plist.get()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    vecs = g.transform(fparts.copy()) / s.scaling
+    qv = g.transform(qparts.copy()) / s.scaling
+    ref = O.kde_sum_c(vecs, fw, s.kde.bw, qv) / np.prod(s.scaling) * g.jac(qparts.copy())
+    ok = ref > 1e-12 * ref.max()
+    return {"config": 1, "N": 100_000, "M": 10_000, "bw": float(s.kde.bw), "fit_s": t_fit,
+            "evaluate_s": t_eval, "pairs_per_s_e2e": 1e9 / t_eval,
+            "max_rel_err_vs_oracle": float(np.max(np.abs(ev[ok] / ref[ok] - 1)))}
+
+
+def config2(args):
+    """MLCV bandwidth optimisation, 1e6-particle 6-D list, 32-point grid."""
+    N = 1_000_000
+    _, w, _, _, data = synthetic_scaled(N)
+    seed = kde.bw_silv(6, np.sum(w) ** 2 / np.sum(w ** 2))
+    # the optimum of this list sits below Silverman's rule: centre the grid there
+    grid = np.logspace(-0.75, -0.15, 32)
+    kde.mlcv_scores(data[:20000], w[:20000], seed, grid)  # warm-up
+    scores, t = timed(lambda: kde.mlcv_scores(data, w, seed, grid, n_splits=10))
+    fb = kde.kfold_bounds(N, 10)
+    nf = np.diff(fb).astype(np.float64)
+    evals = float(np.sum(nf * (N - nf))) * len(grid)
+    best = int(np.argmax(scores))
+    raised = None
+    try:
+        bw, _ = timed(lambda: kde.bw_mlcv(data, w, 10, seed, grid, show=False))
+        bw = float(bw)
+    except Exception as e:  # reference behaviour when the maximum is at an edge
+        raised, bw = str(e), None
+    return {"config": 2, "N": N, "G": len(grid), "K": 10, "mlcv_scores_s": t,
+            "evals_per_s_e2e": evals / t, "argmax": best, "bw_mlcv": bw,
+            "bw_silv": float(seed), "raised": raised,
+            "scores_first_best_last": [float(scores[0]), float(scores[best]), float(scores[-1])]}
+
+
+def config3(args):
+    """kNN adaptive bandwidth (k=10, batches of 1e4) on a 1e7-particle list, then
+    evaluate at 1e8 query points (each rank draws and evaluates its own share)."""
+    from oracle import kds_oracle as O
+
+    rank, world = dist.rank_world()
+    N = 10_000_000
+    M_tot = int(1e8 * args.scale)
+    _, w, _, _, data = synthetic_scaled(N)
+    bw, t_knn = timed(lambda: kde.bw_knn(data, w, k=10, batch_size=10000))
+    off = kde.array_split_bounds(N, 1000)
+    knn_pairs = float(np.sum(np.diff(off).astype(np.float64) ** 2))
+    lo, hi = dist.shard_range(M_tot, rank, world)
+    q = synthetic_scaled(hi - lo, seed=54321 + rank, wseed=1)[4]
+    k = TreeKDE(bw=bw).fit(data, w)
+    k.evaluate(q[:1024], shard=False)  # pack + upload the sources, first launch
+    dens, t_eval = timed(lambda: k.evaluate(q, shard=False))
+    checksum = sum_ranks(float(np.sum(dens)))
+    rec = {"config": 3, "N": N, "k": 10, "batch_size": 10000, "knn_s": t_knn,
+           "knn_pairs_per_s_e2e": knn_pairs / t_knn, "M": M_tot, "evaluate_s": t_eval,
+           "pairs_per_s_e2e": float(N) * M_tot / t_eval, "density_checksum": checksum,
+           "bw_min_med_max": [float(bw.min()), float(np.median(bw)), float(bw.max())]}
+    if rank == 0:
+        ns = 2000
+        ref = O.kde_sum_c(data, w, bw, q[:ns], nthreads=os.cpu_count() or 1)
+        ok = ref > 1e-12 * ref.max()
+        rec["max_rel_err_vs_oracle_{}q".format(ns)] = float(
+            np.max(np.abs(dens[:ns][ok] / ref[ok] - 1)))
+        sub = slice(0, 20000)
+        rec["knn_bit_exact_first_2_batches"] = bool(
+            np.array_equal(bw[sub], O.bw_knn(data[sub], w[sub], k=10, batch_size=10000)))
+    return rec
+
+
+def config4(args):
+    """kdsource-resample: new particles from a 1e7-particle adaptive-bw source to MCPL.
+    (a) device rate for 1e9 particles (records produced in HBM, 1e8 per launch);
+    (b) resample_to_mcpl end to end to a gzip MCPL file for 1e8*scale particles."""
+    import kdsource_b200.api as kds
+    from kdsource_b200 import mcpl
+
+    rank, world = dist.rank_world()
+    N = 10_000_000
+    ps, w, g, sc, _ = synthetic_scaled(N, seed=7)
+    bws = np.random.default_rng(3).uniform(0.2, 0.5, N).astype(np.float32)
+    smp, t_setup = timed(lambda: DeviceSampler(ps, w, bws, make_geom_struct(g, sc, "g")))
+    n_dev = 1_000_000_000
+    lo, hi = dist.shard_range(n_dev, rank, world)
+    per = 100_000_000
+    out = _lib.empty(per * 36, torch.uint8)
+
+    def gen():
+        for s in range(lo, hi, per):
+            smp.sample_device(min(per, hi - s), seed=11, first=s, out=out)
+
+    gen()
+    _, t_dev = timed(gen)
+    del out
+    rec = {"config": 4, "N": N, "sampler_setup_s": t_setup, "device_particles": n_dev,
+           "device_s": t_dev, "device_particles_per_s": n_dev / t_dev}
+    nout = int(1e8 * args.scale)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = os.path.join(base or tempfile.gettempdir(), "kdsb_c4")
+    if rank == 0:
+        shutil.rmtree(tmp, ignore_errors=True)
+        os.makedirs(tmp)
+        mcpl.write_mcpl_file(os.path.join(tmp, "list.mcpl.gz"), ekin=ps[:, 0], x=ps[:, 1],
+                             y=ps[:, 2], z=ps[:, 3], ux=ps[:, 4], uy=ps[:, 5], uz=ps[:, 6],
+                             time=ps[:, 7], weight=w, pdgcode=2112, srcname="synthetic")
+    dist.barrier()
+    cwd = os.getcwd()
+    try:
+        os.chdir(tmp)
+        src = kds.KDSource(kds.PList("list.mcpl.gz", set_params=False), g, bw=bws.astype(np.float64))
+        if rank == 0:
+            src.scaling = np.asarray(sc, dtype=np.float64)  # bandwidths given: no fit needed to save
+            src.save("src.xml", adjust_N=False)
+        dist.barrier()
+        _, t_e2e = timed(lambda: kds.resample_to_mcpl("src.xml", "out.mcpl.gz", nout, rng=1,
+                                                      force=True))
+        if rank == 0:
+            rec.update(e2e_particles=nout, e2e_s=t_e2e, e2e_particles_per_s=nout / t_e2e,
+                       e2e_file_bytes=os.path.getsize("out.mcpl.gz"),
+                       e2e_what="resample_to_mcpl: XML + 1e7-particle MCPL read, upload, "
+                                "generation, D2H, gzip level 1, file on " + (base or "tmp"))
+            with mcpl.MCPLFile("out.mcpl.gz", blocklength=100000) as f:
+                pb = f.read_block()
+                rec["e2e_file_nparticles"] = int(f.nparticles)
+                rec["e2e_first_block_ok"] = bool(np.all(pb.weight == 1) and np.all(pb.z == 0)
+                                                 and np.all(pb.pdgcode == 2112))
+    finally:
+        os.chdir(cwd)
+        dist.barrier()
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return rec
+
+
+def config5(args):
+    """Full pipeline on a 1e8-particle list: kNN + MLCV bandwidth (bw_auto), density map,
+    1e10 resamples.  The density map (1e9 queries = 1e17 pairs) is bounded to
+    1e5*scale queries per rank and its rate reported; resampled records stay in HBM."""
+    rank, world = dist.rank_world()
+    N = int(args.n5)
+    need = 30.0 * N / 1e8 * min(world, 8)
+    if mem_available_gb() < need:
+        return {"config": 5, "skipped": "needs ~{:.0f} GB of host memory, {:.0f} available".format(
+            need, mem_available_gb())}
+    t0 = time.perf_counter()
+    ps, w, g, sc, data = synthetic_scaled(N, seed=5)
+    t_gen = time.perf_counter() - t0
+    grid = np.logspace(-0.3, 0.3, 32)
+
+    def auto():
+        try:
+            return kde.bw_auto(data, w, grid=grid, Nmlcv=1e6, Nbatch=1e4, Nknn=10, show=False)
+        except Exception as e:  # maximum at a grid edge: keep the kNN seed, report it
+            print("bw_auto:", e)
+            return None
+
+    bw, t_bw = timed(auto)
+    note = None
+    if bw is None:
+        note = "MLCV maximum at a grid edge for this list: kNN bandwidth used"
+        bw = kde.bw_knn(data, w, k=10, batch_size=10000)
+    Mq = int(1e5 * args.scale)
+    q = synthetic_scaled(Mq, seed=999 + rank, wseed=1)[4]
+    k = TreeKDE(bw=bw).fit(data, w)
+    _, t_pack = timed(lambda: k._device_state())
+    k.evaluate(q[:1024], shard=False)
+    dens, t_eval = timed(lambda: k.evaluate(q, shard=False))
+    smp, t_setup = timed(lambda: DeviceSampler(ps, w, bw.astype(np.float32),
+                                               make_geom_struct(g, sc, "g")))
+    n_res = 10_000_000_000
+    lo, hi = dist.shard_range(n_res, rank, world)
+    per = 125_000_000
+    out = _lib.empty(per * 36, torch.uint8)
+
+    def gen():
+        for s in range(lo, hi, per):
+            smp.sample_device(min(per, hi - s), seed=13, first=s, out=out)
+
+    _, t_res = timed(gen)
+    return {"config": 5, "N": N, "host_list_generation_s": t_gen, "bw_auto_s": t_bw, "note": note,
+            "source_pack_upload_s": t_pack, "density_queries": Mq * world,
+            "density_s": t_eval, "pairs_per_s_e2e": float(N) * Mq * world / t_eval,
+            "density_map_1e9_queries_projected_s": 1e9 * N / (float(N) * Mq * world / t_eval),
+            "density_checksum": sum_ranks(float(np.sum(dens))),
+            "sampler_setup_s": t_setup, "resamples": n_res, "resample_s": t_res,
+            "resampled_particles_per_s": n_res / t_res}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,3,4")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--n5", type=float, default=1e8, help="list size of configuration 5")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = dist.rank_world()[0]
+    fns = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}
+    for c in [int(x) for x in args.configs.split(",")]:
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(sys.stderr):
+            rec = fns[c](args)
+        rec.update(n_gpus=world, scale=args.scale, wall_s=time.perf_counter() - t0,
+                   host_cores=os.cpu_count())
+        if rank == 0:
+            print(json.dumps(rec), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
