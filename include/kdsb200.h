@@ -155,6 +155,40 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
                      const double* d_ext_uniforms, int slots, int perturb, void* d_out36,
                      int64_t* d_out_idx, double* d_out_parts, void* stream);
 
+/* ---- gzip on the device: the output side of kdsource_resample_to_mcpl, which
+ * always ends in mcpl_closeandgzip_outfile (clib/src/resamplemcpl.c:30-46) ------
+ * The byte stream is cut into members of `member_bytes`; each becomes one gzip
+ * member (RFC 1952) with a single dynamic-Huffman deflate block of literals
+ * (RFC 1951).  Members are laid out back to back (each a multiple of 4 bytes), which
+ * is a valid multi-member .gz file for zlib's gzread (libmcpl), gzip(1), Python. */
+typedef struct {
+  uint32_t code[257]; /* bit-reversed canonical Huffman code of byte b / end-of-block (256) */
+  uint8_t len[257];   /* code lengths, 1..15 */
+  uint32_t hdr_bits;  /* length of the deflate block header (BFINAL..code lengths) */
+  uint32_t hdr[64];   /* the block header, packed LSB first */
+} kdsb200_gz_table;
+/* byte histogram of d_data (256 uint64 counters on the device) */
+int kdsb200_gz_histogram(const void* d_data, uint64_t nbytes, uint64_t* d_hist256, void* stream);
+/* host: Huffman table + block header from a histogram (every byte value stays encodable) */
+int kdsb200_gz_build_table(const uint64_t* h_hist256, kdsb200_gz_table* out);
+uint32_t kdsb200_gz_member_bytes(void); /* default member size: 2048 MCPL-3 records */
+uint64_t kdsb200_gz_scratch_bytes(uint64_t nbytes, uint32_t member_bytes);
+/* d_data (nbytes, multiple of 4) -> d_out (<= out_capacity bytes, multiple of 4);
+ * *d_total = compressed size (device); if it exceeds out_capacity the output is
+ * incomplete and the caller must retry with a larger buffer. */
+int kdsb200_gz_compress(const void* d_data, uint64_t nbytes, uint32_t member_bytes,
+                        const kdsb200_gz_table* h_table, void* d_scratch, void* d_out,
+                        uint64_t out_capacity, uint64_t* d_total, void* stream);
+/* Streaming writer: device batches are compressed on the GPU, copied to pinned host
+ * buffers and written by a worker thread while the caller produces the next batch;
+ * host pieces (the MCPL header) are deflated with zlib as members of their own. */
+typedef struct kdsb200_gz_writer_s kdsb200_gz_writer;
+kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_bytes,
+                                          void* stream);
+int kdsb200_gz_writer_put_host(kdsb200_gz_writer* w, const void* h_data, uint64_t nbytes);
+int kdsb200_gz_writer_put_device(kdsb200_gz_writer* w, const void* d_data, uint64_t nbytes);
+int kdsb200_gz_writer_close(kdsb200_gz_writer* w, uint64_t* bytes_written);
+
 #ifdef __cplusplus
 }
 #endif

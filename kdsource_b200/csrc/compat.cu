@@ -315,19 +315,32 @@ void gz_write_all(gzFile f, const void* src, size_t n) {
   }
 }
 
-void mcpl_write_header(gzFile f, uint64_t np, const char* srcname, bool single, bool pol,
-                       int32_t updg, bool has_uw, double uweight, bool uflags) {
+std::vector<unsigned char> mcpl_header_bytes(uint64_t np, const char* srcname, bool single,
+                                            bool pol, int32_t updg, bool has_uw, double uweight,
+                                            bool uflags) {
   const uint32_t fp = single ? 4 : 8;
   const uint32_t psize = (pol ? 3 : 0) * fp + 7 * fp + (has_uw ? 0 : fp) + (updg ? 0 : 4) +
                          (uflags ? 4 : 0);
-  gz_write_all(f, "MCPL003L", 8);
-  gz_write_all(f, &np, 8);
+  std::vector<unsigned char> h;
+  auto put = [&](const void* p, size_t n) {
+    h.insert(h.end(), (const unsigned char*)p, (const unsigned char*)p + n);
+  };
+  put("MCPL003L", 8);
+  put(&np, 8);
   const uint32_t a[8] = {0, 0, uflags, pol, single, (uint32_t)updg, psize, has_uw};
-  gz_write_all(f, a, 32);
-  if (has_uw) gz_write_all(f, &uweight, 8);
+  put(a, 32);
+  if (has_uw) put(&uweight, 8);
   const uint32_t len = (uint32_t)strlen(srcname);
-  gz_write_all(f, &len, 4);
-  gz_write_all(f, srcname, len);
+  put(&len, 4);
+  put(srcname, len);
+  return h;
+}
+
+void mcpl_write_header(gzFile f, uint64_t np, const char* srcname, bool single, bool pol,
+                       int32_t updg, bool has_uw, double uweight, bool uflags) {
+  const std::vector<unsigned char> h =
+      mcpl_header_bytes(np, srcname, single, pol, updg, has_uw, uweight, uflags);
+  gz_write_all(f, h.data(), h.size());
 }
 
 // rotv (Rodrigues, axis-angle; utils.c:82-103), host, used once when a list is loaded
@@ -924,31 +937,29 @@ void kdsource_resample_to_mcpl(double (*rng_stateless)(void), const char* kds_so
   KDSource* kds = KDS_open(kds_sourcefile);
   Impl* I = ensure_impl(kds);
   const std::string out = mcpl_gz_name(destination_mcpl);
-  gzFile f = gzopen(out.c_str(), "wb1");
-  if (!f) kds_error("could not create output MCPL file");
-  gzbuffer(f, 1 << 20);
-  mcpl_write_header(f, nout, "KDSource resample", true, false, 0, false, 0.0, false);
   (void)KDS_w_mean(kds, 1000, nullptr);  // resamplemcpl.c:35 (its value, w_crit, is not needed)
   // the caller's generator keys the counter-based stream with one draw
   const uint64_t seed = rng_stateless ? (uint64_t)(rng_stateless() * 9007199254740992.0) : I->seed;
   printf("Resampling...\n");
-  const uint64_t B = 1 << 22;
+  // records are produced, gzip-compressed (gzip.cu) and staged on the device; a worker
+  // thread writes the previous batch while the next one is generated
+  const uint64_t B = nout < (1ull << 24) ? nout : (1ull << 24);
+  kdsb200_gz_writer* w = kdsb200_gz_writer_open(out.c_str(), B * 36, (void*)I->stream);
+  if (!w) kds_error(kdsb200_last_error());
+  const std::vector<unsigned char> hdr =
+      mcpl_header_bytes(nout, "KDSource resample", true, false, 0, false, 0.0, false);
+  cuda_or_die(kdsb200_gz_writer_put_host(w, hdr.data(), hdr.size()));
   unsigned char* d_rec;
-  unsigned char* h_rec;
   cu(cudaMalloc(&d_rec, B * 36));
-  cu(cudaMallocHost(&h_rec, B * 36));
   for (uint64_t first = 0; first < nout; first += B) {
     const uint64_t n = nout - first < B ? nout - first : B;
     cuda_or_die(kdsb200_resample(I->d_src, 1, I->d_cdf, I->d_guide, I->guide_bits, I->d_bw,
                                  kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed, first,
                                  n, -1, nullptr, 0, 1, d_rec, nullptr, nullptr, (void*)I->stream));
-    cu(cudaMemcpyAsync(h_rec, d_rec, n * 36, cudaMemcpyDeviceToHost, I->stream));
-    cu(cudaStreamSynchronize(I->stream));
-    gz_write_all(f, h_rec, n * 36);
+    cuda_or_die(kdsb200_gz_writer_put_device(w, d_rec, n * 36));
   }
-  gzclose(f);
+  cuda_or_die(kdsb200_gz_writer_close(w, nullptr));
   cudaFree(d_rec);
-  cudaFreeHost(h_rec);
   KDS_destroy(kds);
   printf("Successfully sampled %llu particles.\n", (unsigned long long)nout);
 }

@@ -16,7 +16,7 @@ from xml.etree.ElementTree import parse
 
 import numpy as np
 
-from . import mcpl
+from . import _lib, mcpl
 from .geom import Geometry
 from .plist import PList
 from .sampler import DEFAULT_SLOTS, DeviceSampler, make_geom_struct
@@ -72,7 +72,7 @@ def _gzip_member(data, level):
 
 
 def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=False,
-                     batch=1 << 22, compresslevel=1, precision="float32", threads=None):
+                     batch=1 << 24, compresslevel=None, precision="float32", threads=None):
     """Resample `nout` particles from an XML source file into a new MCPL file
     (always ``*.mcpl.gz``; refuses to overwrite unless `force`).
 
@@ -81,14 +81,14 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
     returning uniforms in [0,1) is honoured too (it is consumed on the host,
     32 numbers per particle, and fed to the same kernel).
 
-    The GPU produces MCPL-3 records in batches; the host compresses them as
-    independent gzip members on `threads` worker threads (default: all cores)
-    while the next batch is generated.  With torch.distributed initialised each
-    rank produces a contiguous share of the particles and rank 0 assembles the
-    file; the result does not depend on the number of ranks.
+    compresslevel=None (default): the MCPL-3 records are gzip-compressed on the
+    GPU (``kdsb200_gz_writer_*``: order-0 Huffman deflate members), copied to
+    pinned buffers and written by a native worker thread while the next batch is
+    generated.  An int selects host zlib at that level instead (`threads` worker
+    threads, default all cores; 0 = stored).  With torch.distributed initialised
+    each rank produces a contiguous share of the particles and rank 0 assembles
+    the file; the particles do not depend on the number of ranks.
     """
-    from concurrent.futures import ThreadPoolExecutor
-
     from . import dist as _dist
 
     ksrc = pathlib.Path(kds_sourcefile)
@@ -113,37 +113,33 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
         raise RuntimeError("multi-rank resampling needs an explicit integer seed")
     sampler, _ = open_source(ksrc.absolute(), precision=precision)
     lo, hi = _dist.shard_range(nout, rank, world)
-    nthreads = threads or os.cpu_count() or 1
     part_name = str(dst) + ".part{}".format(rank) if world > 1 else None
+    header = mcpl.build_header(nout, "KDSource resample", singleprec=True) if rank == 0 else None
+    if not isinstance(rng, int):
+        batch = min(batch, 1 << 20)  # host-generated uniforms: 256 B per particle
+    batch = int(max(1, min(batch, hi - lo)))
     print("Resampling...")
-    with open(part_name or dst, "wb") as fh, ThreadPoolExecutor(nthreads) as pool:
-        if rank == 0:
-            fh.write(_gzip_member(mcpl.build_header(nout, "KDSource resample", singleprec=True),
-                                  compresslevel))
-        pending = []  # futures of the previous batch, written while the next one is generated
 
-        def drain():
-            for fut in pending:
-                fh.write(fut.result())
-            pending.clear()
-
+    def batches():
+        """(device record tensor, count) per batch; the tensor is reused."""
+        t = _lib.torch()
+        rec = _lib.empty(batch * 36, t.uint8)
         done = lo
         while done < hi:
             n = min(batch, hi - done)
             if isinstance(rng, int):
-                rec = sampler.sample(n, seed=rng, first=done)["records"]
+                sampler.sample_device(n, seed=rng, first=done, out=rec)
             else:
                 ext = np.fromiter((rng() for _ in range(n * DEFAULT_SLOTS)), dtype=np.float64,
                                   count=n * DEFAULT_SLOTS).reshape(n, DEFAULT_SLOTS)
-                rec = sampler.sample(n, first=done, ext_uniforms=ext)["records"]
-            drain()
-            raw = rec.reshape(-1)
-            step = max(36 * 4096, (len(raw) // nthreads + 35) // 36 * 36)
-            for s0 in range(0, len(raw), step):
-                pending.append(pool.submit(_gzip_member, raw[s0:s0 + step].tobytes(),
-                                           compresslevel))
+                sampler.sample_device(n, first=done, ext_uniforms=ext, out=rec)
+            yield rec, n
             done += n
-        drain()
+
+    if compresslevel is None:
+        _write_gpu_gzip(part_name or str(dst), header, batches(), batch)
+    else:
+        _write_host_gzip(part_name or str(dst), header, batches(), compresslevel, threads)
     if world > 1:
         _dist.barrier()
         if rank == 0:
@@ -156,3 +152,51 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
         _dist.barrier()
     if rank == 0:
         print("Successfully sampled {} particles.".format(nout))
+
+
+def _write_gpu_gzip(path, header, batches, batch):
+    """Device-compressed output through the native streaming writer."""
+    import ctypes
+
+    L = _lib.load()
+    w = L.kdsb200_gz_writer_open(os.fsencode(path), batch * 36, _lib.stream())
+    if not w:
+        _lib.check(1)
+    w = ctypes.c_void_p(w)
+    try:
+        if header is not None:
+            _lib.check(L.kdsb200_gz_writer_put_host(w, header, len(header)))
+        for rec, n in batches:
+            _lib.check(L.kdsb200_gz_writer_put_device(w, _lib.ptr(rec), n * 36))
+    except BaseException:
+        L.kdsb200_gz_writer_close(w, None)
+        raise
+    nbytes = ctypes.c_uint64(0)
+    _lib.check(L.kdsb200_gz_writer_close(w, ctypes.byref(nbytes)))
+    return int(nbytes.value)
+
+
+def _write_host_gzip(path, header, batches, compresslevel, threads):
+    """Host zlib output: independent gzip members compressed on a thread pool while
+    the next batch is generated."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    nthreads = threads or os.cpu_count() or 1
+    with open(path, "wb") as fh, ThreadPoolExecutor(nthreads) as pool:
+        if header is not None:
+            fh.write(_gzip_member(header, compresslevel))
+        pending = []  # futures of the previous batch, written while the next one is generated
+
+        def drain():
+            for fut in pending:
+                fh.write(fut.result())
+            pending.clear()
+
+        for rec, n in batches:
+            raw = rec[:n * 36].cpu().numpy()
+            drain()
+            step = max(36 * 4096, (len(raw) // nthreads + 35) // 36 * 36)
+            for s0 in range(0, len(raw), step):
+                pending.append(pool.submit(_gzip_member, raw[s0:s0 + step].tobytes(),
+                                           compresslevel))
+        drain()

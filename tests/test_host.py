@@ -388,3 +388,45 @@ def test_geom_struct_for_sampler():
     assert gs.ms[1].scaling[1] == 3.0 and gs.ms[2].nps == 3 and gs.ms[2].params[2] == 1.0
     with pytest.raises(ValueError):
         make_geom_struct(geo, [1, 2, 3], "g")
+
+
+def test_gzip_table_builder_inflates_with_zlib():
+    """Host half of the device gzip (kdsb200_gz_build_table): the dynamic-Huffman block
+    header and the canonical codes must form a deflate stream zlib accepts -- packed
+    here bit by bit in Python and inflated with zlib (no GPU involved)."""
+    import ctypes
+    import zlib
+
+    from kdsource_b200 import _lib
+
+    L = _lib.load()
+    rng = np.random.default_rng(0)
+
+    def roundtrip(data):
+        hist = np.bincount(np.frombuffer(data, np.uint8), minlength=256).astype(np.uint64)
+        T = _lib.GzTable()
+        assert L.kdsb200_gz_build_table(hist.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                        ctypes.byref(T)) == 0
+        lens = np.array(T.len[:])
+        assert lens.min() >= 1 and lens.max() <= 15          # every symbol encodable
+        assert np.sum(2.0 ** -lens) == pytest.approx(1.0)    # complete prefix code
+        bits = [(T.hdr[j >> 5] >> (j & 31)) & 1 for j in range(T.hdr_bits)]
+        for b in list(data) + [256]:
+            bits += [(T.code[b] >> k) & 1 for k in range(T.len[b])]
+        bits += [0] * (-len(bits) % 8)
+        raw = np.packbits(np.array(bits, dtype=np.uint8), bitorder="little").tobytes()
+        assert zlib.decompress(raw, wbits=-15) == data
+        return len(raw)
+
+    roundtrip(rng.integers(0, 256, 4000, dtype=np.uint8).tobytes())
+    assert roundtrip(bytes([7]) * 3000) < 600
+    roundtrip(b"")
+    # natural Huffman depths beyond 15 bits must be limited
+    roundtrip(np.concatenate([np.full(2 ** k, k, dtype=np.uint8) for k in range(17)]).tobytes())
+    # MCPL-3 records: constant weight / pdg / z / time fields compress, mantissas do not
+    rec = np.zeros((500, 9), dtype=np.float32)
+    rec[:, :6] = rng.normal(size=(500, 6))
+    rec[:, 7] = 1.0
+    raw = rec.view(np.uint8).copy()
+    raw[:, 32:36] = np.frombuffer(np.int32(2112).tobytes(), np.uint8)
+    assert roundtrip(raw.tobytes()) < 0.8 * raw.size
