@@ -5,8 +5,10 @@ API-compatible with the hot-path part of the reference's
 kernel)``, ``fit``, ``evaluate``, ``save`` and the module function ``load``,
 with the same XML source-file format.  Kernel sums run in the CUDA kernels
 behind :class:`kdsource_b200.treekde.TreeKDE`; bandwidth selection in
-:mod:`kdsource_b200.kde`.  The matplotlib ``plot_*`` helpers of the reference
-are presentation code and are not part of this package.
+:mod:`kdsource_b200.kde`.  The ``plot_*`` methods (reference :397-923) compute
+their marginal densities with the same kernels and return ``[fig, [scores,
+errs]]``; the figure is drawn only when matplotlib is installed (``fig`` is None
+otherwise).
 """
 
 import ctypes
@@ -224,3 +226,190 @@ class KDSource:
             file.write(xmlstr)
         print("Successfully saved parameters file {}".format(xmlfilename))
         return xmlfilename
+
+    # ------------------------------------------------------------------
+    # plot back-ends (reference kdsource.py:397-923): a marginal KDE over a column
+    # subset of the fitted samples inside [vec0, vec1], evaluated on a grid
+    # ------------------------------------------------------------------
+    def _range_mask(self, vec0, vec1):
+        data = self.kde.data
+        mask = np.ones(len(data), dtype=bool)
+        if vec0 is not None:
+            mask &= np.logical_and.reduce(np.asarray(vec0) / self.scaling <= data, axis=1)
+        if vec1 is not None:
+            mask &= np.logical_and.reduce(data <= np.asarray(vec1) / self.scaling, axis=1)
+        return mask
+
+    def _marginal(self, cols, points, vec0, vec1, adjust_bw, r_power):
+        """Scores and errors of the marginal KDE over columns `cols` at the (already
+        parametrised, unscaled) `points` ((M, len(cols))).  Same arithmetic as the
+        reference's plot methods; two deliberate differences: a per-particle
+        bandwidth array is masked together with the samples (the reference passes
+        the unmasked array), and ``adjust_bw`` does not modify ``self.kde.bw``."""
+        if self.fitted is False:
+            raise Exception("Must fit before plotting.")
+        mask = self._range_mask(vec0, vec1)
+        if np.sum(mask) == 0:
+            raise Exception("No particles in [vec0,vec1] range.")
+        cols = np.atleast_1d(cols)
+        vecs = self.kde.data[:, cols][mask]
+        allw = self.kde.weights if self.kde.weights is not None else np.ones(len(mask))
+        ws = allw[mask]
+        N_eff = np.sum(ws) ** 2 / np.sum(ws ** 2)
+        scaling = self.scaling[cols]
+        bw = self.kde.bw
+        if np.ndim(bw) == 1:
+            bw = np.asarray(bw)[:len(mask)][mask]
+        if adjust_bw:
+            bw = bw * (bw_silv(1, N_eff) / bw_silv(self.geom.dim, self.N_eff))
+        kde = TreeKDE(kernel=self.kernel, bw=bw)
+        kde.fit(vecs, weights=ws)
+        vol = np.prod(scaling)
+        scores = 1 / vol * kde.evaluate(np.asarray(points, dtype=np.float64) / scaling)
+        errs = np.sqrt(scores * self.R ** r_power / (N_eff * np.mean(bw) * vol))
+        frac = self.J * np.sum(ws) / np.sum(allw)
+        return scores * frac, errs * frac
+
+    @staticmethod
+    def _pyplot():
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError:
+            return None
+        return plt
+
+    def _errorbar(self, x, scores, errs, label, xscale, yscale, xlabel, ylabel):
+        plt = self._pyplot()
+        if plt is None:
+            return None
+        plt.errorbar(x, scores, errs, label=label, capsize=1, linewidth=1)
+        plt.xscale(xscale)
+        plt.yscale(yscale)
+        plt.xlabel(xlabel)
+        plt.ylabel(ylabel)
+        plt.grid()
+        plt.legend()
+        plt.tight_layout()
+        return plt.gcf()
+
+    def _colormesh(self, grids, scores, scale, title, xlabel, ylabel):
+        plt = self._pyplot()
+        if plt is None:
+            return None
+        edges = [np.concatenate((g[:1], (g[1:] + g[:-1]) / 2, g[-1:])) for g in grids]
+        norm = None
+        if scale == "log":
+            import matplotlib.colors as col
+
+            norm = col.LogNorm()
+        plt.pcolormesh(edges[0], edges[1], scores.reshape(len(grids[1]), len(grids[0])),
+                       cmap="jet", norm=norm, rasterized=True)
+        plt.colorbar()
+        plt.title(title)
+        plt.xlabel(xlabel)
+        plt.ylabel(ylabel)
+        plt.tight_layout()
+        return plt.gcf()
+
+    def plot_integr(self, var, grid, vec0=None, vec1=None, **kwargs):
+        """Univariate distribution along the parametrised variable `var` (name or
+        index), integrated over [vec0, vec1] in the other variables
+        (reference kdsource.py:397-508).  kwargs: xscale, yscale, fact, label,
+        adjust_bw.  Returns ``[fig, [scores, errs]]``."""
+        if self.fitted is False:
+            raise Exception("Must fit before plotting.")
+        if isinstance(var, str):
+            var = self.geom.varmap[var]
+        grid = np.asarray(grid, dtype=np.float64)
+        scores, errs = self._marginal([var], grid.reshape(-1, 1), vec0, vec1,
+                                      kwargs.get("adjust_bw", False), 1)
+        if "fact" in kwargs:
+            scores *= kwargs["fact"]
+            errs *= kwargs["fact"]
+        fig = self._errorbar(
+            grid, scores, errs, kwargs.get("label", "KDE"), kwargs.get("xscale", "linear"),
+            kwargs.get("yscale", "log"),
+            r"${}\ [{}]$".format(self.geom.varnames[var], self.geom.units[var]),
+            r"$J\ \left[ \frac{{{}}}{{{}\ s}} \right]$".format(self.plist.pt, self.geom.units[var]))
+        return [fig, [scores, errs]]
+
+    def _plot_metric_axis(self, which, grid_x, vec0, vec1, kwargs, xlabel, ylabel):
+        """plot_E / plot_t: the first (energy) or last (time) metric's variable, with
+        the metric's jacobian applied so the spectrum is per MeV / per ms."""
+        if self.fitted is False:
+            raise Exception("Must fit before plotting.")
+        col = 0 if which == 0 else self.geom.dim - 1
+        metric = self.geom.ms[which]
+        grid_x = np.asarray(grid_x, dtype=np.float64)
+        pts = np.asarray(metric.transform(grid_x), dtype=np.float64).reshape(-1, 1)
+        jacs = np.asarray(metric.jac(grid_x), dtype=np.float64).reshape(-1)
+        scores, errs = self._marginal([col], pts, vec0, vec1, kwargs.get("adjust_bw", False), 1)
+        scores *= jacs
+        errs *= jacs
+        if "fact" in kwargs:
+            scores *= kwargs["fact"]
+            errs *= kwargs["fact"]
+        fig = self._errorbar(grid_x, scores, errs, kwargs.get("label", "KDE"), "log", "log",
+                             xlabel, ylabel)
+        return [fig, [scores, errs]]
+
+    def plot_E(self, grid_E, vec0=None, vec1=None, **kwargs):
+        """Energy spectrum [1/(MeV s)]; assumes energy is the first metric
+        (reference kdsource.py:510-608).  kwargs: fact, label, adjust_bw."""
+        return self._plot_metric_axis(
+            0, grid_E, vec0, vec1, kwargs, r"$E\ [MeV]$",
+            r"$J\ \left[ \frac{{{}}}{{MeV\ s}} \right]$".format(self.plist.pt))
+
+    def plot_t(self, grid_t, vec0=None, vec1=None, **kwargs):
+        """Time distribution; assumes time is the last metric
+        (reference kdsource.py:610-708).  kwargs: fact, label, adjust_bw."""
+        return self._plot_metric_axis(
+            -1, grid_t, vec0, vec1, kwargs, r"$t$ [ms]",
+            r"$J\ \left[ \frac{{{}}}{{s^2}} \right]$".format(self.plist.pt))
+
+    def plot2D_point(self, vrs, grids, part0, **kwargs):
+        """Full multivariate density on a 2-D grid of two particle variables, the
+        others fixed at `part0` (reference kdsource.py:710-785).  The reference
+        multiplies the list returned by ``evaluate`` by J (a TypeError for float J);
+        ``evaluate`` already includes J, so it is used as is."""
+        if self.fitted is False:
+            raise Exception("Must fit before plotting.")
+        vrs = [varmap[v] if isinstance(v, str) else v for v in vrs]
+        grids = [np.asarray(g, dtype=np.float64) for g in grids]
+        parts = np.zeros((len(grids[0]) * len(grids[1]), 7))
+        parts[:, vrs] = np.reshape(np.meshgrid(*grids), (2, -1)).T
+        part0 = np.array(part0, dtype=np.float64)
+        part0[vrs] = 0
+        parts += part0
+        scores, errs = self.evaluate(parts)
+        if "fact" in kwargs:
+            scores *= kwargs["fact"]
+            errs *= kwargs["fact"]
+        title = kwargs.get("title", "KDE") + "\n" + (
+            r"$J\ \left[ \frac{{{}}}{{{}\ s}} \right]$".format(self.plist.pt, self.geom.volunits))
+        fig = self._colormesh(grids, scores, kwargs.get("scale", "linear"), title,
+                              r"${}\ [{}]$".format(varnames[vrs[0]], units[vrs[0]]),
+                              r"${}\ [{}]$".format(varnames[vrs[1]], units[vrs[1]]))
+        return [fig, [scores, errs]]
+
+    def plot2D_integr(self, vrs, grids, vec0=None, vec1=None, **kwargs):
+        """Bivariate distribution along two parametrised variables, integrated over
+        [vec0, vec1] in the others (reference kdsource.py:787-923).  kwargs: scale,
+        fact, title, adjust_bw."""
+        if self.fitted is False:
+            raise Exception("Must fit before plotting.")
+        vrs = [self.geom.varmap[v] if isinstance(v, str) else v for v in vrs]
+        grids = [np.asarray(g, dtype=np.float64) for g in grids]
+        pts = np.reshape(np.meshgrid(*grids), (2, -1)).T
+        scores, errs = self._marginal(vrs, pts, vec0, vec1, kwargs.get("adjust_bw", False), 2)
+        if "fact" in kwargs:
+            scores *= kwargs["fact"]
+            errs *= kwargs["fact"]
+        u0, u1 = self.geom.units[vrs[0]], self.geom.units[vrs[1]]
+        un = u0 + "^2" if u0 == u1 else u0 + u1
+        title = kwargs.get("title", "KDE") + "\n" + (
+            r"$J\ \left[ \frac{{{}}}{{{}\ s}} \right]$".format(self.plist.pt, un))
+        fig = self._colormesh(grids, scores, kwargs.get("scale", "linear"), title,
+                              r"${}\ [{}]$".format(self.geom.varnames[vrs[0]], u0),
+                              r"${}\ [{}]$".format(self.geom.varnames[vrs[1]], u1))
+        return [fig, [scores, errs]]

@@ -42,6 +42,13 @@ def golden_geom():
 
 
 @pytest.fixture(scope="session")
+def golden_kdsource():
+    import numpy as np
+
+    return np.load(os.path.join(GOLDEN, "ref_kdsource.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import kds_oracle
 

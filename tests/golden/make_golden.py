@@ -36,7 +36,7 @@ def import_reference():
     pkg = os.path.join(scratch, "refkds")
     os.makedirs(pkg)
     open(os.path.join(pkg, "__init__.py"), "w").close()
-    for f in ("kde.py", "geom.py", "utils.py"):
+    for f in ("kde.py", "geom.py", "utils.py", "kdsource.py", "plist.py"):
         os.symlink(os.path.join(REF, f), os.path.join(pkg, f))
 
     class TreeKDE:  # shim with KDEpy's interface
@@ -48,11 +48,30 @@ def import_reference():
             return self
 
         def evaluate(self, points):
-            return O.kde_sum(self.data, self.weights, self.bw, points)
+            return O.kde_sum(self.data, self.weights, self.bw, points, kernel=self.kernel)
 
     shim = types.ModuleType("KDEpy")
     shim.TreeKDE = TreeKDE
     sys.modules["KDEpy"] = shim
+    # `mcpl` (python module of the MCPL distribution, plist.py:10): MCPLFile over this
+    # repository's own reader, which is pinned by the reference's 9-particle fixture
+    from kdsource_b200 import mcpl as our_mcpl
+
+    mshim = types.ModuleType("mcpl")
+    mshim.MCPLFile = our_mcpl.MCPLFile
+    sys.modules["mcpl"] = mshim
+    # matplotlib is not installed: the plot_* methods import it only to draw
+    plt = types.ModuleType("matplotlib.pyplot")
+    for name in ("errorbar", "xscale", "yscale", "xlabel", "ylabel", "grid", "legend",
+                 "tight_layout", "pcolormesh", "colorbar", "title", "plot", "show"):
+        setattr(plt, name, lambda *a, **k: None)
+    plt.gcf = lambda: None
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    col = types.ModuleType("matplotlib.colors")
+    col.LogNorm = lambda *a, **k: None
+    mpl.colors = col
+    sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt, "matplotlib.colors": col})
     sys.path.insert(0, scratch)
     import refkds.geom as rgeom
     import refkds.kde as rkde
@@ -69,7 +88,92 @@ def main():
         kde_vectors(rkde, rgeom)
     geom_vectors(rgeom)
     fixture_files()
-    print("wrote ref_kde.npz, ref_geom.npz, ref_fixture_samples.mcpl.gz, ref_fixture_source.xml")
+    kdsource_vectors(rgeom)
+    print("wrote ref_kde.npz, ref_geom.npz, ref_kdsource.npz, ref_fixture_samples.mcpl.gz, "
+          "ref_fixture_source.xml")
+
+
+def kdsource_vectors(rgeom):
+    """The reference's own KDSource object (python/kdsource/kdsource.py, plist.py, run
+    unmodified) on a small MCPL list: fit (scaling, N_eff, Silverman bw), evaluate
+    (densities + errors), and the marginal densities behind plot_integr / plot_E /
+    plot2D_integr, for the Gaussian kernel and the finite-support ones."""
+    import refkds.kdsource as rks
+    import refkds.plist as rpl
+
+    from kdsource_b200 import mcpl as our_mcpl
+
+    out = {}
+    # The one reference defect that has to be worked around to run evaluate() at all:
+    # Geometry.jac reduces over the particle axis (geom.py:205, np.prod(jacs, axis=1)),
+    # which returns one number per metric and makes kdsource.py:246 fail for any number
+    # of query particles other than len(geom.ms).  The per-particle product over the
+    # metrics (axis=0) is what the formula means; everything else runs unmodified.
+    ref_jac = rgeom.Geometry.jac
+
+    def jac_per_particle(self, parts):
+        prod_axis1 = np.prod
+        try:
+            np.prod = lambda a, axis=None, **k: prod_axis1(a, axis=0 if axis == 1 else axis, **k)
+            return ref_jac(self, parts)
+        finally:
+            np.prod = prod_axis1
+
+    rgeom.Geometry.jac = jac_per_particle
+    parts, w = O.synthetic_particles(3000, seed=21, wseed=22)
+    tmp = tempfile.mkdtemp(prefix="refks_")
+    fn = os.path.join(tmp, "list.mcpl.gz")
+    our_mcpl.write_mcpl_file(fn, ekin=parts[:, 0], x=parts[:, 1], y=parts[:, 2], z=parts[:, 3],
+                             ux=parts[:, 4], uy=parts[:, 5], uz=parts[:, 6], time=parts[:, 7],
+                             weight=w, pdgcode=2112, srcname="golden")
+    with open(fn, "rb") as fh:
+        out["list_mcpl_gz"] = np.frombuffer(fh.read(), dtype=np.uint8)
+    q = O.synthetic_particles(200, seed=23, wseed=24)[0]
+    out["queries"] = q
+    gE = np.logspace(-5, -1, 25)
+    gx = np.linspace(-25, 25, 21)
+    gy = np.linspace(-20, 20, 9)
+    out["grid_E"], out["grid_x"], out["grid_y"] = gE, gx, gy
+    vec0 = np.array([0, -100, -100, -1, -1, 0.2])
+    vec1 = np.array([20, 100, 15, 1, 1, 1])
+    out["vec0"], out["vec1"] = vec0, vec1
+    for kern in ("gaussian", "epa", "box"):
+        pl = rpl.PList(fn)
+        geo = rgeom.Geometry([rgeom.Lethargy(10), rgeom.SurfXY(), rgeom.Isotrop()])
+        s = rks.KDSource(pl, geo, bw="silv", J=3.5, kernel=kern)
+        s.fit(importance=[2, 1, 1, 1, 1, 1])
+        k = kern[0]
+        out[k + "_scaling"] = s.scaling
+        out[k + "_N_eff"] = s.N_eff
+        out[k + "_bw"] = s.kde.bw
+        ev, er = s.evaluate(q.copy())
+        out[k + "_evaluate"], out[k + "_evaluate_err"] = ev, er
+        _, (sc, e) = s.plot_integr("x", gx)
+        out[k + "_integr_x"], out[k + "_integr_x_err"] = sc, e
+        _, (sc, e) = s.plot_integr(1, gx, vec0=vec0, vec1=vec1, fact=2.0)
+        out[k + "_integr_x_range"], out[k + "_integr_x_range_err"] = sc, e
+        _, (sc, e) = s.plot_E(gE, vec0=vec0, vec1=vec1)
+        out[k + "_E"], out[k + "_E_err"] = sc, e
+        _, (sc, e) = s.plot2D_integr(["x", "y"], [gx, gy], vec0=vec0, vec1=vec1)
+        out[k + "_2D_xy"], out[k + "_2D_xy_err"] = sc, e
+    # time as the last metric (plot_t) with a Decade parametrisation
+    parts_t = parts.copy()
+    parts_t[:, 7] = np.random.default_rng(25).lognormal(0, 1, len(parts))
+    fnt = os.path.join(tmp, "list_t.mcpl.gz")
+    our_mcpl.write_mcpl_file(fnt, ekin=parts_t[:, 0], x=parts_t[:, 1], y=parts_t[:, 2],
+                             z=parts_t[:, 3], ux=parts_t[:, 4], uy=parts_t[:, 5],
+                             uz=parts_t[:, 6], time=parts_t[:, 7], weight=w, pdgcode=2112,
+                             srcname="golden")
+    with open(fnt, "rb") as fh:
+        out["list_t_mcpl_gz"] = np.frombuffer(fh.read(), dtype=np.uint8)
+    geo = rgeom.Geometry([rgeom.Lethargy(10), rgeom.SurfXY(), rgeom.Isotrop(), rgeom.Decade()])
+    s = rks.KDSource(rpl.PList(fnt), geo, bw=0.4, J=1.0)
+    s.fit()
+    gt = np.logspace(-1.5, 1.5, 17)
+    out["grid_t"] = gt
+    _, (sc, e) = s.plot_t(gt)
+    out["t_scaling"], out["t"], out["t_err"] = s.scaling, sc, e
+    np.savez_compressed(os.path.join(HERE, "ref_kdsource.npz"), **out)
 
 
 def fixture_files():

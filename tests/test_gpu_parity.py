@@ -581,3 +581,75 @@ def test_resample_to_mcpl_gpu_gzip_equals_host_gzip(oracle, tmp_path, monkeypatc
     with mcpl.MCPLFile("gpu.mcpl.gz", blocklength=n) as f:
         pb = f.read_block()
     assert f.nparticles == n and len(pb) == n and np.all(pb.weight == 1)
+
+
+# ------------------------------------------ KDSource object vs the reference's own
+@pytest.mark.parametrize("kernel", ["gaussian", "epa", "box"])
+def test_kdsource_vs_reference_golden(golden_kdsource, tmp_path, monkeypatch, kernel):
+    """fit / evaluate / plot_integr / plot_E / plot2D_integr against the outputs of the
+    reference's own kdsource.py + plist.py run in place (tests/golden/make_golden.py,
+    kernel sum shimmed by the oracle).  fp32 kernel sums: 1e-5 relative; the box kernel
+    is a step function, so single pairs at the support radius may flip in fp32."""
+    import kdsource_b200.api as kds
+
+    g = golden_kdsource
+    monkeypatch.chdir(tmp_path)
+    with open("list.mcpl.gz", "wb") as fh:
+        fh.write(g["list_mcpl_gz"].tobytes())
+    geo = kds.geom.Geometry([kds.geom.Lethargy(10), kds.geom.SurfXY(), kds.geom.Isotrop()])
+    s = kds.KDSource(kds.PList("list.mcpl.gz"), geo, bw="silv", J=3.5, kernel=kernel)
+    s.fit(importance=[2, 1, 1, 1, 1, 1])
+    k = kernel[0]
+    assert np.allclose(s.scaling, g[k + "_scaling"], rtol=1e-13)
+    assert s.N_eff == pytest.approx(float(g[k + "_N_eff"]), rel=1e-13)
+    assert float(s.kde.bw) == pytest.approx(float(g[k + "_bw"]), rel=1e-13)
+
+    def close(got, ref, what):
+        got, ref = np.asarray(got), np.asarray(ref)
+        assert got.shape == ref.shape, what
+        scale = np.max(np.abs(ref))
+        if kernel == "box":
+            assert np.mean(np.abs(got - ref) <= 1e-5 * np.abs(ref) + 1e-12 * scale) > 0.97, what
+            assert np.max(np.abs(got - ref)) < 0.02 * scale, what
+        else:
+            big = np.abs(ref) > 1e-6 * scale
+            assert np.max(np.abs(got[big] / ref[big] - 1)) < 1e-5, what
+            assert np.max(np.abs(got - ref)) < 1e-5 * scale, what
+
+    ev, er = s.evaluate(g["queries"].copy())
+    close(ev, g[k + "_evaluate"], "evaluate")
+    close(er, g[k + "_evaluate_err"], "evaluate errs")
+    gx, gy, gE = g["grid_x"], g["grid_y"], g["grid_E"]
+    vec0, vec1 = g["vec0"], g["vec1"]
+    fig, (sc, e) = s.plot_integr("x", gx)
+    close(sc, g[k + "_integr_x"], "plot_integr")
+    close(e, g[k + "_integr_x_err"], "plot_integr errs")
+    _, (sc, e) = s.plot_integr(1, gx, vec0=vec0, vec1=vec1, fact=2.0)
+    close(sc, g[k + "_integr_x_range"], "plot_integr range")
+    close(e, g[k + "_integr_x_range_err"], "plot_integr range errs")
+    _, (sc, e) = s.plot_E(gE, vec0=vec0, vec1=vec1)
+    close(sc, g[k + "_E"], "plot_E")
+    close(e, g[k + "_E_err"], "plot_E errs")
+    _, (sc, e) = s.plot2D_integr(["x", "y"], [gx, gy], vec0=vec0, vec1=vec1)
+    close(sc, g[k + "_2D_xy"], "plot2D_integr")
+    close(e, g[k + "_2D_xy_err"], "plot2D_integr errs")
+    with pytest.raises(Exception, match="No particles"):
+        s.plot_E(gE, vec0=np.full(6, 1e9), vec1=np.full(6, 2e9))
+    if kernel == "gaussian":
+        # plot2D_point: the full density on an (x, y) grid at a fixed particle
+        part0 = g["queries"][0, :7].copy()
+        _, (sc2, _) = s.plot2D_point(["x", "y"], [gx, gy], part0)
+        pts = np.tile(part0, (len(gx) * len(gy), 1))
+        pts[:, [1, 2]] = np.reshape(np.meshgrid(gx, gy), (2, -1)).T
+        assert np.allclose(sc2, s.evaluate(pts)[0], rtol=1e-12)
+        # time axis (Decade as the last metric)
+        with open("list_t.mcpl.gz", "wb") as fh:
+            fh.write(g["list_t_mcpl_gz"].tobytes())
+        geo_t = kds.geom.Geometry([kds.geom.Lethargy(10), kds.geom.SurfXY(), kds.geom.Isotrop(),
+                                   kds.geom.Decade()])
+        st = kds.KDSource(kds.PList("list_t.mcpl.gz"), geo_t, bw=0.4, J=1.0)
+        st.fit()
+        assert np.allclose(st.scaling, g["t_scaling"], rtol=1e-13)
+        _, (sc, e) = st.plot_t(g["grid_t"])
+        close(sc, g["t"], "plot_t")
+        close(e, g["t_err"], "plot_t errs")

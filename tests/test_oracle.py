@@ -274,3 +274,25 @@ def test_resample_statistics_vs_reference_sampler(oracle):
         a = np.log(ref[:, col]) if col == 0 else ref[:, col]
         b = np.log(got[:, col]) if col == 0 else got[:, col]
         assert ks_2samp(a, b).pvalue > 1e-3, col
+
+
+def test_oracle_evaluate_vs_reference_kdsource(oracle, golden_kdsource, tmp_path):
+    """oracle.evaluate (density, error estimate, J, jacobian, volume factor) against
+    KDSource.evaluate of the reference's own kdsource.py run in place."""
+    from kdsource_b200 import geom as kgeom
+    from kdsource_b200 import mcpl
+
+    g = golden_kdsource
+    fn = tmp_path / "list.mcpl.gz"
+    fn.write_bytes(g["list_mcpl_gz"].tobytes())
+    with mcpl.MCPLFile(str(fn), blocklength=10 ** 6) as f:
+        pb = f.read_block()
+    parts = np.stack((pb.ekin, pb.x, pb.y, pb.z, pb.ux, pb.uy, pb.uz, pb.time), axis=1)
+    geo = kgeom.Geometry([kgeom.Lethargy(10), kgeom.SurfXY(), kgeom.Isotrop()])
+    scaling = g["g_scaling"]
+    data = geo.transform(parts.copy()) / scaling
+    q = g["queries"]
+    ev, er = oracle.evaluate(geo.transform(q.copy()), geo.jac(q.copy()), data, pb.weight,
+                             float(g["g_bw"]), scaling, 3.5, float(g["g_N_eff"]), 6)
+    assert np.allclose(ev, g["g_evaluate"], rtol=1e-12)
+    assert np.allclose(er, g["g_evaluate_err"], rtol=1e-12)
