@@ -317,6 +317,40 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
                      "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": bytes_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "per_unit": "76 B per particle (40 read + 36 written)", "traffic": None}}
+    # device gzip of those records (gz_size + gz_scan + gz_encode kernels): algorithmic bytes
+    # = 2 reads of the records + the compressed stream written
+    nb = nout * 36
+    member = int(L.kdsb200_gz_member_bytes())
+    hist = _lib.empty(258, t.int64)
+    _lib.check(L.kdsb200_gz_histogram(_lib.ptr(out), min(nb, 64 << 20) // 36 * 36, member, 36, 12,
+                                      _lib.ptr(hist), _lib.stream()))
+    hh = hist.cpu().numpy().astype(np.uint64)
+    table = _lib.GzTable()
+    _lib.check(L.kdsb200_gz_build_table(hh.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), 36, 12,
+                                        ctypes.byref(table)))
+    cap = (nb + nb // 4 + (1 << 20)) // 4 * 4
+    gz_out = _lib.empty(cap, t.uint8)
+    gz_scr = _lib.empty(int(L.kdsb200_gz_scratch_bytes(nb, member)), t.uint8)
+    gz_tot = _lib.empty(1, t.int64)
+
+    def gz():
+        _lib.check(L.kdsb200_gz_compress(_lib.ptr(out), nb, member, ctypes.byref(table),
+                                         _lib.ptr(gz_scr), _lib.ptr(gz_out), cap, _lib.ptr(gz_tot),
+                                         _lib.stream()))
+
+    for _ in range(2):
+        gz()
+    ms = float(np.median(time_events(t, gz, 3)))
+    zbytes = int(gz_tot.cpu()[0])
+    sub["resample"]["gzip_device"] = {
+        "particles_per_s": nout / (ms * 1e-3), "ms": ms, "ratio": zbytes / nb,
+        "roofline": {"bound": "hbm", "achieved": (2.0 * nb + zbytes) / (ms * 1e-3) / 1e9,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": (2.0 * nb + zbytes) / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "per_unit": "72 B read (two passes) + {:.1f} B written per particle; "
+                                 "includes the memset of the output buffer".format(zbytes / nout),
+                     "traffic": None}}
+    del gz_out, gz_scr
     if cpu:
         sub["resample"]["cpu_baseline"] = cpu_resample_baseline(ps, ws_, bws, sc_, cores)
     sub["resample"]["e2e"] = resample_e2e(ps, ws_, bws, gs_, sc_, quick)
@@ -380,21 +414,22 @@ def resample_e2e(ps, ws_, bws, gs_, sc_, quick):
         src.fit(scaling=sc_)
         xml = src.save("src.xml", adjust_N=False)
         res = {}
-        for level in (1, 0):
+        for name, level in (("gpu_gzip", None), ("host_zlib_level1", 1)):
             t0 = time.perf_counter()
             kds.resample_to_mcpl(xml, "out.mcpl.gz", nout, rng=1, force=True,
                                  compresslevel=level)
             dt = time.perf_counter() - t0
-            res["gzip{}".format(level)] = {"particles_per_s": nout / dt, "s": dt,
-                                            "file_bytes": os.path.getsize("out.mcpl.gz")}
+            res[name] = {"particles_per_s": nout / dt, "s": dt,
+                         "file_bytes": os.path.getsize("out.mcpl.gz")}
     finally:
         os.chdir(cwd)
         shutil.rmtree(tmp, ignore_errors=True)
-    return {"value": res["gzip1"]["particles_per_s"], "unit": "particles/s",
-            "api": "resample_to_mcpl(xml, out.mcpl.gz, {}) incl. XML/MCPL read, upload, "
-                   "D2H and gzip level 1 to {}".format(nout, base or "tmp"),
-            "d2h_bytes_per_step": 36 * nout, "h2d_bytes_per_step": Nl * 76,
-            "stored_gzip_level0": res["gzip0"], "gzip_level1": res["gzip1"]}
+    return {"value": res["gpu_gzip"]["particles_per_s"], "unit": "particles/s",
+            "api": "resample_to_mcpl(xml, out.mcpl.gz, {}) incl. XML + {}-particle MCPL read, "
+                   "upload, generation, device gzip, D2H and file write to {}".format(
+                       nout, Nl, base or "tmp"),
+            "d2h_bytes_per_step": res["gpu_gzip"]["file_bytes"], "h2d_bytes_per_step": Nl * 76,
+            "gpu_gzip": res["gpu_gzip"], "host_zlib_level1": res["host_zlib_level1"]}
 
 
 def run_ours(args):

@@ -166,11 +166,21 @@ typedef struct {
   uint8_t len[257];   /* code lengths, 1..15 */
   uint32_t hdr_bits;  /* length of the deflate block header (BFINAL..code lengths) */
   uint32_t hdr[64];   /* the block header, packed LSB first */
+  /* record mode: when the last tail_bytes of a record equal the previous record's, they
+   * are sent as one LZ77 match (length tail_bytes, distance rec_bytes) of match_nbits bits */
+  uint32_t rec_bytes, tail_bytes, match_bits, match_nbits;
 } kdsb200_gz_table;
-/* byte histogram of d_data (256 uint64 counters on the device) */
-int kdsb200_gz_histogram(const void* d_data, uint64_t nbytes, uint64_t* d_hist256, void* stream);
-/* host: Huffman table + block header from a histogram (every byte value stays encodable) */
-int kdsb200_gz_build_table(const uint64_t* h_hist256, kdsb200_gz_table* out);
+/* Histogram of the symbols the encoder will emit for d_data (258 uint64 counters on the
+ * device): bytes 0..255, [256] unused, [257] = records whose tail repeats.  rec_bytes = 0:
+ * plain byte stream (no matches); otherwise rec_bytes and tail_bytes are multiples of 4,
+ * member_bytes a multiple of 256 records and nbytes whole records. */
+int kdsb200_gz_histogram(const void* d_data, uint64_t nbytes, uint32_t member_bytes,
+                         uint32_t rec_bytes, uint32_t tail_bytes, uint64_t* d_hist258,
+                         void* stream);
+/* host: Huffman table + block header from that histogram (every byte value stays
+ * encodable, so the table is valid for data the histogram has not seen) */
+int kdsb200_gz_build_table(const uint64_t* h_hist258, uint32_t rec_bytes, uint32_t tail_bytes,
+                           kdsb200_gz_table* out);
 uint32_t kdsb200_gz_member_bytes(void); /* default member size: 2048 MCPL-3 records */
 uint64_t kdsb200_gz_scratch_bytes(uint64_t nbytes, uint32_t member_bytes);
 /* d_data (nbytes, multiple of 4) -> d_out (<= out_capacity bytes, multiple of 4);
@@ -184,7 +194,7 @@ int kdsb200_gz_compress(const void* d_data, uint64_t nbytes, uint32_t member_byt
  * host pieces (the MCPL header) are deflated with zlib as members of their own. */
 typedef struct kdsb200_gz_writer_s kdsb200_gz_writer;
 kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_bytes,
-                                          void* stream);
+                                          uint32_t rec_bytes, uint32_t tail_bytes, void* stream);
 int kdsb200_gz_writer_put_host(kdsb200_gz_writer* w, const void* h_data, uint64_t nbytes);
 int kdsb200_gz_writer_put_device(kdsb200_gz_writer* w, const void* d_data, uint64_t nbytes);
 int kdsb200_gz_writer_close(kdsb200_gz_writer* w, uint64_t* bytes_written);

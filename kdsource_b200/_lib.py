@@ -64,6 +64,10 @@ class GzTable(ctypes.Structure):
         ("len", ctypes.c_uint8 * 257),
         ("hdr_bits", ctypes.c_uint32),
         ("hdr", ctypes.c_uint32 * 64),
+        ("rec_bytes", ctypes.c_uint32),
+        ("tail_bytes", ctypes.c_uint32),
+        ("match_bits", ctypes.c_uint32),
+        ("match_nbits", ctypes.c_uint32),
     ]
 
 
@@ -111,13 +115,16 @@ _SIGNATURES = {
                                  c_i64,
                                  ctypes.POINTER(Geom), c_i32, c_u64, c_u64, c_u64, c_i64, c_void_p,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "kdsb200_gz_histogram": (c_int, [c_void_p, c_u64, c_void_p, c_void_p]),
-    "kdsb200_gz_build_table": (c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(GzTable)]),
+    "kdsb200_gz_histogram": (c_int, [c_void_p, c_u64, ctypes.c_uint32, ctypes.c_uint32,
+                                     ctypes.c_uint32, c_void_p, c_void_p]),
+    "kdsb200_gz_build_table": (c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint32,
+                                       ctypes.c_uint32, ctypes.POINTER(GzTable)]),
     "kdsb200_gz_member_bytes": (ctypes.c_uint32, []),
     "kdsb200_gz_scratch_bytes": (c_u64, [c_u64, ctypes.c_uint32]),
     "kdsb200_gz_compress": (c_int, [c_void_p, c_u64, ctypes.c_uint32, ctypes.POINTER(GzTable),
                                     c_void_p, c_void_p, c_u64, c_void_p, c_void_p]),
-    "kdsb200_gz_writer_open": (c_void_p, [ctypes.c_char_p, c_u64, c_void_p]),
+    "kdsb200_gz_writer_open": (c_void_p, [ctypes.c_char_p, c_u64, ctypes.c_uint32,
+                                          ctypes.c_uint32, c_void_p]),
     "kdsb200_gz_writer_put_host": (c_int, [c_void_p, c_void_p, c_u64]),
     "kdsb200_gz_writer_put_device": (c_int, [c_void_p, c_void_p, c_u64]),
     "kdsb200_gz_writer_close": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint64)]),

@@ -6,9 +6,11 @@
 // deflate them (zlib level 1 on 16 cores: ~1e7 particles/s), so the compression runs
 // on the device too: the record stream is cut into members of `member_bytes`, each
 // member becomes one complete gzip member (RFC 1952) holding a single dynamic-Huffman
-// deflate block (RFC 1951) of literals only -- no LZ77 matches; MCPL-3 records are
-// floats, the gain of level-1 zlib over an order-0 Huffman code is a few percent --
-// and the members are laid out back to back.  Concatenated gzip members are a valid
+// deflate block (RFC 1951): Huffman-coded literals plus, for fixed-size records, one
+// kind of LZ77 match -- "the last `tail_bytes` of this record repeat the previous
+// record's" (distance = record size), which is what the constant time / weight /
+// pdgcode fields of a resampled MCPL list are.  That brings the file size to within
+// a few percent of level-1 zlib.  The members are laid out back to back.  Concatenated gzip members are a valid
 // gzip file for zlib's gzread (libmcpl), gzip(1) and Python's gzip module.
 //
 //   pass 1 (gz_size_kernel)   per member: code-length sum per thread, CRC-32
@@ -35,6 +37,8 @@ constexpr uint32_t CRC_POLY = 0xEDB88320u;  // reflected CRC-32 (IEEE 802.3), as
 // device image of the table (uploaded at the start of every compress call)
 struct GzDev {
   uint32_t entry[257];   // len << 16 | bit-reversed code
+  uint32_t rec_bytes, tail_bytes;       // record-aware mode (0: plain byte stream)
+  uint32_t match_bits, match_nbits;     // length code + extra + distance code + extra
   uint32_t hdr_bits;
   uint32_t hdr[64];
   uint32_t crc_tab[256];
@@ -154,21 +158,47 @@ static void crc_advance_matrix(uint64_t nbytes, uint32_t* out) {
 }
 
 // ---- device ---------------------------------------------------------------------
+// does the tail of the record at member offset o repeat the previous record's tail?
+// (the first record of a member has no history: every member is its own stream)
+__device__ __forceinline__ bool gz_tail_match(const unsigned char* member, uint32_t o, uint32_t R,
+                                              uint32_t S) {
+  if (o < R) return false;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(member + o + R - S);
+  const uint32_t* b = reinterpret_cast<const uint32_t*>(member + o - S);
+  bool eq = true;
+  for (uint32_t k = 0; k < S / 4; k++) eq = eq && (__ldg(a + k) == __ldg(b + k));
+  return eq;
+}
+
+// histogram of the symbols the encoder will emit: bytes 0..255, [257] = tail matches
 __global__ void gz_hist_kernel(const unsigned char* __restrict__ data, uint64_t nbytes,
+                               uint32_t member_bytes, uint32_t R, uint32_t S,
                                unsigned long long* __restrict__ hist) {
-  __shared__ unsigned int h[256];
-  h[threadIdx.x] = 0;
+  __shared__ unsigned int h[258];
+  for (int i = threadIdx.x; i < 258; i += blockDim.x) h[i] = 0;
   __syncthreads();
-  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i + 4 <= nbytes;
-       i += (uint64_t)gridDim.x * blockDim.x * 4) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(data + i);
-    atomicAdd(&h[w & 255u], 1u);
-    atomicAdd(&h[(w >> 8) & 255u], 1u);
-    atomicAdd(&h[(w >> 16) & 255u], 1u);
-    atomicAdd(&h[w >> 24], 1u);
+  const uint64_t step = R ? R : 4;
+  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * step; i + step <= nbytes;
+       i += (uint64_t)gridDim.x * blockDim.x * step) {
+    uint32_t lit = (uint32_t)step;
+    if (R && S) {
+      const uint64_t mbase = i / member_bytes * member_bytes;
+      if (gz_tail_match(data + mbase, (uint32_t)(i - mbase), R, S)) {
+        lit -= S;
+        atomicAdd(&h[257], 1u);
+      }
+    }
+    for (uint32_t o = 0; o < lit; o += 4) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(data + i + o);
+      atomicAdd(&h[w & 255u], 1u);
+      atomicAdd(&h[(w >> 8) & 255u], 1u);
+      atomicAdd(&h[(w >> 16) & 255u], 1u);
+      atomicAdd(&h[w >> 24], 1u);
+    }
   }
   __syncthreads();
-  if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+  for (int i = threadIdx.x; i < 258; i += blockDim.x)
+    if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
 }
 
 // chunk of thread t in a member of nb bytes: right-aligned frames of `chunk` bytes, so
@@ -210,13 +240,24 @@ __global__ void __launch_bounds__(GZ_THREADS)
   gz_chunk(nb, member_bytes / GZ_THREADS, t, lo, hi);
   uint32_t bits = 0, crc = 0;
   const unsigned char* p = data + base;
-  for (uint32_t o = lo; o < hi; o += 4) {  // chunks are multiples of 4 bytes
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + o));
+  const uint32_t R = T->rec_bytes, S = T->tail_bytes, mbits = T->match_nbits;
+  // chunks are whole records (or multiples of 4 bytes in plain mode)
+  for (uint32_t r = lo; r < hi; r += R ? R : (hi - lo)) {
+    const uint32_t rend = R ? r + R : hi;
+    uint32_t lit_end = rend;
+    if (S && gz_tail_match(p, r, R, S)) {
+      lit_end -= S;
+      bits += mbits;
+    }
+    for (uint32_t o = r; o < rend; o += 4) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + o));
+      const bool lit = o < lit_end;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t b = (w >> (8 * k)) & 255u;
-      bits += s_len[b];
-      crc = s_crc[(crc ^ b) & 255u] ^ (crc >> 8);
+      for (int k = 0; k < 4; k++) {
+        const uint32_t b = (w >> (8 * k)) & 255u;
+        if (lit) bits += s_len[b];
+        crc = s_crc[(crc ^ b) & 255u] ^ (crc >> 8);
+      }
     }
   }
   thread_bits[m * GZ_THREADS + t] = bits;
@@ -361,9 +402,9 @@ __global__ void __launch_bounds__(GZ_THREADS)
   uint32_t* wp = words + (start >> 5);
   bool first = true;
   const unsigned char* p = data + base;
-  auto emit = [&](uint32_t e) {
-    acc |= (uint64_t)(e & 0xffffu) << nbit;
-    nbit += e >> 16;
+  auto emit_bits = [&](uint32_t v, uint32_t n) {  // n <= 32 bits, LSB first
+    acc |= (uint64_t)v << nbit;
+    nbit += n;
     if (nbit >= 32u) {
       if (first) {
         atomicOr(wp, (uint32_t)acc);
@@ -376,12 +417,21 @@ __global__ void __launch_bounds__(GZ_THREADS)
       nbit -= 32u;
     }
   };
-  for (uint32_t o = lo; o < hi; o += 4) {
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + o));
-    emit(s_ent[w & 255u]);
-    emit(s_ent[(w >> 8) & 255u]);
-    emit(s_ent[(w >> 16) & 255u]);
-    emit(s_ent[w >> 24]);
+  auto emit = [&](uint32_t e) { emit_bits(e & 0xffffu, e >> 16); };
+  const uint32_t R = T->rec_bytes, S = T->tail_bytes;
+  const uint32_t mcode = T->match_bits, mbits = T->match_nbits;
+  for (uint32_t r = lo; r < hi; r += R ? R : (hi - lo)) {
+    uint32_t lit_end = R ? r + R : hi;
+    const bool match = S && gz_tail_match(p, r, R, S);
+    if (match) lit_end -= S;
+    for (uint32_t o = r; o < lit_end; o += 4) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + o));
+      emit(s_ent[w & 255u]);
+      emit(s_ent[(w >> 8) & 255u]);
+      emit(s_ent[(w >> 16) & 255u]);
+      emit(s_ent[w >> 24]);
+    }
+    if (match) emit_bits(mcode, mbits);
   }
   if (t == GZ_THREADS - 1) emit(s_ent[256]);  // end of block
   if (nbit) atomicOr(wp, (uint32_t)acc);
@@ -393,32 +443,85 @@ using namespace kdsb;
 
 extern "C" {
 
-int kdsb200_gz_histogram(const void* d_data, uint64_t nbytes, uint64_t* d_hist256, void* stream) {
+static int gz_check_records(uint32_t member_bytes, uint32_t rec_bytes, uint32_t tail_bytes,
+                            uint64_t nbytes) {
+  if (member_bytes == 0 || member_bytes % (GZ_THREADS * 4) != 0 || nbytes % 4 != 0 ||
+      member_bytes > (1u << 24)) {
+    set_error("gzip: member_bytes must be a multiple of %d (<= 2^24) and nbytes of 4",
+              GZ_THREADS * 4);
+    return 1;
+  }
+  if (rec_bytes == 0) return 0;
+  if (rec_bytes % 4 || tail_bytes % 4 || tail_bytes > rec_bytes || rec_bytes > 32768 ||
+      (tail_bytes && (tail_bytes < 4 || tail_bytes > 256)) ||
+      member_bytes % (GZ_THREADS * rec_bytes) != 0 || nbytes % rec_bytes != 0) {
+    set_error("gzip: record mode needs rec_bytes %% 4 == 0 (<= 32768), tail_bytes in 4..256 "
+              "(%% 4 == 0), member_bytes a multiple of %d records and whole records",
+              GZ_THREADS);
+    return 1;
+  }
+  return 0;
+}
+
+int kdsb200_gz_histogram(const void* d_data, uint64_t nbytes, uint32_t member_bytes,
+                         uint32_t rec_bytes, uint32_t tail_bytes, uint64_t* d_hist258,
+                         void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  KDSB_CUDA(cudaMemsetAsync(d_hist256, 0, 256 * sizeof(uint64_t), st));
+  KDSB_CUDA(cudaMemsetAsync(d_hist258, 0, 258 * sizeof(uint64_t), st));
   if (nbytes < 4) return 0;
-  const uint64_t words = nbytes / 4;
-  const unsigned blocks = (unsigned)std::min<uint64_t>((words + 255) / 256, (uint64_t)sm_count() * 8);
-  gz_hist_kernel<<<blocks, 256, 0, st>>>((const unsigned char*)d_data, nbytes,
-                                         (unsigned long long*)d_hist256);
+  if (gz_check_records(member_bytes, rec_bytes, tail_bytes, nbytes)) return 1;
+  const uint64_t units = nbytes / (rec_bytes ? rec_bytes : 4);
+  const unsigned blocks = (unsigned)std::min<uint64_t>((units + 255) / 256, (uint64_t)sm_count() * 8);
+  gz_hist_kernel<<<blocks, 256, 0, st>>>((const unsigned char*)d_data, nbytes, member_bytes,
+                                         rec_bytes, tail_bytes, (unsigned long long*)d_hist258);
   KDSB_CUDA(cudaGetLastError());
   return 0;
 }
 
-int kdsb200_gz_build_table(const uint64_t* h_hist256, kdsb200_gz_table* out) {
+int kdsb200_gz_build_table(const uint64_t* h_hist258, uint32_t rec_bytes, uint32_t tail_bytes,
+                           kdsb200_gz_table* out) {
   memset(out, 0, sizeof(*out));
-  uint64_t freq[257];
-  for (int i = 0; i < 256; i++) freq[i] = h_hist256[i] + 1;  // every byte stays encodable
+  // RFC 1951 3.2.5: length / distance symbols with their base values and extra bits
+  static const uint16_t lbase[29] = {3,  4,  5,  6,  7,  8,  9,  10, 11,  13,  15,  17,  19,  23, 27,
+                                     31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+  static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2,
+                                   2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+  static const uint16_t dbase[30] = {1,   2,   3,   4,   5,   7,    9,    13,   17,   25,
+                                     33,  49,  65,  97,  129, 193,  257,  385,  513,  769,
+                                     1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+  static const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2,  2,  3,  3,  4,  4,  5,  5,  6,
+                                   6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+  const bool use_match = rec_bytes && tail_bytes >= 3 && tail_bytes <= 258 &&
+                         rec_bytes <= 32768 && h_hist258[257] > 0;
+  int lsym = 0, dsym = 0;
+  if (use_match) {
+    while (lsym < 28 && lbase[lsym + 1] <= tail_bytes) lsym++;
+    while (dsym < 29 && dbase[dsym + 1] <= rec_bytes) dsym++;
+  }
+  const int nlit = use_match ? 257 + lsym + 1 : 257;  // literal/length codes sent
+  std::vector<uint64_t> freq(nlit, 0);
+  for (int i = 0; i < 256; i++) freq[i] = h_hist258[i] + 1;  // every byte stays encodable
   freq[256] = 1;                                             // end of block
-  huffman_lengths(freq, 257, 15, out->len);
-  canonical_codes(out->len, 257, out->code);
-  // code lengths of the 257 literal/length codes + one distance code of length 0
-  // ("no distance codes", RFC 1951 3.2.7), each sent as a plain code-length symbol
-  uint8_t seq[258];
-  memcpy(seq, out->len, 257);
-  seq[257] = 0;
+  if (use_match) freq[257 + lsym] = h_hist258[257];
+  std::vector<uint8_t> len(nlit);
+  std::vector<uint32_t> code(nlit);
+  huffman_lengths(freq.data(), nlit, 15, len.data());
+  canonical_codes(len.data(), nlit, code.data());
+  memcpy(out->len, len.data(), 257);
+  memcpy(out->code, code.data(), 257 * sizeof(uint32_t));
+  // code lengths of the literal/length codes, then of the distance codes: either one
+  // code of length 0 ("no distance codes", RFC 1951 3.2.7) or codes 0..dsym with only
+  // the last one in use (a single distance code is sent with length 1)
+  std::vector<uint8_t> seq(len);
+  if (use_match) {
+    for (int i = 0; i < dsym; i++) seq.push_back(0);
+    seq.push_back(1);
+  } else {
+    seq.push_back(0);
+  }
+  const int ndist = use_match ? dsym + 1 : 1;
   uint64_t clfreq[19] = {0};
-  for (int i = 0; i < 258; i++) clfreq[seq[i]]++;
+  for (uint8_t v : seq) clfreq[v]++;
   uint8_t cllen[19];
   uint32_t clcode[19];
   huffman_lengths(clfreq, 19, 7, cllen);
@@ -427,14 +530,33 @@ int kdsb200_gz_build_table(const uint64_t* h_hist256, kdsb200_gz_table* out) {
   int hclen = 19;
   while (hclen > 4 && cllen[order[hclen - 1]] == 0) hclen--;
   BitWriter bw(out->hdr, 64 * 32);
-  bool ok = bw.put(1, 1) && bw.put(2, 2) && bw.put(0, 5) && bw.put(0, 5) && bw.put(hclen - 4, 4);
+  bool ok = bw.put(1, 1) && bw.put(2, 2) && bw.put(nlit - 257, 5) && bw.put(ndist - 1, 5) &&
+            bw.put(hclen - 4, 4);
   for (int i = 0; i < hclen && ok; i++) ok = bw.put(cllen[order[i]], 3);
-  for (int i = 0; i < 258 && ok; i++) ok = bw.put(clcode[seq[i]], cllen[seq[i]]);
+  for (size_t i = 0; i < seq.size() && ok; i++) ok = bw.put(clcode[seq[i]], cllen[seq[i]]);
   if (!ok) {
     set_error("gz_build_table: block header does not fit %d bits", 64 * 32);
     return 1;
   }
   out->hdr_bits = bw.nbits;
+  if (use_match) {
+    // <length code><length extra bits><distance code: the single 1-bit code 0><extra bits>
+    uint32_t words[2] = {0, 0};
+    BitWriter mw(words, 64);
+    mw.put(code[257 + lsym], len[257 + lsym]);
+    mw.put(tail_bytes - lbase[lsym], lext[lsym]);
+    mw.put(0, 1);
+    mw.put(rec_bytes - dbase[dsym], dext[dsym]);
+    if (mw.nbits <= 32) {
+      out->rec_bytes = rec_bytes;
+      out->tail_bytes = tail_bytes;
+      out->match_bits = words[0];
+      out->match_nbits = mw.nbits;
+    } else {
+      set_error("gz_build_table: match code longer than 32 bits");
+      return 1;
+    }
+  }
   return 0;
 }
 
@@ -454,14 +576,7 @@ int kdsb200_gz_compress(const void* d_data, uint64_t nbytes, uint32_t member_byt
     KDSB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st));
     return 0;
   }
-  if (member_bytes == 0 || member_bytes % (GZ_THREADS * 4) != 0 || nbytes % 4 != 0) {
-    set_error("gz_compress: member_bytes must be a multiple of %d and nbytes of 4", GZ_THREADS * 4);
-    return 1;
-  }
-  if (member_bytes > (1u << 24)) {
-    set_error("gz_compress: member_bytes too large");
-    return 1;
-  }
+  if (gz_check_records(member_bytes, h_table->rec_bytes, h_table->tail_bytes, nbytes)) return 1;
   if ((reinterpret_cast<uintptr_t>(d_data) & 3) || (reinterpret_cast<uintptr_t>(d_out) & 3) ||
       (reinterpret_cast<uintptr_t>(d_scratch) & 7) || (out_capacity & 3)) {
     set_error("gz_compress: buffers must be 4-byte aligned (scratch 8), capacity a multiple of 4");
@@ -476,6 +591,10 @@ int kdsb200_gz_compress(const void* d_data, uint64_t nbytes, uint32_t member_byt
   static thread_local GzDev img;
   for (int i = 0; i < 257; i++) img.entry[i] = ((uint32_t)h_table->len[i] << 16) | h_table->code[i];
   img.hdr_bits = h_table->hdr_bits;
+  img.rec_bytes = h_table->rec_bytes;
+  img.tail_bytes = h_table->tail_bytes;
+  img.match_bits = h_table->match_bits;
+  img.match_nbits = h_table->match_nbits;
   memcpy(img.hdr, h_table->hdr, sizeof(img.hdr));
   for (uint32_t n = 0; n < 256; n++) {
     uint32_t c = n;

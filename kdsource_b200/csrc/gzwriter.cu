@@ -34,7 +34,7 @@ struct kdsb200_gz_writer_s {
   int fd = -1;
   cudaStream_t st = nullptr;
   uint64_t cap = 0, file_off = 0;
-  uint32_t member = 0;
+  uint32_t member = 0, rec_bytes = 0, tail_bytes = 0;
   bool have_table = false;
   kdsb200_gz_table table;
   unsigned char* d_out[2] = {nullptr, nullptr};
@@ -42,7 +42,7 @@ struct kdsb200_gz_writer_s {
   unsigned char* d_scratch = nullptr;
   uint64_t* d_total = nullptr;
   uint64_t* d_hist = nullptr;
-  uint64_t* h_small = nullptr;  // pinned: [0] total, [1..256] histogram
+  uint64_t* h_small = nullptr;  // pinned: [0] total, [1..258] histogram
   cudaEvent_t ev[2] = {nullptr, nullptr};
   int next_slot = 0, write_threads = 4;
   // worker
@@ -114,9 +114,14 @@ using namespace kdsb;
 extern "C" {
 
 kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_bytes,
-                                          void* stream) {
+                                          uint32_t rec_bytes, uint32_t tail_bytes, void* stream) {
   if (max_batch_bytes == 0 || (max_batch_bytes & 3)) {
     set_error("gz_writer_open: max_batch_bytes must be a positive multiple of 4");
+    return nullptr;
+  }
+  if (rec_bytes && (kdsb200_gz_member_bytes() % (256 * rec_bytes) != 0 || rec_bytes % 4 ||
+                    tail_bytes % 4 || tail_bytes > rec_bytes || tail_bytes > 256)) {
+    set_error("gz_writer_open: unsupported record layout (%u, %u)", rec_bytes, tail_bytes);
     return nullptr;
   }
   kdsb200_gz_writer_s* w = new kdsb200_gz_writer_s();
@@ -128,6 +133,8 @@ kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_b
   }
   w->st = (cudaStream_t)stream;
   w->member = kdsb200_gz_member_bytes();
+  w->rec_bytes = rec_bytes;
+  w->tail_bytes = tail_bytes;
   // Huffman coding never needs more than 15 bits per byte, but a table built from the
   // first batch keeps the typical output below the input; leave generous headroom
   w->cap = (max_batch_bytes + max_batch_bytes / 4 + (1u << 20) + 3) / 4 * 4;
@@ -140,8 +147,8 @@ kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_b
   }
   ok = ok && cudaMalloc(&w->d_scratch, scratch) == cudaSuccess;
   ok = ok && cudaMalloc(&w->d_total, 8) == cudaSuccess;
-  ok = ok && cudaMalloc(&w->d_hist, 256 * 8) == cudaSuccess;
-  ok = ok && cudaMallocHost(&w->h_small, 257 * 8) == cudaSuccess;
+  ok = ok && cudaMalloc(&w->d_hist, 258 * 8) == cudaSuccess;
+  ok = ok && cudaMallocHost(&w->h_small, 259 * 8) == cudaSuccess;
   if (!ok) {
     set_error("gz_writer_open: out of device or pinned memory (batch of %llu bytes)",
               (unsigned long long)max_batch_bytes);
@@ -200,12 +207,20 @@ int kdsb200_gz_writer_put_device(kdsb200_gz_writer* w, const void* d_data, uint6
               (unsigned long long)nbytes, (unsigned long long)max_in);
     return 1;
   }
+  if (w->rec_bytes && nbytes % w->rec_bytes) {
+    set_error("gz_writer_put_device: %llu bytes are not whole %u-byte records",
+              (unsigned long long)nbytes, w->rec_bytes);
+    return 1;
+  }
   if (!w->have_table) {  // one Huffman table for the whole file, from the first batch
-    const uint64_t sample = nbytes < (64u << 20) ? nbytes : (64u << 20);
-    if (kdsb200_gz_histogram(d_data, sample, w->d_hist, w->st)) return 1;
-    KDSB_CUDA(cudaMemcpyAsync(w->h_small + 1, w->d_hist, 256 * 8, cudaMemcpyDeviceToHost, w->st));
+    uint64_t sample = nbytes < (64u << 20) ? nbytes : (64u << 20);
+    if (w->rec_bytes) sample -= sample % w->rec_bytes;
+    if (kdsb200_gz_histogram(d_data, sample, w->member, w->rec_bytes, w->tail_bytes, w->d_hist,
+                             w->st))
+      return 1;
+    KDSB_CUDA(cudaMemcpyAsync(w->h_small + 1, w->d_hist, 258 * 8, cudaMemcpyDeviceToHost, w->st));
     KDSB_CUDA(cudaStreamSynchronize(w->st));
-    if (kdsb200_gz_build_table(w->h_small + 1, &w->table)) return 1;
+    if (kdsb200_gz_build_table(w->h_small + 1, w->rec_bytes, w->tail_bytes, &w->table)) return 1;
     w->have_table = true;
   }
   const int slot = w->next_slot;

@@ -159,7 +159,8 @@ def _write_gpu_gzip(path, header, batches, batch):
     import ctypes
 
     L = _lib.load()
-    w = L.kdsb200_gz_writer_open(os.fsencode(path), batch * 36, _lib.stream())
+    # MCPL-3 records: 36 bytes, the last 12 (time, weight, pdgcode) usually repeat
+    w = L.kdsb200_gz_writer_open(os.fsencode(path), batch * 36, 36, 12, _lib.stream())
     if not w:
         _lib.check(1)
     w = ctypes.c_void_p(w)

@@ -486,7 +486,7 @@ def test_kdsource_pipeline_fit_evaluate_save_load(oracle, tmp_path, monkeypatch)
 
 
 # ------------------------------------------------------------------ device gzip
-def _gz_compress(L, t, data, member=None):
+def _gz_compress(L, t, data, member=None, rec=0, tail=0):
     import ctypes
 
     from kdsource_b200 import _lib
@@ -494,14 +494,16 @@ def _gz_compress(L, t, data, member=None):
     d = t.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
     n = len(data)
     member = member or L.kdsb200_gz_member_bytes()
-    hist = _lib.empty(256, t.int64)
-    _lib.check(L.kdsb200_gz_histogram(_lib.ptr(d), n, _lib.ptr(hist), _lib.stream()))
+    hist = _lib.empty(258, t.int64)
+    _lib.check(L.kdsb200_gz_histogram(_lib.ptr(d), n, member, rec, tail, _lib.ptr(hist),
+                                      _lib.stream()))
     h = hist.cpu().numpy().astype(np.uint64)
-    assert np.array_equal(h, np.bincount(np.frombuffer(data, np.uint8)[:n // 4 * 4],
-                                         minlength=256).astype(np.uint64))
+    if not rec:
+        assert np.array_equal(h[:256], np.bincount(np.frombuffer(data, np.uint8)[:n // 4 * 4],
+                                                   minlength=256).astype(np.uint64))
     T = _lib.GzTable()
     _lib.check(L.kdsb200_gz_build_table(h.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
-                                        ctypes.byref(T)))
+                                        rec, tail, ctypes.byref(T)))
     cap = (n * 2 + 4096) // 4 * 4
     out = _lib.empty(cap, t.uint8)
     scratch = _lib.empty(L.kdsb200_gz_scratch_bytes(n, member), t.uint8)
@@ -553,6 +555,26 @@ def test_device_gzip_roundtrip():
     # small member size (more members, other chunk length)
     data = cases["many_members_ragged"][:1024 * 50 + 40]
     assert gzip.decompress(_gz_compress(L, t, data, member=1024)) == data
+    # record mode (MCPL-3 layout): constant tails become matches; tails that change,
+    # member boundaries (no history) and partial members still round-trip
+    nrec = 2048 * 5 + 777
+    rec = rng.integers(0, 256, (nrec, 36), dtype=np.uint8)
+    rec[:, 24:] = np.frombuffer(np.array([0.0, 1.0], np.float32).tobytes()
+                                + np.int32(2112).tobytes(), np.uint8)
+    rec[rng.integers(0, nrec, 300), 28:32] = rng.integers(0, 256, (300, 4), dtype=np.uint8)
+    data = rec.tobytes()
+    plain = _gz_compress(L, t, data)
+    matched = _gz_compress(L, t, data, rec=36, tail=12)
+    assert gzip.decompress(plain) == data and gzip.decompress(matched) == data
+    assert len(matched) < 0.93 * len(plain)
+    rec[:, 24:] = rng.integers(0, 256, (nrec, 12), dtype=np.uint8)  # no tail ever repeats
+    data = rec.tobytes()
+    assert gzip.decompress(_gz_compress(L, t, data, rec=36, tail=12)) == data
+    wide = np.repeat(rng.integers(0, 256, (1, 64), dtype=np.uint8), 256 * 9 + 3, axis=0)
+    wide[:, :8] = rng.integers(0, 256, (len(wide), 8), dtype=np.uint8)
+    data = wide.tobytes()
+    gz = _gz_compress(L, t, data, member=64 * 256 * 2, rec=64, tail=56)
+    assert gzip.decompress(gz) == data and len(gz) < 0.25 * len(data)
 
 
 def test_resample_to_mcpl_gpu_gzip_equals_host_gzip(oracle, tmp_path, monkeypatch):

@@ -402,17 +402,37 @@ def test_gzip_table_builder_inflates_with_zlib():
     L = _lib.load()
     rng = np.random.default_rng(0)
 
-    def roundtrip(data):
-        hist = np.bincount(np.frombuffer(data, np.uint8), minlength=256).astype(np.uint64)
+    def roundtrip(data, rec=0, tail=0):
+        """Pack the stream the way the device encoder does: literals, and in record mode
+        one (length tail, distance rec) match where a record's tail repeats."""
+        raw_in = np.frombuffer(data, np.uint8)
+        hist = np.zeros(258, dtype=np.uint64)
+        symbols = []  # byte values, 256 = end of block, 257 = tail match
+        if rec:
+            recs = raw_in.reshape(-1, rec)
+            for i, r in enumerate(recs):
+                m = i > 0 and np.array_equal(r[rec - tail:], recs[i - 1][rec - tail:])
+                symbols += list(r[:rec - tail] if m else r) + ([257] if m else [])
+        else:
+            symbols = list(raw_in)
+        hist[:258] = np.bincount(np.array(symbols + [257], dtype=np.int64), minlength=258)
+        hist[257] -= 1
+        hist[256] = 0
         T = _lib.GzTable()
         assert L.kdsb200_gz_build_table(hist.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
-                                        ctypes.byref(T)) == 0
+                                        rec, tail, ctypes.byref(T)) == 0
         lens = np.array(T.len[:])
         assert lens.min() >= 1 and lens.max() <= 15          # every symbol encodable
-        assert np.sum(2.0 ** -lens) == pytest.approx(1.0)    # complete prefix code
+        if not T.match_nbits:
+            assert np.sum(2.0 ** -lens) == pytest.approx(1.0)    # complete prefix code
+        else:
+            assert (T.rec_bytes, T.tail_bytes) == (rec, tail) and T.match_nbits <= 32
         bits = [(T.hdr[j >> 5] >> (j & 31)) & 1 for j in range(T.hdr_bits)]
-        for b in list(data) + [256]:
-            bits += [(T.code[b] >> k) & 1 for k in range(T.len[b])]
+        for b in symbols + [256]:
+            if b == 257:
+                bits += [(T.match_bits >> k) & 1 for k in range(T.match_nbits)]
+            else:
+                bits += [(T.code[b] >> k) & 1 for k in range(T.len[b])]
         bits += [0] * (-len(bits) % 8)
         raw = np.packbits(np.array(bits, dtype=np.uint8), bitorder="little").tobytes()
         assert zlib.decompress(raw, wbits=-15) == data
@@ -429,4 +449,13 @@ def test_gzip_table_builder_inflates_with_zlib():
     rec[:, 7] = 1.0
     raw = rec.view(np.uint8).copy()
     raw[:, 32:36] = np.frombuffer(np.int32(2112).tobytes(), np.uint8)
-    assert roundtrip(raw.tobytes()) < 0.8 * raw.size
+    plain = roundtrip(raw.tobytes())
+    assert plain < 0.8 * raw.size
+    # record mode: the constant (time, weight, pdgcode) tail becomes one match per record
+    assert roundtrip(raw.tobytes(), rec=36, tail=12) < 0.9 * plain
+    # other record layouts: long tails and distances with extra bits on both codes
+    rec2 = rng.integers(0, 256, (300, 100), dtype=np.uint8)
+    rec2[:, 40:] = rec2[0, 40:]
+    rec2[17, 99] ^= 1  # one record whose tail differs
+    assert roundtrip(rec2.tobytes(), rec=100, tail=60) < 0.55 * rec2.size
+    roundtrip(rec2.tobytes(), rec=100, tail=4)
