@@ -155,6 +155,24 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
                      const double* d_ext_uniforms, int slots, int perturb, void* d_out36,
                      int64_t* d_out_idx, double* d_out_parts, void* stream);
 
+/* ---- MCPL-3 records -> particles on the device: the decode step of PList_get /
+ * mcpl_read (clib/src/plist.c:69-89, python/kdsource/plist.py:349-395) ----------- */
+typedef struct {
+  int32_t record_bytes;     /* particle size from the file header */
+  int32_t single_precision; /* 1: float fields, 0: double */
+  int32_t off_pos;          /* byte offsets inside a record: position[3] */
+  int32_t off_dir;          /* packed direction (2 values) followed by signed ekin */
+  int32_t off_time;
+  int32_t off_weight;       /* -1: universal weight */
+  int32_t off_pdg;          /* -1: universal pdg code */
+  int32_t universal_pdg;
+  double universal_weight;
+} kdsb200_mcpl_layout;
+/* d_raw (n records, little endian) -> d_parts8 (n,8) fp64 [ekin,x,y,z,ux,uy,uz,t],
+ * d_weights (n) fp64, d_pdg (n) int32.  Bit-identical to the host decoder. */
+int kdsb200_mcpl_unpack(const void* d_raw, uint64_t n, const kdsb200_mcpl_layout* h_layout,
+                        double* d_parts8, double* d_weights, int32_t* d_pdg, void* stream);
+
 /* ---- gzip on the device: the output side of kdsource_resample_to_mcpl, which
  * always ends in mcpl_closeandgzip_outfile (clib/src/resamplemcpl.c:30-46) ------
  * The byte stream is cut into members of `member_bytes`; each becomes one gzip

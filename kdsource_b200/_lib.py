@@ -56,6 +56,22 @@ class Geom(ctypes.Structure):
     ]
 
 
+class McplLayout(ctypes.Structure):
+    """kdsb200_mcpl_layout"""
+
+    _fields_ = [
+        ("record_bytes", ctypes.c_int32),
+        ("single_precision", ctypes.c_int32),
+        ("off_pos", ctypes.c_int32),
+        ("off_dir", ctypes.c_int32),
+        ("off_time", ctypes.c_int32),
+        ("off_weight", ctypes.c_int32),
+        ("off_pdg", ctypes.c_int32),
+        ("universal_pdg", ctypes.c_int32),
+        ("universal_weight", ctypes.c_double),
+    ]
+
+
 class GzTable(ctypes.Structure):
     """kdsb200_gz_table"""
 
@@ -115,6 +131,8 @@ _SIGNATURES = {
                                  c_i64,
                                  ctypes.POINTER(Geom), c_i32, c_u64, c_u64, c_u64, c_i64, c_void_p,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kdsb200_mcpl_unpack": (c_int, [c_void_p, c_u64, ctypes.POINTER(McplLayout), c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
     "kdsb200_gz_histogram": (c_int, [c_void_p, c_u64, ctypes.c_uint32, ctypes.c_uint32,
                                      ctypes.c_uint32, c_void_p, c_void_p]),
     "kdsb200_gz_build_table": (c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint32,

@@ -7,6 +7,7 @@
 // generator, the PCIe copy and the file system work concurrently.  Small host-side
 // pieces (the MCPL header) go through zlib as a gzip member of their own.
 #include <fcntl.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -156,6 +157,12 @@ kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_b
     kdsb200_gz_writer_close(w, &dummy);
     return nullptr;
   }
+  // pwrite of slices on KDSB200_WRITE_THREADS threads (default 4).  Measured on tmpfs
+  // (1e9 particles, 22.5 GB): 2, 8 and 16 threads give the same 2.6 GB/s -- writes to one
+  // file serialise on its inode lock -- so this only helps file systems that stripe.
+  const char* e = getenv("KDSB200_WRITE_THREADS");
+  const int nt = e ? atoi(e) : 4;
+  w->write_threads = nt < 1 ? 1 : (nt > 64 ? 64 : nt);
   w->worker = std::thread(writer_loop, w);
   return w;
 }

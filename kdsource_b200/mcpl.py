@@ -287,6 +287,43 @@ class MCPLFile:
         self._pos += n
         return np.frombuffer(buf, dtype=self._dtype, count=n)
 
+    def read_raw_bytes(self, n):
+        """Up to n records as they lie in the file: (uint8 array, count) or (None, 0)."""
+        n = int(min(n, self.nparticles - self._pos))
+        if n <= 0:
+            return None, 0
+        buf = np.empty(n * self._dtype.itemsize, dtype=np.uint8)
+        view = memoryview(buf)
+        got = 0
+        while got < len(buf):
+            k = self._fh.readinto(view[got:])
+            if not k:
+                raise IOError("MCPL: unexpected end of file")
+            got += k
+        self._pos += n
+        return buf, n
+
+    def device_layout(self):
+        """Record layout for the device decoder (``kdsb200_mcpl_unpack``); None for
+        big-endian files, which only the host decoder reads."""
+        if self.hdr.endian != "<":
+            return None
+        from . import _lib
+
+        f = self._dtype.fields
+        lay = _lib.McplLayout()
+        lay.record_bytes = self._dtype.itemsize
+        lay.single_precision = int(bool(self.hdr.opt_singleprec))
+        lay.off_pos = f["pos"][1]
+        lay.off_dir = f["dirpack"][1]  # dirpack[2] is followed directly by ekin
+        lay.off_time = f["time"][1]
+        lay.off_weight = f["weight"][1] if "weight" in f else -1
+        lay.off_pdg = f["pdgcode"][1] if "pdgcode" in f else -1
+        lay.universal_pdg = int(self.hdr.opt_universalpdgcode)
+        lay.universal_weight = float(self.hdr.opt_universalweight)
+        assert f["ekin"][1] == lay.off_dir + 2 * (4 if lay.single_precision else 8)
+        return lay
+
     def read_block(self):
         rec = self.read_raw(self.blocklength)
         if rec is None:

@@ -123,6 +123,48 @@ class PList:
             parts = parts[:, [0, 2, 3, 1, 5, 6, 4, 7]]
         return parts, ws
 
+    def get_device(self, N=-1, skip=0):
+        """:meth:`get` for device-side consumers (the sampler): the records are uploaded
+        as they lie in the file and decoded by ``kdsb200_mcpl_unpack``; returns CUDA
+        tensors ``(parts (n,8) float64, ws (n,) float64)`` with the same values as
+        :meth:`get`.  Filtering and the rigid transformation use torch tensor ops
+        (buffer plumbing, not a compute path)."""
+        import ctypes
+
+        from . import _lib
+
+        L = _lib.load()
+        t = _lib.torch()
+        with mcpl.MCPLFile(self.filename) as pl:
+            lay = pl.device_layout()
+            if lay is None:  # big-endian file: host decoder
+                parts, ws = self.get(N, skip)
+                return _lib.to_dev(parts), _lib.to_dev(ws)
+            if N < 0:
+                N = pl.nparticles
+            pl.skip_forward(skip)
+            buf, n = pl.read_raw_bytes(N)
+        if n == 0:
+            return _lib.empty(0, t.float64).reshape(0, 8), _lib.empty(0, t.float64)
+        d_raw = t.from_numpy(buf).cuda()
+        parts = _lib.empty(n * 8, t.float64)
+        ws = _lib.empty(n, t.float64)
+        pdg = _lib.empty(n, t.int32)
+        _lib.check(L.kdsb200_mcpl_unpack(_lib.ptr(d_raw), n, ctypes.byref(lay), _lib.ptr(parts),
+                                         _lib.ptr(ws), _lib.ptr(pdg), _lib.stream()))
+        keep = (ws > 0) & (pdg == pt2pdg(self.pt))
+        parts = parts.reshape(n, 8)[keep]
+        ws = ws[keep]
+        if self.trasl is not None:
+            parts[:, 1:4] += t.as_tensor(self.trasl, dtype=t.float64, device="cuda")
+        if self.rot is not None:
+            R = t.as_tensor(self.rot.as_matrix(), dtype=t.float64, device="cuda")
+            parts[:, 1:4] = parts[:, 1:4] @ R.T
+            parts[:, 4:7] = parts[:, 4:7] @ R.T
+        if self.x2z:
+            parts = parts[:, [0, 2, 3, 1, 5, 6, 4, 7]]
+        return parts.contiguous(), ws.contiguous()
+
     def rotvec(self):
         return None if self.rot is None else np.asarray(self.rot.as_rotvec(), dtype=np.float64)
 

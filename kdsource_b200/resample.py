@@ -46,7 +46,7 @@ def open_source(kds_sourcefile, precision="float32"):
     scaling = np.array(root.find("scaling").text.split(), dtype="float64")
     bwel = root.find("BW")
     variable = bool(int(bwel.attrib["variable"]))
-    parts, ws = plist.get(-1)
+    parts, ws = plist.get_device(-1)  # decoded on the device, stays there
     if len(parts) == 0:
         raise RuntimeError("Empty particle list")
     if variable:

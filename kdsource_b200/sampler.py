@@ -69,13 +69,18 @@ class DeviceSampler:
     def __init__(self, parts, weights, bw, geom_struct, pdgcode=2112, precision="float32"):
         L = _lib.load()
         t = _lib.torch()
-        parts = np.ascontiguousarray(parts, dtype=np.float64)
-        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        on_device = t.is_tensor(parts)  # (N,8) / (N,) float64 CUDA tensors (PList.get_device)
+        if on_device:
+            parts = parts.to(device="cuda", dtype=t.float64).contiguous()
+            weights = weights.to(device="cuda", dtype=t.float64).contiguous()
+        else:
+            parts = np.ascontiguousarray(parts, dtype=np.float64)
+            weights = np.ascontiguousarray(weights, dtype=np.float64)
         if parts.ndim != 2 or parts.shape[1] != 8 or len(parts) == 0:
             raise ValueError("parts must have shape (N, 8) with N > 0")
         if len(weights) != len(parts):
             raise ValueError("weights must have one entry per particle")
-        if np.any(weights <= 0):
+        if bool((weights <= 0).any()):
             raise ValueError("weights must be positive (filter w <= 0 first)")
         if precision not in ("float32", "float64"):
             raise ValueError("precision must be 'float32' or 'float64'")
@@ -83,13 +88,15 @@ class DeviceSampler:
         self.precision = precision
         self.geom = geom_struct
         self.pdgcode = int(pdgcode)
-        self.sum_w = float(np.sum(weights))
-        d_parts = _lib.to_dev(parts)
+        # fp64 sum in a fixed order on the host (the CDF scale must not depend on where
+        # the list was decoded)
+        self.sum_w = float(np.sum(weights.cpu().numpy() if on_device else weights))
+        d_parts = parts if on_device else _lib.to_dev(parts)
         self.f32 = precision == "float32"
         self.src = _lib.empty(self.N * 8, t.float32 if self.f32 else t.float64)
         _lib.check(L.kdsb200_convert_particles(_lib.ptr(d_parts), self.N, int(self.f32),
                                                _lib.ptr(self.src), _lib.stream()))
-        d_w = _lib.to_dev(weights)
+        d_w = weights if on_device else _lib.to_dev(weights)
         scratch = _lib.empty(L.kdsb200_cdf_scratch_words(self.N), t.int64)
         self.cdf = _lib.empty(self.N, t.int64)  # uint64 payload
         _lib.check(L.kdsb200_weights_cdf(_lib.ptr(d_w), self.N, self.sum_w, _lib.ptr(scratch),

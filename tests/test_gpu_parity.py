@@ -683,3 +683,43 @@ def test_kdsource_vs_reference_golden(golden_kdsource, tmp_path, monkeypatch, ke
         _, (sc, e) = st.plot_t(g["grid_t"])
         close(sc, g["t"], "plot_t")
         close(e, g["t_err"], "plot_t errs")
+
+
+def test_plist_get_device_equals_host_decoder(oracle, tmp_path):
+    """kdsb200_mcpl_unpack (records decoded on the device) against the host decoder,
+    bit for bit: single/double precision, universal weight / pdg code, polarisation and
+    user flags in the record, invalid particles filtered, translation/rotation/x2z."""
+    from kdsource_b200 import mcpl
+    from kdsource_b200.plist import PList
+
+    parts, w = oracle.synthetic_particles(5000, seed=31, wseed=32, z_spread=3.0)
+    parts[:, 7] = np.random.default_rng(1).uniform(0, 5, len(parts))
+    w[::17] = 0.0                      # invalid: dropped
+    pdg = np.full(len(parts), 2112, dtype=np.int32)
+    pdg[::23] = 22                     # other particle type: dropped
+    cols = dict(ekin=parts[:, 0], x=parts[:, 1], y=parts[:, 2], z=parts[:, 3], ux=parts[:, 4],
+                uy=parts[:, 5], uz=parts[:, 6], time=parts[:, 7])
+    one = np.ones(len(parts))
+    variants = {
+        "single": dict(weight=w, pdgcode=pdg),
+        "double": dict(weight=w, pdgcode=pdg, double_prec=True),
+        "universal": dict(weight=2.5, pdgcode=2112),
+        "pol_flags": dict(weight=w, pdgcode=pdg, polx=0.1 * one, poly=0.2 * one, polz=0.3 * one,
+                          userflags=np.arange(len(parts), dtype=np.uint32), double_prec=True),
+    }
+    for name, kw in variants.items():
+        fn = str(tmp_path / (name + ".mcpl.gz"))
+        mcpl.write_mcpl_file(fn, srcname="t", **cols, **kw)
+        for plkw in (dict(), dict(trasl=[1.0, -2.0, 0.5], rot=[0.1, 0.2, -0.3], switch_x2z=True)):
+            pl = PList(fn, set_params=False, **plkw)
+            hp, hw = pl.get(-1)
+            dp, dw = pl.get_device(-1)
+            assert dp.shape == hp.shape and len(hp) > 0, name
+            assert np.array_equal(dw.cpu().numpy(), hw), name
+            if plkw:
+                assert np.allclose(dp.cpu().numpy(), hp, rtol=1e-13, atol=1e-13), name
+            else:
+                assert np.array_equal(dp.cpu().numpy(), hp), name
+        hp, hw = PList(fn, set_params=False).get(100, skip=4000)
+        dp, dw = PList(fn, set_params=False).get_device(100, skip=4000)
+        assert np.array_equal(dp.cpu().numpy(), hp) and np.array_equal(dw.cpu().numpy(), hw)

@@ -41,4 +41,30 @@ if which in ("all", "resample"):
     for _ in range(3):
         smp.sample_device(10_000_000, seed=1)
     t.cuda.synchronize()
+if which in ("all", "gzip"):
+    import ctypes
+
+    L = _lib.load()
+    bws = np.random.default_rng(3).uniform(0.2, 0.5, N).astype(np.float32)
+    smp = DeviceSampler(parts, w, bws, make_geom_struct(g, scaling, "g"))
+    n = 10_000_000
+    rec = smp.sample_device(n, seed=1)["records"]
+    nb, member = n * 36, int(L.kdsb200_gz_member_bytes())
+    hist = _lib.empty(258, t.int64)
+    _lib.check(L.kdsb200_gz_histogram(_lib.ptr(rec), 64 << 20, member, 36, 12, _lib.ptr(hist),
+                                      _lib.stream()))
+    hh = hist.cpu().numpy().astype(np.uint64)
+    table = _lib.GzTable()
+    _lib.check(L.kdsb200_gz_build_table(hh.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), 36, 12,
+                                        ctypes.byref(table)))
+    cap = (nb + nb // 4 + (1 << 20)) // 4 * 4
+    out = _lib.empty(cap, t.uint8)
+    scr = _lib.empty(int(L.kdsb200_gz_scratch_bytes(nb, member)), t.uint8)
+    tot = _lib.empty(1, t.int64)
+    for _ in range(3):
+        _lib.check(L.kdsb200_gz_compress(_lib.ptr(rec), nb, member, ctypes.byref(table),
+                                         _lib.ptr(scr), _lib.ptr(out), cap, _lib.ptr(tot),
+                                         _lib.stream()))
+    t.cuda.synchronize()
+    print("gzip ratio", int(tot.cpu()[0]) / nb)
 print("done", which)

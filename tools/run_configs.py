@@ -208,13 +208,17 @@ def config4(args):
             src.scaling = np.asarray(sc, dtype=np.float64)  # bandwidths given: no fit needed to save
             src.save("src.xml", adjust_N=False)
         dist.barrier()
+        from kdsource_b200.resample import open_source
+
+        _, t_open = timed(lambda: open_source("src.xml"))
+        rec["open_source_s"] = t_open
         _, t_e2e = timed(lambda: kds.resample_to_mcpl("src.xml", "out.mcpl.gz", nout, rng=1,
                                                       force=True))
         if rank == 0:
             rec.update(e2e_particles=nout, e2e_s=t_e2e, e2e_particles_per_s=nout / t_e2e,
                        e2e_file_bytes=os.path.getsize("out.mcpl.gz"),
-                       e2e_what="resample_to_mcpl: XML + 1e7-particle MCPL read, upload, "
-                                "generation, D2H, gzip level 1, file on " + (base or "tmp"))
+                       e2e_what="resample_to_mcpl: XML + 1e7-particle MCPL read and device decode, "
+                                "generation, device gzip, D2H, file on " + (base or "tmp"))
             with mcpl.MCPLFile("out.mcpl.gz", blocklength=100000) as f:
                 pb = f.read_block()
                 rec["e2e_file_nparticles"] = int(f.nparticles)
