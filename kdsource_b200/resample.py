@@ -72,7 +72,7 @@ def _gzip_member(data, level):
 
 
 def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=False,
-                     batch=1 << 24, compresslevel=None, precision="float32", threads=None):
+                     batch=1 << 22, compresslevel=None, precision="float32", threads=None):
     """Resample `nout` particles from an XML source file into a new MCPL file
     (always ``*.mcpl.gz``; refuses to overwrite unless `force`).
 
@@ -111,7 +111,13 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
             raise RuntimeError("multi-rank resampling needs an explicit integer seed")
     if world > 1 and not isinstance(rng, int):
         raise RuntimeError("multi-rank resampling needs an explicit integer seed")
+    import time
+
+    timing = os.environ.get("KDSB200_TIMING")
+    t_start = time.perf_counter()
     sampler, _ = open_source(ksrc.absolute(), precision=precision)
+    if timing:
+        print("[timing] open_source {:.3f} s".format(time.perf_counter() - t_start))
     lo, hi = _dist.shard_range(nout, rank, world)
     part_name = str(dst) + ".part{}".format(rank) if world > 1 else None
     header = mcpl.build_header(nout, "KDSource resample", singleprec=True) if rank == 0 else None
@@ -140,6 +146,8 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
         _write_gpu_gzip(part_name or str(dst), header, batches(), batch)
     else:
         _write_host_gzip(part_name or str(dst), header, batches(), compresslevel, threads)
+    if timing:
+        print("[timing] total {:.3f} s".format(time.perf_counter() - t_start))
     if world > 1:
         _dist.barrier()
         if rank == 0:
@@ -158,12 +166,18 @@ def _write_gpu_gzip(path, header, batches, batch):
     """Device-compressed output through the native streaming writer."""
     import ctypes
 
+    import time
+
     L = _lib.load()
+    timing = os.environ.get("KDSB200_TIMING")
+    t0 = time.perf_counter()
     # MCPL-3 records: 36 bytes, the last 12 (time, weight, pdgcode) usually repeat
     w = L.kdsb200_gz_writer_open(os.fsencode(path), batch * 36, 36, 12, _lib.stream())
     if not w:
         _lib.check(1)
     w = ctypes.c_void_p(w)
+    if timing:
+        print("[timing] gz_writer_open {:.3f} s".format(time.perf_counter() - t0))
     try:
         if header is not None:
             _lib.check(L.kdsb200_gz_writer_put_host(w, header, len(header)))
@@ -172,8 +186,12 @@ def _write_gpu_gzip(path, header, batches, batch):
     except BaseException:
         L.kdsb200_gz_writer_close(w, None)
         raise
+    if timing:
+        print("[timing] batches submitted {:.3f} s".format(time.perf_counter() - t0))
     nbytes = ctypes.c_uint64(0)
     _lib.check(L.kdsb200_gz_writer_close(w, ctypes.byref(nbytes)))
+    if timing:
+        print("[timing] writer closed {:.3f} s".format(time.perf_counter() - t0))
     return int(nbytes.value)
 
 

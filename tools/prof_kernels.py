@@ -51,7 +51,7 @@ if which in ("all", "gzip"):
     rec = smp.sample_device(n, seed=1)["records"]
     nb, member = n * 36, int(L.kdsb200_gz_member_bytes())
     hist = _lib.empty(258, t.int64)
-    _lib.check(L.kdsb200_gz_histogram(_lib.ptr(rec), 64 << 20, member, 36, 12, _lib.ptr(hist),
+    _lib.check(L.kdsb200_gz_histogram(_lib.ptr(rec), (64 << 20) // 36 * 36, member, 36, 12, _lib.ptr(hist),
                                       _lib.stream()))
     hh = hist.cpu().numpy().astype(np.uint64)
     table = _lib.GzTable()
