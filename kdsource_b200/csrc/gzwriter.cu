@@ -240,16 +240,29 @@ int kdsb200_gz_writer_put_device(kdsb200_gz_writer* w, const void* d_data, uint6
       return 1;
     }
   }
-  if (kdsb200_gz_compress(d_data, nbytes, w->member, &w->table, w->d_scratch, w->d_out[slot],
-                          w->cap, w->d_total, w->st))
-    return 1;
-  KDSB_CUDA(cudaMemcpyAsync(w->h_small, w->d_total, 8, cudaMemcpyDeviceToHost, w->st));
-  KDSB_CUDA(cudaStreamSynchronize(w->st));
-  const uint64_t total = w->h_small[0];
-  if (total > w->cap) {
-    set_error("gz_writer_put_device: compressed batch (%llu bytes) exceeds the buffer (%llu)",
-              (unsigned long long)total, (unsigned long long)w->cap);
-    return 1;
+  uint64_t total = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if (kdsb200_gz_compress(d_data, nbytes, w->member, &w->table, w->d_scratch, w->d_out[slot],
+                            w->cap, w->d_total, w->st))
+      return 1;
+    KDSB_CUDA(cudaMemcpyAsync(w->h_small, w->d_total, 8, cudaMemcpyDeviceToHost, w->st));
+    KDSB_CUDA(cudaStreamSynchronize(w->st));
+    total = w->h_small[0];
+    if (total <= w->cap) break;
+    if (attempt == 1) {
+      set_error("gz_writer_put_device: compressed batch (%llu bytes) exceeds the buffer (%llu)",
+                (unsigned long long)total, (unsigned long long)w->cap);
+      return 1;
+    }
+    // this batch does not look like the data the table was built from: rebuild the table
+    // from the batch itself (an order-0 code with every symbol present cannot expand its
+    // own data by more than the block headers) and encode again
+    if (kdsb200_gz_histogram(d_data, nbytes, w->member, w->rec_bytes, w->tail_bytes, w->d_hist,
+                             w->st))
+      return 1;
+    KDSB_CUDA(cudaMemcpyAsync(w->h_small + 1, w->d_hist, 258 * 8, cudaMemcpyDeviceToHost, w->st));
+    KDSB_CUDA(cudaStreamSynchronize(w->st));
+    if (kdsb200_gz_build_table(w->h_small + 1, w->rec_bytes, w->tail_bytes, &w->table)) return 1;
   }
   KDSB_CUDA(cudaMemcpyAsync(w->h_out[slot], w->d_out[slot], total, cudaMemcpyDeviceToHost, w->st));
   KDSB_CUDA(cudaEventRecord(w->ev[slot], w->st));

@@ -577,6 +577,45 @@ def test_device_gzip_roundtrip():
     assert gzip.decompress(gz) == data and len(gz) < 0.25 * len(data)
 
 
+def test_gz_writer_streams_and_recovers_from_a_stale_table(tmp_path):
+    """The native writer: host member + device batches, in order; a batch that the
+    file's Huffman table (built from the first batch) would expand beyond the staging
+    buffer makes the writer rebuild the table from that batch and encode it again."""
+    import ctypes
+    import gzip
+
+    from kdsource_b200 import _lib
+
+    L = _lib.load()
+    t = _lib.torch()
+    rng = np.random.default_rng(3)
+    n = 36 * 2048 * 6 + 36 * 100
+    zeros = np.zeros(n, dtype=np.uint8)
+    noise = rng.integers(0, 256, n, dtype=np.uint8)   # ~15 bits/byte under the zeros' table
+    mixed = rng.integers(0, 4, n, dtype=np.uint8)
+    path = str(tmp_path / "w.gz")
+    w = L.kdsb200_gz_writer_open(os.fsencode(path), n, 0, 0, _lib.stream())
+    assert w
+    w = ctypes.c_void_p(w)
+    head = b"host header bytes" * 10
+    _lib.check(L.kdsb200_gz_writer_put_host(w, head, len(head)))
+    for arr in (zeros, noise, mixed, noise[:36 * 7]):
+        d = t.from_numpy(arr).cuda()
+        _lib.check(L.kdsb200_gz_writer_put_device(w, _lib.ptr(d), len(arr)))
+    nbytes = ctypes.c_uint64(0)
+    _lib.check(L.kdsb200_gz_writer_close(w, ctypes.byref(nbytes)))
+    assert nbytes.value == os.path.getsize(path)
+    want = head + zeros.tobytes() + noise.tobytes() + mixed.tobytes() + noise[:36 * 7].tobytes()
+    assert gzip.open(path).read() == want
+    # a batch larger than the writer was opened for is refused, not truncated
+    w = ctypes.c_void_p(L.kdsb200_gz_writer_open(os.fsencode(path), 36 * 1000, 36, 12,
+                                                 _lib.stream()))
+    d = t.from_numpy(noise[:36 * 2000].copy()).cuda()
+    assert L.kdsb200_gz_writer_put_device(w, _lib.ptr(d), 36 * 2000) != 0
+    assert b"limit" in L.kdsb200_last_error()
+    L.kdsb200_gz_writer_close(w, None)
+
+
 def test_resample_to_mcpl_gpu_gzip_equals_host_gzip(oracle, tmp_path, monkeypatch):
     """resample_to_mcpl through the device compressor + native writer gives the same
     MCPL stream as the host-zlib path, and libz's gzread-style reader accepts it."""
