@@ -555,6 +555,11 @@ def test_device_gzip_roundtrip():
     # small member size (more members, other chunk length)
     data = cases["many_members_ragged"][:1024 * 50 + 40]
     assert gzip.decompress(_gz_compress(L, t, data, member=1024)) == data
+    # more members than one tile of the offset scan (256): 1500 and 301 members
+    data = rng.integers(0, 16, 1024 * 1500 - 24, dtype=np.uint8).tobytes()
+    assert gzip.decompress(_gz_compress(L, t, data, member=1024)) == data
+    data = np.minimum(rng.geometric(0.3, mb * 300 + 72), 255).astype(np.uint8).tobytes()
+    assert gzip.decompress(_gz_compress(L, t, data)) == data
     # record mode (MCPL-3 layout): constant tails become matches; tails that change,
     # member boundaries (no history) and partial members still round-trip
     nrec = 2048 * 5 + 777
