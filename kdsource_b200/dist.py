@@ -53,6 +53,31 @@ def allreduce_sum_numpy(a):
     return t.cpu().numpy()
 
 
+def allgather_rows(a):
+    """Concatenate the ranks' arrays along axis 0 (shares may differ in length);
+    the result is on every rank."""
+    td = _td()
+    if td is None or td.get_world_size() == 1:
+        return a
+    import torch
+
+    a = np.ascontiguousarray(a)
+    world = td.get_world_size()
+    cuda = td.get_backend() == "nccl"
+    n = torch.tensor([a.shape[0]], dtype=torch.int64)
+    n = n.cuda() if cuda else n
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    td.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    pad = np.zeros((max(sizes),) + a.shape[1:], dtype=a.dtype)
+    pad[:a.shape[0]] = a
+    t = torch.from_numpy(pad)
+    t = t.cuda() if cuda else t
+    parts = [torch.empty_like(t) for _ in range(world)]
+    td.all_gather(parts, t)
+    return np.concatenate([p.cpu().numpy()[:k] for p, k in zip(parts, sizes)], axis=0)
+
+
 def barrier():
     td = _td()
     if td is not None:

@@ -69,6 +69,25 @@ class Metric:
         centre = np.average(vecs, axis=0, weights=weights)
         return np.sqrt(np.average((vecs - centre) ** 2, axis=0, weights=weights))
 
+    # -- the same statistics when every rank holds a share of the list:
+    # `allsum` adds a numpy array over the ranks.  Two phases, like the formulas
+    # above: weighted mean first, then the weighted mean squared deviation from it.
+    @staticmethod
+    def _wavg_sharded(vals, weights, allsum):
+        if weights is None:
+            num, den = vals.sum(axis=0), np.array([float(len(vals))])
+        else:
+            num, den = (vals * weights[:, None]).sum(axis=0), np.array([weights.sum()])
+        tot = allsum(np.concatenate((num, den)))
+        return tot[:-1] / tot[-1]
+
+    def mean_sharded(self, vecs, weights, allsum):
+        return self._wavg_sharded(vecs, weights, allsum)
+
+    def std_sharded(self, vecs, weights, allsum):
+        centre = self.mean_sharded(vecs, weights, allsum)
+        return np.sqrt(self._wavg_sharded((vecs - centre) ** 2, weights, allsum))
+
     # -- serialisation --------------------------------------------------------
     def params(self):
         return [getattr(self, n) for n in self._param_names]
@@ -167,6 +186,15 @@ class Geometry(Metric):
 
     def std(self, parts=None, vecs=None, weights=None):
         return self._per_metric("std", parts, vecs, weights)
+
+    def std_sharded(self, vecs, weights, allsum):
+        """:meth:`std` of the union of the ranks' samples (`vecs`, `weights` are this
+        rank's share; `allsum` sums an array over the ranks)."""
+        out, col = [], 0
+        for m in self.ms:
+            out.append(m.std_sharded(vecs[:, col:col + m.dim], weights, allsum))
+            col += m.dim
+        return np.concatenate(out)
 
     def save(self, gtree):
         gtree.set("order", str(len(self.ms)))
@@ -495,6 +523,16 @@ class Isotrop(Metric):
             vecs = self.transform(dirs)
         mn = self.mean(vecs=vecs, weights=weights)
         pooled = np.sqrt(np.mean(np.average((vecs - mn) ** 2, axis=0, weights=weights)))
+        return np.array(3 * [pooled])
+
+    def mean_sharded(self, vecs, weights, allsum):
+        mn = self._wavg_sharded(vecs, weights, allsum)
+        norm = np.linalg.norm(mn)
+        return mn / (norm if norm != 0 else 1)
+
+    def std_sharded(self, vecs, weights, allsum):
+        mn = self.mean_sharded(vecs, weights, allsum)
+        pooled = np.sqrt(np.mean(self._wavg_sharded((vecs - mn) ** 2, weights, allsum)))
         return np.array(3 * [pooled])
 
 

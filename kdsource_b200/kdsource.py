@@ -82,20 +82,48 @@ class KDSource:
         self.R = R[self.kernel[0]]
         self.fitted = False
 
-    def fit(self, N=-1, skip=0, scaling=None, importance=None, bw_method=None, **kwargs):
+    def fit(self, N=-1, skip=0, scaling=None, importance=None, bw_method=None, sharded=False,
+            **kwargs):
         """Load up to N particles (after `skip`) and fit the KDE model
         (reference kdsource.py:132-213): scaling = weighted std of each KDE
         variable / importance (or the given scaling; zeros -> 1), then the
-        bandwidth method, if any, on the scaled variables."""
-        parts, ws = self.plist.get(N, skip)
-        N = len(parts)
+        bandwidth method, if any, on the scaled variables.
+
+        sharded=True (with torch.distributed initialised): every rank reads and
+        transforms only its contiguous share of the N particles; N_eff and the scaling
+        come from all-reduced weighted moments, and the transformed samples are
+        all-gathered so that every rank ends with the same fitted model as an
+        unsharded fit."""
+        from . import dist as _dist
+
+        rank, world = _dist.rank_world()
+        sharded = bool(sharded) and world > 1
+        if sharded:
+            from . import mcpl as _mcpl
+
+            with _mcpl.MCPLFile(self.plist.filename) as f:
+                avail = max(0, f.nparticles - skip)
+            n_req = avail if N < 0 else min(N, avail)
+            lo, hi = _dist.shard_range(n_req, rank, world)
+            parts, ws = self.plist.get(hi - lo, skip + lo)
+            N = int(round(_dist.allreduce_sum_numpy(np.array([float(len(parts))]))[0]))
+        else:
+            parts, ws = self.plist.get(N, skip)
+            N = len(parts)
         if N == 0:
             raise Exception("No particles for fitting.")
         print("Using {} particles for fit.".format(N))
         vecs = self.geom.transform(parts)
-        self.N_eff = np.sum(ws) ** 2 / np.sum(ws ** 2)
+        if sharded:
+            sw, sw2 = _dist.allreduce_sum_numpy(np.array([np.sum(ws), np.sum(ws ** 2)]))
+            self.N_eff = sw ** 2 / sw2
+        else:
+            self.N_eff = np.sum(ws) ** 2 / np.sum(ws ** 2)
         if scaling is None:
-            scaling = self.geom.std(vecs=vecs, weights=ws)
+            if sharded:
+                scaling = self.geom.std_sharded(vecs, ws, _dist.allreduce_sum_numpy)
+            else:
+                scaling = self.geom.std(vecs=vecs, weights=ws)
             if importance is None:
                 importance = [1] * self.geom.dim
             elif len(importance) != self.geom.dim:
@@ -105,6 +133,9 @@ class KDSource:
             scaling = np.array(scaling)
         scaling[scaling == 0] = STD_DEFAULT
         self.scaling = scaling
+        if sharded:  # from here on every rank holds the whole (transformed) sample
+            vecs = _dist.allgather_rows(vecs)
+            ws = _dist.allgather_rows(ws)
         if bw_method is not None:
             if bw_method not in bw_methods:
                 raise Exception("Invalid bw_method. Available: {}".format(list(bw_methods)))
