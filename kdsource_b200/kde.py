@@ -52,6 +52,12 @@ def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_
     N, D = data.shape
     batch_off = np.ascontiguousarray(batch_off, dtype=np.int64)
     nb = len(batch_off) - 1
+    if nb < 1 or N == 0:
+        raise ValueError("knn_batched needs at least one non-empty batch")
+    smallest = int(np.min(np.diff(batch_off)))
+    if kk > smallest:  # scikit-learn's check in kneighbors (kde.py:96)
+        raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = {}, "
+                         "n_samples_fit = {}".format(kk, smallest))
     rank, world = _dist.rank_world()
     b_lo, b_hi = _dist.shard_range(nb, rank, world)
     r_lo, r_hi = int(batch_off[b_lo]), int(batch_off[b_hi])

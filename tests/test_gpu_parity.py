@@ -767,3 +767,76 @@ def test_plist_get_device_equals_host_decoder(oracle, tmp_path):
         hp, hw = PList(fn, set_params=False).get(100, skip=4000)
         dp, dw = PList(fn, set_params=False).get_device(100, skip=4000)
         assert np.array_equal(dp.cpu().numpy(), hp) and np.array_equal(dw.cpu().numpy(), hw)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases_small_ragged_and_degenerate(oracle):
+    """Tile boundaries, single samples, empty inputs and the errors the reference
+    raises (scikit-learn's n_neighbors check, MLCV maximum at a grid edge)."""
+    from kdsource_b200 import kde
+    from kdsource_b200.sampler import DeviceSampler, make_geom_struct
+    from kdsource_b200 import geom as kgeom
+    from kdsource_b200.treekde import TreeKDE
+
+    rng = np.random.default_rng(17)
+    # evaluate: source counts around the 512-source tile, query counts around the CTA tile
+    for N in (1, 2, 511, 512, 513, 1025):
+        data = rng.normal(size=(N, 3))
+        w = rng.uniform(0.5, 1.5, N)
+        for M in (1, 1023, 1024, 1025):
+            q = rng.normal(size=(M, 3))
+            got = TreeKDE(bw=0.7).fit(data, w).evaluate(q)
+            ref = oracle.kde_sum_c(data, w, 0.7, q)
+            assert np.allclose(got, ref, rtol=1e-5, atol=1e-300), (N, M)
+    # a source of weight zero contributes nothing; all-but-one zero weights
+    data = rng.normal(size=(300, 2))
+    w = np.zeros(300)
+    w[7] = 2.0
+    got = TreeKDE(bw=0.5).fit(data, w).evaluate(data[:5])
+    assert np.allclose(got, oracle.kde_sum_c(data[7:8], None, 0.5, data[:5]), rtol=1e-5)
+    with pytest.raises(ValueError):
+        TreeKDE(bw=0.5).fit(data, np.zeros(300))
+    with pytest.raises(ValueError):
+        TreeKDE(bw=0.5).evaluate(data)          # not fitted
+    with pytest.raises(ValueError):
+        TreeKDE(bw=0.5).fit(data).evaluate(np.zeros((3, 5)))  # wrong dimension
+    # MLCV: as many folds as samples (leave-one-out), fewer samples than n_splits, G = 1
+    d = rng.normal(size=(23, 2))
+    wv = rng.uniform(0.5, 1.5, 23)
+    for K in (2, 10, 23, 50):
+        got = kde.mlcv_scores(d, wv, 0.6, np.array([0.8, 1.0, 1.3]), n_splits=K)
+        ref = oracle.mlcv_scores_c(d, wv, 0.6, np.array([0.8, 1.0, 1.3]), min(K, 23))
+        assert np.allclose(got, ref, rtol=1e-5), K
+    assert kde.mlcv_scores(d, None, 0.6, np.array([1.0]), 5)[0] == pytest.approx(
+        oracle.mlcv_scores_c(d, None, 0.6, np.array([1.0]), 5)[0], rel=1e-5)
+    # an isolated test point under a tiny bandwidth: log(0) = -inf, as in the reference
+    far = np.concatenate((rng.normal(size=(40, 2)), [[1e3, 1e3]]))
+    sc = kde.mlcv_scores(far, None, 0.05, np.array([1.0]), 41)
+    assert np.isneginf(sc[0])
+    with pytest.raises(Exception, match="Maximum not found"):
+        kde.bw_mlcv(d, wv, grid=np.array([1.0, 1.1]), show=False)
+    # kNN: k+1 equal to the batch size is fine, larger is scikit-learn's error
+    x = rng.normal(size=(40, 3))
+    off = kde.array_split_bounds(40, 4)
+    kth, dist, idx = kde.knn_batched(x, 10, off, want_dist=True, want_idx=True)
+    rd, ri = oracle.knn(x, 10, off)
+    assert np.array_equal(dist, rd) and np.array_equal(idx, ri) and np.array_equal(kth, rd[:, -1])
+    with pytest.raises(ValueError, match="n_neighbors <= n_samples_fit"):
+        kde.knn_batched(x, 11, off)
+    one = kde.knn_batched(x[:1], 1, np.array([0, 1]))[0]
+    assert one[0] == 0.0
+    # resampling from a single source particle, and a single output particle
+    parts, wp = oracle.synthetic_particles(1, seed=2, wseed=3)
+    g = kgeom.Geometry([kgeom.Energy(), kgeom.Vol(), kgeom.Isotrop()])
+    gs = make_geom_struct(g, np.array([0.1, 1, 1, 1, 0.2, 0.2, 0.2]), "g")
+    smp = DeviceSampler(parts, wp, 0.5, gs)
+    out = smp.sample(1, seed=4, want=("idx", "parts", "records"))
+    assert out["idx"][0] == 0 and out["records"].shape == (1, 36)
+    many = smp.sample(1000, seed=5, want=("idx", "parts"))
+    assert np.all(many["idx"] == 0)
+    assert np.allclose(np.linalg.norm(many["parts"][:, 4:7], axis=1), 1.0, atol=1e-5)
+    assert abs(np.mean(many["parts"][:, 1]) - parts[0, 1]) < 0.2 and np.std(many["parts"][:, 1]) > 0.3
+    with pytest.raises(ValueError):
+        DeviceSampler(parts, np.array([0.0]), 0.5, gs)
+    with pytest.raises(ValueError):
+        DeviceSampler(np.zeros((0, 8)), np.zeros(0), 0.5, gs)
