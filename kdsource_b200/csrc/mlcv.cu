@@ -318,13 +318,35 @@ int kdsb200_mlcv_poly_slots(int G) {
 uint64_t kdsb200_mlcv_mpad(uint64_t M) { return (M + CV_THREADS - 1) / CV_THREADS * CV_THREADS; }
 
 int kdsb200_mlcv_nsplit(uint64_t N, uint64_t M) {
+  // Source-dimension split that fills whole waves of 2 CTAs/SM best.  A CTA of the
+  // headline shape runs for hundreds of milliseconds, so a ragged last wave costs
+  // several percent (3907 row tiles = 13.2 waves -> 14); splitting the sources three
+  // ways gives 39.6 -> 40.  The split costs one extra pass over nsplit*M*G doubles.
   const uint64_t qt = kdsb200_mlcv_mpad(M) / CV_THREADS;
   const uint64_t ntl = n_tiles_for(N);
   if (!qt || !ntl) return 1;
-  const uint64_t target = (uint64_t)sm_count() * 2 * 3;
-  uint64_t ns = (target + qt - 1) / qt;
-  if (ns > ntl) ns = ntl;
-  return (int)(ns < 1 ? 1 : ns);
+  const uint64_t slots = (uint64_t)sm_count() * 2;
+  uint64_t lo = (3 * slots + qt - 1) / qt;  // at least ~3 waves when the problem allows
+  if (lo < 1) lo = 1;
+  if (lo > ntl) lo = ntl;
+  uint64_t hi = lo + 7;
+  if (hi > ntl) hi = ntl;
+  if (hi > 64) hi = lo > 64 ? lo : 64;
+  uint64_t best = lo;
+  double best_eff = -1.0;
+  for (uint64_t ns = lo; ns <= hi; ns++) {
+    const uint64_t tps = (ntl + ns - 1) / ns;
+    const uint64_t real = (ntl + tps - 1) / tps;  // splits actually launched
+    const uint64_t ctas = real * qt;
+    const uint64_t waves = (ctas + slots - 1) / slots;
+    // useful tile-visits over the capacity of the waves the grid occupies
+    const double eff = (double)(qt * ntl) / ((double)waves * slots * tps);
+    if (eff > best_eff + 0.004) {  // prefer fewer splits unless the gain is real
+      best_eff = eff;
+      best = ns;
+    }
+  }
+  return (int)best;
 }
 
 int kdsb200_mlcv_scores_f32(const float* d_packed, uint64_t N, int D, const float* d_qT,
