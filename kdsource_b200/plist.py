@@ -100,6 +100,10 @@ class PList:
         """Up to N particles after skipping `skip`: ``(parts (n,8), ws (n,))`` with
         columns [ekin,x,y,z,dx,dy,dz,t]; invalid particles (w<=0 or other pdg
         code) are dropped (reference plist.py:349-395)."""
+        if self._use_device_decoder(N, skip):
+            # large lists: records decoded on the GPU (bit-identical, see get_device)
+            parts, ws = self.get_device(N, skip)
+            return parts.cpu().numpy(), ws.cpu().numpy()
         with mcpl.MCPLFile(self.filename) as pl:
             if N < 0:
                 N = pl.nparticles
@@ -122,6 +126,22 @@ class PList:
         if self.x2z:
             parts = parts[:, [0, 2, 3, 1, 5, 6, 4, 7]]
         return parts, ws
+
+    DEVICE_DECODE_MIN = 1 << 20  # records; below this the host decoder is as fast
+
+    def _use_device_decoder(self, N, skip):
+        try:
+            with mcpl.MCPLFile(self.filename) as pl:
+                n = max(0, pl.nparticles - skip)
+                little = pl.hdr.endian == "<"
+            n = n if N < 0 else min(N, n)
+            if n < self.DEVICE_DECODE_MIN or not little:
+                return False
+            import torch
+
+            return torch.cuda.is_available()
+        except Exception:
+            return False
 
     def get_device(self, N=-1, skip=0):
         """:meth:`get` for device-side consumers (the sampler): the records are uploaded

@@ -767,6 +767,14 @@ def test_plist_get_device_equals_host_decoder(oracle, tmp_path):
         hp, hw = PList(fn, set_params=False).get(100, skip=4000)
         dp, dw = PList(fn, set_params=False).get_device(100, skip=4000)
         assert np.array_equal(dp.cpu().numpy(), hp) and np.array_equal(dw.cpu().numpy(), hw)
+    # get() switches to the device decoder for large lists: same arrays either way
+    pl = PList(str(tmp_path / "single.mcpl.gz"), set_params=False)
+    host = pl.get(-1)
+    pl.DEVICE_DECODE_MIN = 1000
+    assert pl._use_device_decoder(-1, 0)
+    dev = pl.get(-1)
+    assert isinstance(dev[0], np.ndarray)
+    assert np.array_equal(dev[0], host[0]) and np.array_equal(dev[1], host[1])
 
 
 # ------------------------------------------------------------------ edge cases
