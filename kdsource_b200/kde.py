@@ -44,7 +44,9 @@ def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_
 
     Returns (kth, dist, idx): ``kth`` (N,) distance to the kk-th neighbour,
     ``dist`` (N,kk) ascending, ``idx`` (N,kk) int32 indices inside the batch
-    ordered by (distance, index).  Batches are sharded over ranks.
+    ordered by (distance, index).  Batches are sharded over ranks.  In a batch
+    with fewer than kk rows the missing neighbours are (+inf, -1); ``bw_knn``
+    refuses that case like scikit-learn does.
     """
     L = _lib.load()
     t = _lib.torch()
@@ -54,10 +56,6 @@ def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_
     nb = len(batch_off) - 1
     if nb < 1 or N == 0:
         raise ValueError("knn_batched needs at least one non-empty batch")
-    smallest = int(np.min(np.diff(batch_off)))
-    if kk > smallest:  # scikit-learn's check in kneighbors (kde.py:96)
-        raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = {}, "
-                         "n_samples_fit = {}".format(kk, smallest))
     rank, world = _dist.rank_world()
     b_lo, b_hi = _dist.shard_range(nb, rank, world)
     r_lo, r_hi = int(batch_off[b_lo]), int(batch_off[b_hi])
@@ -119,6 +117,10 @@ def bw_knn(data, weights=None, K_eff=100, k=None, batch_size=10000, precision="f
     print("Correction factor: f_k = k_float / k = {}".format(f_k))
     print("Effective total neighbors: K_eff = {}".format(K_eff))
     off = array_split_bounds(N, batches)
+    smallest = int(np.min(np.diff(off)))
+    if k + 1 > smallest:  # scikit-learn's check in kneighbors (kde.py:96)
+        raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = {}, "
+                         "n_samples_fit = {}".format(k + 1, smallest))
     kth, _, _ = knn_batched(data, k + 1, off, precision=precision)
     return kth * (f_k) ** (1 / dim)
 

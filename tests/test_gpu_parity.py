@@ -830,7 +830,7 @@ def test_edge_cases_small_ragged_and_degenerate(oracle):
     rd, ri = oracle.knn(x, 10, off)
     assert np.array_equal(dist, rd) and np.array_equal(idx, ri) and np.array_equal(kth, rd[:, -1])
     with pytest.raises(ValueError, match="n_neighbors <= n_samples_fit"):
-        kde.knn_batched(x, 11, off)
+        kde.bw_knn(x, np.ones(40), k=10, batch_size=10)
     one = kde.knn_batched(x[:1], 1, np.array([0, 1]))[0]
     assert one[0] == 0.0
     # resampling from a single source particle, and a single output particle

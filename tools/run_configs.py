@@ -91,7 +91,7 @@ def config1(args):
                              weight=w, pdgcode=2112, srcname="synthetic")
         s = kds.KDSource(kds.PList(fn), g, bw="silv")
         _, t_fit = timed(lambda: s.fit())
-        s.evaluate(qparts[:256])  # warm-up (context, first launch)
+        s.evaluate(qparts)  # warm-up (context, source packing, buffers of this shape)
         (ev, er), t_eval = timed(lambda: s.evaluate(qparts))
         fparts, fw = s.plist.get()
     finally:
