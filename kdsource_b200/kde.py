@@ -184,6 +184,7 @@ class MLCVPlan:
         self.w_scale = 1.0 / wmax
         self.lc_ref = -D * np.log2(hmin)
         self.h2d_bytes = 0
+        self._acct = None
         if M == 0:
             return
         f_loc = fold_of[r_lo:r_hi]
@@ -228,11 +229,25 @@ class MLCVPlan:
             self.chunks.append((g0, gsub, gt, nk, sbuf, partial))
         #: kernel launches per launch() call
         self.n_launches = len(self.chunks) * (2 if self.nsplit > 1 else 1)
-        #: kernel evaluations (exponentials that enter a score) per launch() call
-        tr = float(N) - nf[f_loc]
-        self.n_evals = float(np.sum(tr)) * len(self.grid)
-        #: (row, source, g) slots the kernel executes: per CTA of 256 rows, all source
-        #: tiles except those inside the excluded interval shared by all its rows
+        self._acct = (nf, f_loc, fb)  # for the lazily computed work counters below
+
+    @property
+    def n_evals(self):
+        """Kernel evaluations (exponentials that enter a score) per launch() call."""
+        if self._acct is None:
+            return 0.0
+        nf, f_loc, _ = self._acct
+        return float(np.sum(float(self.N) - nf[f_loc])) * len(self.grid)
+
+    @property
+    def n_slots(self):
+        """(row, source, g) slots the kernel executes per launch(): per CTA of 256 rows,
+        all source tiles except those inside the excluded interval shared by all its
+        rows (benchmark accounting; not needed to run the search)."""
+        if self._acct is None:
+            return 0.0
+        _, f_loc, fb = self._acct
+        N, M, Mpad = self.N, self.M, self.Mpad
         TS = 512
         ntiles = (N + TS - 1) // TS
         lo_pad = np.full(Mpad, -1, dtype=np.int64)
@@ -243,7 +258,7 @@ class MLCVPlan:
         cta_hi = hi_pad.reshape(-1, 256).min(axis=1)
         skipped = np.clip(cta_hi // TS - (cta_lo + TS - 1) // TS, 0, None)
         skipped[cta_hi <= cta_lo] = 0
-        self.n_slots = float(np.sum(ntiles - skipped)) * TS * 256 * len(self.grid)
+        return float(np.sum(ntiles - skipped)) * TS * 256 * len(self.grid)
 
     def launch(self):
         if self.M == 0:
