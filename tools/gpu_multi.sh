@@ -1,7 +1,10 @@
 #!/bin/bash
+# N-GPU evidence run: sharded-path equivalence check, bench.py at N ranks, configuration 3 at full size
 cd "$(dirname "$0")/.."
 O=gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > $O/bench_2gpu.json 2> $O/bench_2gpu.err; echo "2gpu rc=$?"; tail -c 1200 $O/bench_2gpu.json; tail -5 $O/bench_2gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > $O/bench_2gpu_ref.json 2> $O/bench_2gpu_ref.err; echo "2gpu ref rc=$?"; cat $O/bench_2gpu_ref.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/multi_check.py > $O/multi_check.log 2>&1; echo "multi_check rc=$?"; tail -5 $O/multi_check.log
+N=${1:-8}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+nvidia-smi -L | wc -l; free -g | sed -n 2p; nproc
+timeout 600 $TR --master-port 29513 tools/multi_check.py > $O/multi_check_${N}.log 2>&1; echo "multi_check rc=$?"; tail -3 $O/multi_check_${N}.log
+timeout 900 $TR --master-port 29514 bench.py --gpus $N --steps 3 --warmup 3 > $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err; echo "bench rc=$?"; tail -3 $O/bench_${N}gpu.err; cat $O/bench_${N}gpu.json | cut -c1-900
+timeout 900 $TR --master-port 29515 tools/run_configs.py --configs 3 > $O/configs_${N}gpu.jsonl 2> $O/configs_${N}gpu.err; echo "configs rc=$?"; tail -3 $O/configs_${N}gpu.err; cat $O/configs_${N}gpu.jsonl
