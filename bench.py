@@ -271,7 +271,16 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
             kn()
         ms = float(np.median(time_events(t, kn, 3)))
         pk = float(np.sum(np.diff(off).astype(np.float64) ** 2))
-        res[prec] = {"pairs_per_s": pk / (ms * 1e-3), "ms": ms}
+        # distance arithmetic only (the top-k selection is amortised over the pairs):
+        # fp64 mode 3d-1 = 17 DADD/DMUL per pair (no contraction: bit-exact with numpy),
+        # fp32 mode 2d = 12 packed lane-ops per pair
+        ops, peak, unit = ((17.0, peaks["dfma"], "fp64 lane-op/s") if use64
+                           else (12.0, peaks["ffma2"], "fp32 lane-op/s"))
+        res[prec] = {"pairs_per_s": pk / (ms * 1e-3), "ms": ms,
+                     "roofline": {"bound": "fp64" if use64 else "fp32",
+                                  "achieved": pk * ops / (ms * 1e-3) / 1e9, "peak": peak / 1e9,
+                                  "unit": "G" + unit, "frac": pk * ops / (ms * 1e-3) / peak,
+                                  "traffic": None}}
     # fp64 pipe: d subtractions + d multiplies + (d-1) additions per pair, no FMA
     # contraction (bit-exact with numpy/sklearn): 3d-1 DP ops per pair
     sub["knn"] = {"workload": "N={:g}, k=10, batch_size=1e4, d=6".format(Nk), **res,
@@ -453,7 +462,8 @@ def run_ours(args):
     cal = calibrate()
     hbm, hbm_src = measured_peaks()
     peaks = {"mufu": cal["mufu_ex2_lane_ops_per_s"], "ffma2": cal["ffma2_lane_ops_per_s"],
-             "ffma": cal["ffma_lane_ops_per_s"], "hbm_gbs": hbm}
+             "ffma": cal["ffma_lane_ops_per_s"], "dfma": cal["dfma_lane_ops_per_s"],
+             "hbm_gbs": hbm}
 
     plan = kde.MLCVPlan(data, w, bw, grid, n_splits=K_MLCV)
     flush = t.empty(256 << 20, dtype=t.uint8, device="cuda")

@@ -82,6 +82,18 @@ __global__ void __launch_bounds__(256) calib_kernel(float* out, int iters, float
     float x, y;
     f2_unpack(f2_add(f2_add(p0, p1), f2_add(p2, p3)), x, y);
     a0 = x + y + s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
+  } else if (MODE == 4) {  // fp64 pipe: DFMA
+    double d0 = a0, d1 = a1, d2 = a2, d3 = a3, d4 = a4, d5 = a5, d6 = a6, d7 = a7;
+    const double dm = 0.999, dc = 1e-3;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        d0 = fma(d0, dm, dc); d1 = fma(d1, dm, dc); d2 = fma(d2, dm, dc); d3 = fma(d3, dm, dc);
+        d4 = fma(d4, dm, dc); d5 = fma(d5, dm, dc); d6 = fma(d6, dm, dc); d7 = fma(d7, dm, dc);
+      }
+    }
+    a0 = (float)(d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7);
+    a1 = a2 = a3 = a4 = a5 = a6 = a7 = 0.f;
   } else {  // MUFU.EX2
     a0 = -1e-3f * a0; a1 = -1e-3f * a1; a2 = -1e-3f * a2; a3 = -1e-3f * a3;
     a4 = -1e-3f * a4; a5 = -1e-3f * a5; a6 = -1e-3f * a6; a7 = -1e-3f * a7;
@@ -115,7 +127,7 @@ int kdsb200_device_info(int* sm, int* cc_major, int* cc_minor, int* clock_khz) {
   return 0;
 }
 
-// mode 0: FFMA, 1: FFMA2, 2: MUFU.EX2.  Returns lane-operations per second
+// mode 0: FFMA, 1: FFMA2, 2: MUFU.EX2, 3: FFMA2+FFMA interleaved, 4: DFMA.  Returns lane-operations per second
 // (FFMA2 counts two per lane-instruction) measured with CUDA events.
 int kdsb200_calibrate_pipe(int mode, float* d_scratch /* >= sm*8*256 floats */, int iters,
                            double* ops_per_s, void* stream) {
@@ -129,6 +141,7 @@ int kdsb200_calibrate_pipe(int mode, float* d_scratch /* >= sm*8*256 floats */, 
     if (mode == 0) calib_kernel<0><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     else if (mode == 1) calib_kernel<1><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     else if (mode == 3) calib_kernel<3><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
+    else if (mode == 4) calib_kernel<4><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     else calib_kernel<2><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     KDSB_CUDA(cudaEventRecord(e1, st));
     KDSB_CUDA(cudaEventSynchronize(e1));

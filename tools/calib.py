@@ -1,4 +1,4 @@
-"""Print device info and calibrated pipe rates (FFMA, FFMA2, MUFU.EX2)."""
+"""Print device info and calibrated pipe rates (FFMA, FFMA2, MUFU.EX2, DFMA)."""
 import ctypes
 import json
 import os
@@ -16,7 +16,8 @@ def calibrate(iters=4096):
                                      ctypes.byref(clk)))
     scratch = _lib.empty(sm.value * 8 * 256, t.float32)
     out = {"sm": sm.value, "cc": "{}.{}".format(ma.value, mi.value), "clock_khz": clk.value}
-    for mode, name in ((0, "ffma"), (1, "ffma2"), (2, "mufu_ex2"), (3, "ffma2_plus_ffma")):
+    for mode, name in ((0, "ffma"), (1, "ffma2"), (2, "mufu_ex2"), (3, "ffma2_plus_ffma"),
+                       (4, "dfma")):
         r = ctypes.c_double()
         _lib.check(L.kdsb200_calibrate_pipe(mode, _lib.ptr(scratch), iters, ctypes.byref(r),
                                             _lib.stream()))
