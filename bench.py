@@ -143,6 +143,29 @@ def cpu_mlcv_baseline(data, w, bw, grid, nthreads=0):
     return evals / dt, dt, n
 
 
+def cpu_mlcv_tree_baseline(data, w, bw, grid):
+    """The reference's algorithm as it runs on a CPU -- one process per grid point
+    (joblib), K tree builds + truncated ball-query sums each (oracle.mlcv_scores_tree,
+    SURVEY appendix D) -- on a bounded sample, in dense-equivalent evaluations/s.  At
+    sample sizes that finish in seconds it is slower than the dense OpenMP port used for
+    `cpu_baseline`; its cost grows like N log N instead of N^2, so it would overtake the
+    port somewhere above 1e5 particles."""
+    from oracle import kds_oracle as O
+
+    n = min(12_000, len(data))
+    cores = os.cpu_count() or 1
+    g = grid[::max(1, len(grid) // min(cores, len(grid)))][:cores]
+    fb = O.kfold_bounds(n, K_MLCV)
+    nf = np.diff(fb)
+    evals = float(np.sum(nf * (n - nf))) * len(g)
+    t0 = time.perf_counter()
+    O.mlcv_scores_tree(data[:n], w[:n], bw, g, K_MLCV, n_jobs=-1)
+    dt = time.perf_counter() - t0
+    return {"value": evals / dt, "unit": UNIT + " (dense-equivalent)", "cores": cores,
+            "kind": "port", "sample": "cKDTree ball query + numpy per fold, joblib over {} grid "
+            "points, first {} particles ({:.1f} s)".format(len(g), n, dt)}
+
+
 def run_reference(args):
     """`--impl reference`: the CPU implementation of the path on the host cores.
     The reference's MLCV is Python + KDEpy + joblib, none of which can run on the
@@ -551,6 +574,11 @@ def run_ours(args):
         v, dt, n = cpu_mlcv_baseline(data, w, bw, grid)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "first {} particles, G={}, K={} ({:.1f} s)".format(n, G_MLCV, K_MLCV, dt)}
+        if not args.no_sub:
+            try:
+                cpu["tree_variant"] = cpu_mlcv_tree_baseline(data, w, bw, grid)
+            except Exception as e:  # joblib workers unavailable: keep the dense baseline
+                cpu["tree_variant"] = {"unavailable": str(e)[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,

@@ -236,6 +236,66 @@ def cv_score(bw, data, weights=None, n_splits=10):
     return np.mean(scores)
 
 
+def kde_sum_tree(data, weights, bw, points, eps=1e-3):
+    """KDEpy ``TreeKDE.evaluate`` as the reference runs it, restated from SURVEY appendix D
+    (KDEpy>=1.1.12 is not in the tree): scipy ``cKDTree`` over the samples, one support
+    radius from the largest bandwidth (:func:`treekde_radius`), approximate ball query
+    ``query_ball_point(q, r, p=2, eps=eps*sqrt(N))`` per query point, Gaussian terms
+    summed over the returned neighbours only.  This is the *algorithm* whose CPU time
+    the reference arm of bench.py reports; its values differ from the exact sum by the
+    truncation (SURVEY: 2.4 % median)."""
+    from scipy.spatial import cKDTree
+
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    N, d = data.shape
+    wn = normalise_weights(weights, N)
+    h = np.broadcast_to(np.asarray(bw, dtype=np.float64), (N,))
+    coef = wn * (2 * np.pi) ** (-d / 2) * h ** (-d)
+    ih2 = 0.5 / h ** 2
+    tree = cKDTree(data)
+    r = treekde_radius(float(np.max(h)), atol=eps)
+    out = np.zeros(len(pts))
+    for m, idx in enumerate(tree.query_ball_point(pts, r, p=2, eps=eps * np.sqrt(N))):
+        if idx:
+            idx = np.asarray(idx)
+            diff = data[idx] - pts[m]
+            out[m] = np.sum(coef[idx] * np.exp(-np.einsum("ij,ij->i", diff, diff) * ih2[idx]))
+    return out
+
+
+def cv_score_tree(bw, data, weights=None, n_splits=10):
+    """:func:`cv_score` with the TreeKDE-like truncated sum (one fold = one tree build +
+    one evaluate of the test points, exactly the work of kde.py:134-151)."""
+    data = np.asarray(data, dtype=np.float64)
+    N = len(data)
+    fb = kfold_bounds(N, n_splits)
+    scores = []
+    for f in range(n_splits):
+        t0, t1 = fb[f], fb[f + 1]
+        train = np.r_[0:t0, t1:N]
+        bw_tr = np.asarray(bw)[train] if np.ndim(bw) == 1 else bw
+        w_tr = None if weights is None else np.asarray(weights)[train]
+        dens = kde_sum_tree(data[train], w_tr, bw_tr, data[t0:t1])
+        with np.errstate(divide="ignore"):
+            if weights is not None:
+                scores.append(np.mean(np.asarray(weights)[t0:t1] * np.log(dens)))
+            else:
+                scores.append(np.mean(np.log(dens)))
+    return np.mean(scores)
+
+
+def mlcv_scores_tree(data, weights, seed, grid, n_splits=10, n_jobs=-1):
+    """The reference's grid search as it runs on a CPU (kde.py:204-211): one process per
+    grid point (joblib, ``n_jobs=-1``), each scoring ``grid[g] * seed`` with the
+    TreeKDE-like estimator."""
+    from joblib import Parallel, delayed
+
+    seed = np.asarray(seed, dtype=np.float64)
+    return np.array(Parallel(n_jobs=n_jobs)(
+        delayed(cv_score_tree)(g * seed, data, weights, n_splits) for g in grid))
+
+
 def mlcv_scores_c(data, weights, seed, grid, n_splits=10, nthreads=0):
     """CV scores for every grid factor (kde.py:204-211) via kds_oracle.c."""
     data = np.ascontiguousarray(data, dtype=np.float64)

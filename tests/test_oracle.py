@@ -153,6 +153,27 @@ def test_kde_sum_vs_independent_libraries(oracle):
     assert np.allclose(ours, g(pts.T), rtol=1e-10)
 
 
+def test_tree_variant_brackets_the_hard_cutoff_sums(oracle):
+    """The TreeKDE-like restatement used as the CPU timing baseline (cKDTree approximate
+    ball query): its sums lie between the hard-cutoff sums at r/(1+eps') and r(1+eps'),
+    eps' = 1e-3 sqrt(N), and its CV score is the score of those sums."""
+    rng = np.random.default_rng(8)
+    data = rng.normal(size=(4000, 3))
+    w = rng.uniform(0.5, 1.5, 4000)
+    q = rng.normal(size=(300, 3))
+    h = 0.3
+    r = oracle.treekde_radius(h)
+    e = 1e-3 * np.sqrt(len(data))
+    tree = oracle.kde_sum_tree(data, w, h, q)
+    lo = oracle.kde_sum_c(data, w, h, q, cutoff=r / (1 + e))
+    hi = oracle.kde_sum_c(data, w, h, q, cutoff=r * (1 + e))
+    assert np.all(tree >= lo * (1 - 1e-12)) and np.all(tree <= hi * (1 + 1e-12))
+    assert np.all(tree <= oracle.kde_sum_c(data, w, h, q) * (1 + 1e-12))
+    sc = oracle.mlcv_scores_tree(data[:600], w[:600], 0.5, np.array([1.0, 1.5]), 5, n_jobs=1)
+    assert sc[1] == pytest.approx(oracle.cv_score_tree(0.75, data[:600], w[:600], 5), rel=1e-12)
+    assert abs(sc[1] - oracle.cv_score(0.75, data[:600], w[:600], 5)) < 0.05
+
+
 def test_treekde_radius_matches_survey_probe(oracle):
     # SURVEY appendix D probe: bw=0.295 -> r = 1.1214 = 3.80 bw
     assert oracle.treekde_radius(0.295) == pytest.approx(1.1214, abs=2e-3)
