@@ -146,7 +146,7 @@ class MLCVPlan:
     per-CTA partial sums and assembles the scores of the rows of this rank.
     """
 
-    def __init__(self, data, weights, seed, grid, n_splits=10, rows=None):
+    def __init__(self, data, weights, seed, grid, n_splits=10, rows=None, nsplit=None):
         L = _lib.load()
         t = _lib.torch()
         data = np.ascontiguousarray(data, dtype=np.float64)
@@ -217,7 +217,9 @@ class MLCVPlan:
         d_rows = d_data[r_lo:r_hi]  # contiguous row slice of the (N,D) tensor
         _lib.check(L.kdsb200_pack_queries_f32(_lib.ptr(d_rows), M, Mpad, D, cen_p,
                                               _lib.ptr(self.qT), _lib.stream()))
-        self.nsplit = L.kdsb200_mlcv_nsplit(N, M)
+        # source-dimension split (None: the library picks the one that fills whole waves)
+        self.nsplit = int(nsplit) if nsplit else L.kdsb200_mlcv_nsplit(N, M)
+        self.nsplit = max(1, min(self.nsplit, (N + 511) // 512))
         self.nblk = Mpad // 256
         self.chunks = []
         for g0 in range(0, len(self.grid), 32):

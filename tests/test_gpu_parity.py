@@ -161,6 +161,25 @@ def test_mlcv_vs_golden_reference(golden_kde):
     assert np.allclose(auto, g["auto"], rtol=1e-12)
 
 
+def test_mlcv_source_split_invariance(oracle, scaled):
+    """The fused single-pass kernel (nsplit=1) and every source split give the same
+    scores (fp64 partial sums; only the summation order of the splits differs)."""
+    from kdsource_b200 import kde
+
+    data, w = scaled["data"][:6000], scaled["w"][:6000]
+    grid = np.logspace(-0.2, 0.3, 9)
+    ref = oracle.mlcv_scores_c(data, w, 0.4, grid, 10)
+    got = {}
+    for ns in (1, 2, 3, 7, 12, 64):
+        plan = kde.MLCVPlan(data, w, 0.4, grid, n_splits=10, nsplit=ns)
+        plan.launch()
+        got[ns] = plan.collect()
+        assert np.allclose(got[ns], ref, rtol=1e-5), ns
+        assert np.allclose(got[ns], got[1], rtol=1e-12), ns
+    assert kde.MLCVPlan(data, w, 0.4, grid, nsplit=1).n_launches == 1
+    assert kde.MLCVPlan(data, w, 0.4, grid, nsplit=3).n_launches == 2
+
+
 @pytest.mark.parametrize("G", [1, 5, 10, 13, 32, 40])
 def test_mlcv_vs_oracle_grid_sizes(oracle, scaled, G):
     from kdsource_b200 import kde
