@@ -63,6 +63,21 @@ int kdsb200_kde_eval_kernel_f32(const float* d_packed, uint64_t N, int D, const 
                                 uint64_t M, uint64_t Mpad, int kernel, double cutoff,
                                 double out_scale, int nsplit, double* d_partial, double* d_out,
                                 void* stream);
+/* Split-coordinate fp32 mode (Gaussian kernel): every recentred coordinate is stored as
+ * hi + lo with hi a multiple of 1/grid (grid a power of two with max|x - c| * grid < 2^22),
+ * so the difference q - x is formed like in fp64 and the error no longer grows with
+ * |x - c| / h.  Sources: tiles of 512 x (2D+2) rows; queries d_qT [2D][Mpad]. */
+uint64_t kdsb200_packed_split_floats(uint64_t N, int D);
+int kdsb200_pack_sources_split_f32(const double* d_data, const double* d_w, const double* d_bw,
+                                   double bw_scalar, uint64_t N, int D, const double* h_center,
+                                   double w_scale, double lc_ref, double grid, float* d_packed,
+                                   void* stream);
+int kdsb200_pack_queries_split_f32(const double* d_pts, uint64_t M, uint64_t Mpad, int D,
+                                   const double* h_center, double grid, float* d_qT,
+                                   void* stream);
+int kdsb200_kde_eval_split_f32(const float* d_packed, uint64_t N, int D, const float* d_qT,
+                               uint64_t M, uint64_t Mpad, double out_scale, int nsplit,
+                               double* d_partial, double* d_out, void* stream);
 /* fp64 mode (1e-12 parity).  d_scratch: 2N + nsplit*M doubles. */
 int kdsb200_kde_eval_kernel_f64(const double* d_data, const double* d_w, const double* d_bw,
                                 double bw_scalar, uint64_t N, int D, double w_scale,

@@ -112,6 +112,14 @@ _SIGNATURES = {
     "kdsb200_kde_eval_kernel_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_u64, c_int,
                                             c_double, c_void_p, c_u64, c_int, c_double, c_int,
                                             c_void_p, c_void_p, c_void_p]),
+    "kdsb200_packed_split_floats": (c_u64, [c_u64, c_int]),
+    "kdsb200_pack_sources_split_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_u64, c_int,
+                                               c_double_p, c_double, c_double, c_double, c_void_p,
+                                               c_void_p]),
+    "kdsb200_pack_queries_split_f32": (c_int, [c_void_p, c_u64, c_u64, c_int, c_double_p, c_double,
+                                               c_void_p, c_void_p]),
+    "kdsb200_kde_eval_split_f32": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_u64, c_u64, c_double,
+                                           c_int, c_void_p, c_void_p, c_void_p]),
     "kdsb200_mlcv_gtile": (c_int, [c_int]),
     "kdsb200_mlcv_mpad": (c_u64, [c_u64]),
     "kdsb200_mlcv_nsplit": (c_int, [c_u64, c_u64]),

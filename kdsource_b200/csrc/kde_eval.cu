@@ -210,6 +210,148 @@ __global__ void __launch_bounds__(EV_THREADS, 2)
     out[(uint64_t)blockIdx.y * Mpad + mbase + qi * EV_THREADS] = accd[qi] * out_scale;
 }
 
+// ---------------------------------------------------------------------------
+// split-coordinate variant ("float32x2"): fp32 speed class, accuracy independent of h
+// ---------------------------------------------------------------------------
+// In the plain fp32 kernel a coordinate carries the rounding error 2^-24 |x - c|, which the
+// bandwidth magnifies by (|x - c| / h)(r / h).  Here every recentred
+// coordinate v is stored as v_hi + v_lo with v_hi on the grid 2^-S (exact in fp32, and so
+// is any difference q_hi - x_hi) and v_lo the remainder, so
+//     delta = (q_hi - x_hi) + (q_lo - x_lo)
+// is the fp64 difference rounded once.  (4D+1) packed lane-ops + 1 MUFU per pair instead of
+// (2D+1).  Tile rows: -x_hi[D], -x_lo[D], a2 = log2(e)/(2 h^2), nlc.
+__global__ void pack_sources_split_kernel(const double* __restrict__ data,
+                                          const double* __restrict__ w,
+                                          const double* __restrict__ bw, double bw_scalar,
+                                          uint64_t N, int D, Center cen, double w_scale,
+                                          double lc_ref, double grid, float* __restrict__ packed) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t ntl = n_tiles_for(N);
+  if (i >= ntl * TS) return;
+  const int rows = 2 * D + 2;
+  float* tile = packed + (i / TS) * (uint64_t)rows * TS + (i % TS);
+  if (i >= N) {
+    for (int k = 0; k <= 2 * D; k++) tile[(uint64_t)k * TS] = 0.f;
+    tile[(uint64_t)(2 * D + 1) * TS] = INFINITY;
+    return;
+  }
+  const double h = bw ? bw[i] : bw_scalar;
+  const double wi = (w ? w[i] : 1.0) * w_scale;
+  for (int k = 0; k < D; k++) {
+    const double v = data[i * D + k] - cen.c[k];
+    const double hi = rint(v * grid) / grid;
+    tile[(uint64_t)k * TS] = (float)(-hi);
+    tile[(uint64_t)(D + k) * TS] = (float)(-(v - hi));
+  }
+  tile[(uint64_t)(2 * D) * TS] = (float)(0.72134752044448170368 / (h * h));  // log2(e)/2
+  const double lc = log2(wi) - D * log2(h);
+  tile[(uint64_t)(2 * D + 1) * TS] = (float)(lc_ref - lc);
+}
+
+__global__ void pack_queries_split_kernel(const double* __restrict__ pts, uint64_t M, uint64_t Mpad,
+                                          int D, Center cen, double grid, float* __restrict__ qT) {
+  const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mpad) return;
+  for (int k = 0; k < D; k++) {
+    const double v = m < M ? pts[m * D + k] - cen.c[k] : 0.0;
+    const double hi = rint(v * grid) / grid;
+    qT[(uint64_t)k * Mpad + m] = (float)hi;
+    qT[(uint64_t)(D + k) * Mpad + m] = (float)(v - hi);
+  }
+}
+
+constexpr int EVS_STAGES = 2;
+
+template <int D>
+__global__ void __launch_bounds__(EV_THREADS, 2)
+    kde_eval_split_kernel(const float* __restrict__ packed, uint32_t n_tiles,
+                          uint32_t tiles_per_split, const float* __restrict__ qT, uint64_t Mpad,
+                          double out_scale, double* __restrict__ out) {
+  constexpr int ROWS = 2 * D + 2;
+  constexpr int TILE_FLOATS = ROWS * TS;
+  constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tiles = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(8) uint64_t full[EVS_STAGES];
+  const int tid = threadIdx.x;
+  const uint32_t t0 = blockIdx.y * tiles_per_split;
+  const uint32_t t1 = min(n_tiles, t0 + tiles_per_split);
+  const uint32_t nt = t1 > t0 ? t1 - t0 : 0;
+  if (tid == 0) {
+    for (int s = 0; s < EVS_STAGES; s++) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (uint32_t p = 0; p < (uint32_t)(EVS_STAGES - 1) && p < nt; p++) {
+      mbar_expect_tx(&full[p], TILE_BYTES);
+      tma_load_1d(tiles + p * TILE_FLOATS, packed + (uint64_t)(t0 + p) * TILE_FLOATS, TILE_BYTES,
+                  &full[p]);
+    }
+  }
+  const uint64_t mbase = (uint64_t)blockIdx.x * (EV_THREADS * EV_Q) + tid;
+  float qh[EV_Q][D], ql[EV_Q][D];
+#pragma unroll
+  for (int qi = 0; qi < EV_Q; qi++)
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      qh[qi][k] = qT[(uint64_t)k * Mpad + mbase + qi * EV_THREADS];
+      ql[qi][k] = qT[(uint64_t)(D + k) * Mpad + mbase + qi * EV_THREADS];
+    }
+  double accd[EV_Q];
+#pragma unroll
+  for (int qi = 0; qi < EV_Q; qi++) accd[qi] = 0.0;
+
+  for (uint32_t it = 0; it < nt; it++) {
+    const uint32_t s = it % EVS_STAGES;
+    const uint32_t parity = (it / EVS_STAGES) & 1u;
+    if (tid == 0 && it + EVS_STAGES - 1 < nt) {
+      const uint32_t ps = (it + EVS_STAGES - 1) % EVS_STAGES;
+      mbar_expect_tx(&full[ps], TILE_BYTES);
+      tma_load_1d(tiles + ps * TILE_FLOATS,
+                  packed + (uint64_t)(t0 + it + EVS_STAGES - 1) * TILE_FLOATS, TILE_BYTES,
+                  &full[ps]);
+    }
+    mbar_wait(&full[s], parity);
+    const float* tile = tiles + s * TILE_FLOATS;
+    f2_t acc[EV_Q];
+#pragma unroll
+    for (int qi = 0; qi < EV_Q; qi++) acc[qi] = 0ull;
+#pragma unroll 1
+    for (int j = 0; j < TS; j += 2) {
+      float2 r[ROWS];
+#pragma unroll
+      for (int k = 0; k < ROWS; k++) r[k] = *reinterpret_cast<const float2*>(tile + k * TS + j);
+      const f2_t a2 = f2_pack(r[2 * D].x, r[2 * D].y);
+      const f2_t nl = f2_pack(r[2 * D + 1].x, r[2 * D + 1].y);
+#pragma unroll
+      for (int qi = 0; qi < EV_Q; qi++) {
+        f2_t t = 0ull;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+          const f2_t dh = f2_add(f2_pack(qh[qi][k], qh[qi][k]), f2_pack(r[k].x, r[k].y));
+          const f2_t dl = f2_add(f2_pack(ql[qi][k], ql[qi][k]), f2_pack(r[D + k].x, r[D + k].y));
+          const f2_t dd = f2_add(dh, dl);
+          t = f2_fma(dd, dd, t);
+        }
+        float e0, e1;
+        f2_unpack(f2_fma(t, a2, nl), e0, e1);
+        acc[qi] = f2_add(acc[qi], f2_pack(ex2_approx(-e0), ex2_approx(-e1)));
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < EV_Q; qi++) {
+      float lo, hi;
+      f2_unpack(acc[qi], lo, hi);
+      accd[qi] += (double)lo + (double)hi;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int qi = 0; qi < EV_Q; qi++)
+    out[(uint64_t)blockIdx.y * Mpad + mbase + qi * EV_THREADS] = accd[qi] * out_scale;
+}
+
 __global__ void reduce_splits_kernel(const double* __restrict__ partial, int nsplit, uint64_t M,
                                      uint64_t Mpad, double* __restrict__ out) {
   const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,6 +460,20 @@ __global__ void coef_f64_kernel(const double* __restrict__ w, const double* __re
   }
 }
 
+template <int D>
+static int launch_eval_split(const float* packed, uint32_t n_tiles, uint32_t tps, int nsplit,
+                             const float* qT, uint64_t Mpad, double out_scale, double* out,
+                             cudaStream_t st) {
+  const size_t smem = (size_t)EVS_STAGES * (2 * D + 2) * TS * sizeof(float);
+  dim3 grid((unsigned)(Mpad / (EV_THREADS * EV_Q)), (unsigned)nsplit);
+  KDSB_CUDA(cudaFuncSetAttribute(kde_eval_split_kernel<D>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kde_eval_split_kernel<D><<<grid, EV_THREADS, smem, st>>>(packed, n_tiles, tps, qT, Mpad,
+                                                           out_scale, out);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace kdsb
 
 using namespace kdsb;
@@ -361,6 +517,97 @@ int kdsb200_pack_queries_f32(const double* d_pts, uint64_t M, uint64_t Mpad, int
   pack_queries_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       d_pts, M, Mpad, D, cen, d_qT);
   KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+uint64_t kdsb200_packed_split_floats(uint64_t N, int D) {
+  return n_tiles_for(N) * (uint64_t)(2 * D + 2) * TS;
+}
+
+int kdsb200_pack_sources_split_f32(const double* d_data, const double* d_w, const double* d_bw,
+                                   double bw_scalar, uint64_t N, int D, const double* h_center,
+                                   double w_scale, double lc_ref, double grid, float* d_packed,
+                                   void* stream) {
+  if (D < 1 || D > 8 || !(grid > 0)) {
+    set_error("pack_sources_split: D=%d out of range 1..8 or grid <= 0", D);
+    return 1;
+  }
+  Center cen;
+  for (int k = 0; k < 8; k++) cen.c[k] = k < D ? h_center[k] : 0.0;
+  const uint64_t tot = n_tiles_for(N) * TS;
+  if (tot == 0) return 0;
+  pack_sources_split_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_data, d_w, d_bw, bw_scalar, N, D, cen, w_scale, lc_ref, grid, d_packed);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kdsb200_pack_queries_split_f32(const double* d_pts, uint64_t M, uint64_t Mpad, int D,
+                                   const double* h_center, double grid, float* d_qT,
+                                   void* stream) {
+  if (D < 1 || D > 8 || !(grid > 0)) {
+    set_error("pack_queries_split: D=%d out of range 1..8 or grid <= 0", D);
+    return 1;
+  }
+  Center cen;
+  for (int k = 0; k < 8; k++) cen.c[k] = k < D ? h_center[k] : 0.0;
+  if (Mpad == 0) return 0;
+  pack_queries_split_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_pts, M, Mpad, D, cen, grid, d_qT);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kdsb200_kde_eval_split_f32(const float* d_packed, uint64_t N, int D, const float* d_qT,
+                               uint64_t M, uint64_t Mpad, double out_scale, int nsplit,
+                               double* d_partial, double* d_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) return 0;
+  if (Mpad % (EV_THREADS * EV_Q) != 0 || Mpad < M) {
+    set_error("kde_eval_split_f32: Mpad=%llu must be a multiple of %d and >= M",
+              (unsigned long long)Mpad, EV_THREADS * EV_Q);
+    return 1;
+  }
+  const uint32_t ntl = (uint32_t)n_tiles_for(N);
+  if (nsplit < 1) nsplit = 1;
+  if ((uint32_t)nsplit > ntl && ntl > 0) nsplit = (int)ntl;
+  const uint32_t tps = ntl ? (ntl + nsplit - 1) / nsplit : 0;
+  if (ntl) nsplit = (int)((ntl + tps - 1) / tps);
+  double* target;
+  if (nsplit == 1 && Mpad == M) {
+    target = d_out;
+  } else {
+    if (!d_partial) {
+      set_error("kde_eval_split_f32: partial buffer required (nsplit=%d)", nsplit);
+      return 1;
+    }
+    target = d_partial;
+  }
+  int rc = 1;
+  switch (D) {
+#define KDSB_CASE(d)                                                                              \
+  case d:                                                                                         \
+    rc = launch_eval_split<d>(d_packed, ntl, tps, nsplit, d_qT, Mpad, out_scale, target, st);     \
+    break;
+    KDSB_CASE(1)
+    KDSB_CASE(2)
+    KDSB_CASE(3)
+    KDSB_CASE(4)
+    KDSB_CASE(5)
+    KDSB_CASE(6)
+    KDSB_CASE(7)
+    KDSB_CASE(8)
+#undef KDSB_CASE
+    default:
+      set_error("kde_eval_split_f32: D=%d out of range 1..8", D);
+      return 1;
+  }
+  if (rc) return rc;
+  if (target != d_out) {
+    reduce_splits_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(target, nsplit, M, Mpad,
+                                                                      d_out);
+    KDSB_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

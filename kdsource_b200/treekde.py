@@ -12,6 +12,11 @@ Semantics: ``out[m] = sum_i w_i/sum(w) (2 pi)^(-d/2) h_i^-d exp(-|q_m - x_i|^2 /
 ``cutoff="treekde"`` applies the hard support radius KDEpy's TreeKDE derives
 from the largest bandwidth; a float is an explicit radius.
 
+``dtype``: ``"float32"`` (default; 1e-5 for bandwidths down to ~0.1 of the data's
+spread), ``"float32x2"`` (Gaussian kernel; coordinates carried as hi + lo floats so the
+error does not grow with spread / bandwidth: ~1e-6, about half the speed) or
+``"float64"`` (1e-12).
+
 ``kernel="epa"`` / ``"box"`` (the other two names the reference passes to KDEpy,
 kdsource.py:60-65) are KDEpy's radially symmetric finite-support kernels scaled
 to unit variance: support radius ``R_i = h_i sqrt(5)`` (epa) or ``h_i sqrt(3)``
@@ -58,8 +63,8 @@ class TreeKDE:
             raise ValueError("bw must be a scalar or a 1-D array")
         self.bw = bw
         self.cutoff = cutoff
-        if dtype not in ("float32", "float64"):
-            raise ValueError("dtype must be 'float32' or 'float64'")
+        if dtype not in ("float32", "float32x2", "float64"):
+            raise ValueError("dtype must be 'float32', 'float32x2' or 'float64'")
         self.dtype = dtype
         self.data = None
         self.weights = None
@@ -168,7 +173,25 @@ class TreeKDE:
         d_w = _lib.to_dev(w) if w is not None else None
         d_bw = _lib.to_dev(bw_arr) if bw_arr is not None else None
         w_scale = 1.0 / sumw
-        if self.dtype == "float32" and gauss:
+        if self.dtype == "float32x2":
+            if not gauss:
+                raise ValueError("dtype='float32x2' is implemented for the gaussian kernel")
+            if dev["cutoff"]:
+                raise ValueError("dtype='float32x2' has no cutoff mode")
+            # hi parts live on the grid 2^-S, chosen so that |x - c| 2^S < 2^20 (two spare
+            # bits for query points outside the sources' bounding box)
+            maxabs = float(np.max(np.abs(self.data - center))) if N else 1.0
+            S = 20 - int(np.ceil(np.log2(max(maxabs, 1e-300))))
+            dev["grid"] = float(2.0 ** S)
+            lc_ref = np.log2(wmax * w_scale) - D * np.log2(hmin)
+            packed = _lib.empty(L.kdsb200_packed_split_floats(N, D), t.float32)
+            cen_keep, cen_p = _lib.hostvec(center)
+            _lib.check(L.kdsb200_pack_sources_split_f32(
+                _lib.ptr(d_data), _lib.ptr(d_w), _lib.ptr(d_bw), bw_scalar, N, D, cen_p,
+                w_scale, lc_ref, dev["grid"], _lib.ptr(packed), _lib.stream()))
+            dev["packed"] = packed
+            dev["out_scale"] = float(2.0 ** lc_ref * (2 * np.pi) ** (-D / 2))
+        elif self.dtype == "float32" and gauss:
             lc_ref = np.log2(wmax * w_scale) - D * np.log2(hmin)
             packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
             cen_keep, cen_p = _lib.hostvec(center)
@@ -208,7 +231,18 @@ class TreeKDE:
         d_out = _lib.empty(M, t.float64)
         if M == 0:
             return d_out
-        if self.dtype == "float32":
+        if self.dtype == "float32x2":
+            Mpad = L.kdsb200_eval_mpad(M)
+            qT = _lib.empty(Mpad * 2 * D, t.float32)
+            cen_keep, cen_p = _lib.hostvec(dev["center"])
+            _lib.check(L.kdsb200_pack_queries_split_f32(_lib.ptr(d_pts), M, Mpad, D, cen_p,
+                                                        dev["grid"], _lib.ptr(qT), _lib.stream()))
+            nsplit = L.kdsb200_eval_nsplit(N, M)
+            partial = _lib.empty(nsplit * Mpad, t.float64)
+            _lib.check(L.kdsb200_kde_eval_split_f32(
+                _lib.ptr(dev["packed"]), N, D, _lib.ptr(qT), M, Mpad, dev["out_scale"], nsplit,
+                _lib.ptr(partial), _lib.ptr(d_out), _lib.stream()))
+        elif self.dtype == "float32":
             Mpad = L.kdsb200_eval_mpad(M)
             qT = _lib.empty(Mpad * D, t.float32)
             cen_keep, cen_p = _lib.hostvec(dev["center"])

@@ -81,6 +81,39 @@ def test_evaluate_cutoff_and_dims(oracle):
     assert one[0] == pytest.approx((2 * np.pi) ** -3 * 0.4 ** -6, rel=1e-6)
 
 
+def test_evaluate_split_precision_small_bandwidth(oracle, scaled):
+    """dtype="float32x2": coordinates as hi + lo floats.  With a bandwidth of 2-3 % of the
+    data's spread the plain fp32 kernel is past its 1e-5 domain (error ~ spread/h^2); the
+    split kernel stays below 4e-6 (what remains is the fp32 rounding of the exponent itself),
+    scalar and per-particle bandwidths, D = 1..8."""
+    from kdsource_b200.treekde import TreeKDE
+
+    data, w = scaled["data"], scaled["w"]
+    rng = np.random.default_rng(9)
+    q = data[rng.integers(0, len(data), 1500)] + rng.normal(scale=0.03, size=(1500, 6))
+    errs = {}
+    for name, bw in (("scalar", 0.03), ("adaptive", rng.uniform(0.02, 0.05, len(data)))):
+        ref = oracle.kde_sum_c(data, w, bw, q)
+        ok = ref > 1e-12 * ref.max()
+        for dt in ("float32", "float32x2"):
+            got = TreeKDE(bw=bw, dtype=dt).fit(data, w).evaluate(q)
+            errs[name, dt] = float(np.max(np.abs(got[ok] / ref[ok] - 1)))
+        assert errs[name, "float32x2"] < 4e-6, errs
+        assert errs[name, "float32x2"] < 0.2 * errs[name, "float32"], errs
+    for d in (1, 2, 3, 5, 7, 8):
+        X = rng.normal(size=(3000, d)) * 3 + 50.0  # far from the origin: recentring matters
+        Q = X[:700] + rng.normal(scale=0.1, size=(700, d))
+        wx = rng.uniform(0.5, 2, 3000)
+        ref = oracle.kde_sum_c(X, wx, 0.2, Q)
+        got = TreeKDE(bw=0.2, dtype="float32x2").fit(X, wx).evaluate(Q)
+        assert np.max(np.abs(got / ref - 1)) < 4e-6, d
+    # queries far outside the sources' box: densities underflow, nothing breaks
+    far = TreeKDE(bw=0.2, dtype="float32x2").fit(X, wx).evaluate(X[:10] + 1e4)
+    assert np.all(far == 0)
+    with pytest.raises(ValueError):
+        TreeKDE(kernel="epa", bw=0.2, dtype="float32x2").fit(X).evaluate(Q)
+
+
 @pytest.mark.parametrize("kernel", ["epa", "box"])
 def test_evaluate_finite_support_kernels(oracle, scaled, kernel):
     """KDEpy's radial Epanechnikov / box kernels (kdsource.py:60-65), scalar and

@@ -56,6 +56,12 @@ def case_evaluate(rng, worst):
         # radius, so in fp32 the Epanechnikov sum is held to 2e-4 (use dtype="float64" beyond)
         assert e32 < (1e-5 if kern == "gaussian" else 2e-4), ("evaluate fp32", kern, D, N, M, e32)
         worst["evaluate_fp32_" + kern] = max(worst.get("evaluate_fp32_" + kern, 0), e32)
+    if kern == "gaussian":
+        gx2 = TreeKDE(bw=bw, dtype="float32x2").fit(data, w).evaluate(q)
+        big = ref > 1e-12 * ref.max()
+        ex2 = float(np.max(np.abs(gx2[big] / ref[big] - 1))) if big.any() else 0.0
+        assert ex2 < 4e-6, ("evaluate float32x2", D, N, M, ex2)
+        worst["evaluate_fp32x2"] = max(worst.get("evaluate_fp32x2", 0), ex2)
 
 
 def case_mlcv(rng, worst):
