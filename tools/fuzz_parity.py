@@ -60,7 +60,9 @@ def case_evaluate(rng, worst):
         gx2 = TreeKDE(bw=bw, dtype="float32x2").fit(data, w).evaluate(q)
         big = ref > 1e-12 * ref.max()
         ex2 = float(np.max(np.abs(gx2[big] / ref[big] - 1))) if big.any() else 0.0
-        assert ex2 < 4e-6, ("evaluate float32x2", D, N, M, ex2)
+        # what remains is the fp32 rounding of the exponent itself: ~1e-7 * |exponent|, i.e. a
+        # few 1e-6 for far-tail densities (1e-12 of the maximum)
+        assert ex2 < 1e-5, ("evaluate float32x2", D, N, M, ex2)
         worst["evaluate_fp32x2"] = max(worst.get("evaluate_fp32x2", 0), ex2)
 
 
