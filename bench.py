@@ -233,7 +233,7 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
     parts, w, g, scaling, data = synthetic_scaled(N)
     _, _, _, _, q = synthetic_scaled(M, seed=54321, wseed=1)
     bw = kde.bw_silv(D_MLCV, np.sum(w) ** 2 / np.sum(w ** 2))
-    k = TreeKDE(bw=bw).fit(data, w)
+    k = TreeKDE(bw=bw, dtype="float32").fit(data, w)
     dev = k._device_state()
     d_q = _lib.to_dev(q)
 
@@ -255,6 +255,19 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
                      "peak": peaks["ffma2"] / 1e9, "unit": "Glane-op/s",
                      "frac": pairs * 13 / (ms * 1e-3) / peaks["ffma2"],
                      "per_unit": "13 FP32 lane-ops + 1 MUFU per pair (d=6)", "traffic": None}}
+    # split-coordinate kernel (dtype="float32x2", what dtype="auto" selects for small bandwidths)
+    k2 = TreeKDE(bw=bw, dtype="float32x2").fit(data, w)
+    dev2 = k2._device_state()
+    for _ in range(2):
+        k2.evaluate_device(d_q, M, dev2)
+    ms2 = float(np.median(time_events(t, lambda: k2.evaluate_device(d_q, M, dev2), 3)))
+    sub["evaluate"]["float32x2"] = {
+        "pairs_per_s": pairs / (ms2 * 1e-3), "ms": ms2,
+        "roofline": {"bound": "fp32", "achieved": pairs * 25 / (ms2 * 1e-3) / 1e9,
+                     "peak": peaks["ffma2"] / 1e9, "unit": "Glane-op/s",
+                     "frac": pairs * 25 / (ms2 * 1e-3) / peaks["ffma2"],
+                     "per_unit": "25 FP32 lane-ops + 1 MUFU per pair (d=6)", "traffic": None}}
+    del k2, dev2
     if cpu:
         from oracle import kds_oracle as O
 

@@ -12,10 +12,11 @@ Semantics: ``out[m] = sum_i w_i/sum(w) (2 pi)^(-d/2) h_i^-d exp(-|q_m - x_i|^2 /
 ``cutoff="treekde"`` applies the hard support radius KDEpy's TreeKDE derives
 from the largest bandwidth; a float is an explicit radius.
 
-``dtype``: ``"float32"`` (default; 1e-5 for bandwidths down to ~0.1 of the data's
-spread), ``"float32x2"`` (Gaussian kernel; coordinates carried as hi + lo floats so the
-error does not grow with spread / bandwidth: ~1e-6, about half the speed) or
-``"float64"`` (1e-12).
+``dtype``: ``"float32"`` (1e-5 while the smallest bandwidth is above ~0.28 of the
+data's spread: the coordinate rounding error grows like (spread / h)^2),
+``"float32x2"`` (Gaussian kernel; coordinates carried as hi + lo floats, error
+independent of spread / bandwidth, ~57 % of the fp32 rate), ``"float64"`` (1e-12), or
+``"auto"`` (default): float32, switching to float32x2 below that bandwidth ratio.
 
 ``kernel="epa"`` / ``"box"`` (the other two names the reference passes to KDEpy,
 kdsource.py:60-65) are KDEpy's radially symmetric finite-support kernels scaled
@@ -55,7 +56,10 @@ def treekde_radius(bw_max, atol=1e-3):
 
 
 class TreeKDE:
-    def __init__(self, kernel="gaussian", bw=1.0, cutoff=None, dtype="float32"):
+    #: below this bandwidth / spread ratio dtype="auto" switches to the split-coordinate kernel
+    AUTO_SPLIT_BELOW = 0.28
+
+    def __init__(self, kernel="gaussian", bw=1.0, cutoff=None, dtype="auto"):
         if kernel not in _KERNEL_ALIASES:
             raise ValueError("Unknown kernel {!r}".format(kernel))
         self.kernel = _KERNEL_ALIASES[kernel]
@@ -63,8 +67,8 @@ class TreeKDE:
             raise ValueError("bw must be a scalar or a 1-D array")
         self.bw = bw
         self.cutoff = cutoff
-        if dtype not in ("float32", "float32x2", "float64"):
-            raise ValueError("dtype must be 'float32', 'float32x2' or 'float64'")
+        if dtype not in ("auto", "float32", "float32x2", "float64"):
+            raise ValueError("dtype must be 'auto', 'float32', 'float32x2' or 'float64'")
         self.dtype = dtype
         self.data = None
         self.weights = None
@@ -143,7 +147,7 @@ class TreeKDE:
         bw_arr, bw_scalar = self._bw_array()
         d = self._dev
         if (d is not None and d["data_ref"] is self.data and d["weights_ref"] is self.weights
-                and d["dtype"] == self.dtype and d["cutoff_spec"] == self.cutoff
+                and d["dtype_spec"] == self.dtype and d["cutoff_spec"] == self.cutoff
                 and d["kernel"] == self.kernel
                 and d["bw_scalar_snap"] == bw_scalar
                 and ((bw_arr is None) == (d["bw_snap"] is None))
@@ -164,16 +168,24 @@ class TreeKDE:
         else:
             center = self.data.mean(axis=0)
         gauss = self.kernel == "gaussian"
-        dev = {"N": N, "D": D, "center": center, "kernel": self.kernel,
+        dtype = self.dtype
+        if dtype == "auto":
+            dtype = "float32"
+            if gauss and self.cutoff is None and N > 1:
+                spread = float(np.max(np.sqrt(np.average((self.data - center) ** 2, axis=0,
+                                                         weights=w))))
+                if hmin < self.AUTO_SPLIT_BELOW * spread:
+                    dtype = "float32x2"
+        dev = {"N": N, "D": D, "center": center, "kernel": self.kernel, "dtype_spec": self.dtype,
                "cutoff": self._cutoff_radius(hmax) if gauss else 0.0,
-               "data_ref": self.data, "weights_ref": self.weights, "dtype": self.dtype,
+               "data_ref": self.data, "weights_ref": self.weights, "dtype": dtype,
                "cutoff_spec": self.cutoff, "bw_scalar_snap": bw_scalar,
                "bw_snap": None if bw_arr is None else bw_arr.copy()}
         d_data = _lib.to_dev(self.data)
         d_w = _lib.to_dev(w) if w is not None else None
         d_bw = _lib.to_dev(bw_arr) if bw_arr is not None else None
         w_scale = 1.0 / sumw
-        if self.dtype == "float32x2":
+        if dtype == "float32x2":
             if not gauss:
                 raise ValueError("dtype='float32x2' is implemented for the gaussian kernel")
             if dev["cutoff"]:
@@ -191,7 +203,7 @@ class TreeKDE:
                 w_scale, lc_ref, dev["grid"], _lib.ptr(packed), _lib.stream()))
             dev["packed"] = packed
             dev["out_scale"] = float(2.0 ** lc_ref * (2 * np.pi) ** (-D / 2))
-        elif self.dtype == "float32" and gauss:
+        elif dtype == "float32" and gauss:
             lc_ref = np.log2(wmax * w_scale) - D * np.log2(hmin)
             packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
             cen_keep, cen_p = _lib.hostvec(center)
@@ -200,7 +212,7 @@ class TreeKDE:
                 w_scale, lc_ref, 0, _lib.ptr(packed), _lib.stream()))
             dev["packed"] = packed
             dev["out_scale"] = float(2.0 ** lc_ref * (2 * np.pi) ** (-D / 2))
-        elif self.dtype == "float32":
+        elif dtype == "float32":
             # finite-support kernels: linear coefficients w_i R_i^-D / 2^lc_ref (mode 1)
             # with the support radius R_i in place of the bandwidth
             sc = _SUPPORT_SCALE[self.kernel]
@@ -231,7 +243,7 @@ class TreeKDE:
         d_out = _lib.empty(M, t.float64)
         if M == 0:
             return d_out
-        if self.dtype == "float32x2":
+        if dev["dtype"] == "float32x2":
             Mpad = L.kdsb200_eval_mpad(M)
             qT = _lib.empty(Mpad * 2 * D, t.float32)
             cen_keep, cen_p = _lib.hostvec(dev["center"])
@@ -242,7 +254,7 @@ class TreeKDE:
             _lib.check(L.kdsb200_kde_eval_split_f32(
                 _lib.ptr(dev["packed"]), N, D, _lib.ptr(qT), M, Mpad, dev["out_scale"], nsplit,
                 _lib.ptr(partial), _lib.ptr(d_out), _lib.stream()))
-        elif self.dtype == "float32":
+        elif dev["dtype"] == "float32":
             Mpad = L.kdsb200_eval_mpad(M)
             qT = _lib.empty(Mpad * D, t.float32)
             cen_keep, cen_p = _lib.hostvec(dev["center"])

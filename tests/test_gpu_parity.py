@@ -112,6 +112,18 @@ def test_evaluate_split_precision_small_bandwidth(oracle, scaled):
     assert np.all(far == 0)
     with pytest.raises(ValueError):
         TreeKDE(kernel="epa", bw=0.2, dtype="float32x2").fit(X).evaluate(Q)
+    # dtype="auto" (the default) picks the kernel from bandwidth / spread
+    unit = scaled["data"]
+    assert TreeKDE(bw=0.5).fit(unit, w)._device_state()["dtype"] == "float32"
+    assert TreeKDE(bw=0.1).fit(unit, w)._device_state()["dtype"] == "float32x2"
+    assert TreeKDE(bw=0.1).fit(unit * 100, w)._device_state()["dtype"] == "float32x2"
+    assert TreeKDE(bw=30.0).fit(unit * 100, w)._device_state()["dtype"] == "float32"
+    assert TreeKDE(bw=0.1, cutoff=1.0).fit(unit, w)._device_state()["dtype"] == "float32"
+    assert TreeKDE(kernel="epa", bw=0.1).fit(unit, w)._device_state()["dtype"] == "float32"
+    auto = TreeKDE(bw=0.03).fit(data, w).evaluate(q)
+    ref = oracle.kde_sum_c(data, w, 0.03, q)
+    ok = ref > 1e-12 * ref.max()
+    assert np.max(np.abs(auto[ok] / ref[ok] - 1)) < 4e-6
 
 
 @pytest.mark.parametrize("kernel", ["epa", "box"])
