@@ -33,6 +33,7 @@ struct GzJob {
 
 struct kdsb200_gz_writer_s {
   int fd = -1;
+  int device = 0;
   cudaStream_t st = nullptr;
   uint64_t cap = 0, file_off = 0;
   uint32_t member = 0, rec_bytes = 0, tail_bytes = 0;
@@ -70,6 +71,7 @@ static bool pwrite_all(int fd, const unsigned char* p, uint64_t n, uint64_t off)
 }
 
 static void writer_loop(kdsb200_gz_writer_s* w) {
+  cudaSetDevice(w->device);  // a new thread starts on device 0; the events live on w->device
   for (;;) {
     GzJob job;
     {
@@ -133,6 +135,7 @@ kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_b
     return nullptr;
   }
   w->st = (cudaStream_t)stream;
+  cudaGetDevice(&w->device);
   w->member = kdsb200_gz_member_bytes();
   w->rec_bytes = rec_bytes;
   w->tail_bytes = tail_bytes;
