@@ -18,11 +18,20 @@ bw = kde.bw_silv(6, np.sum(w) ** 2 / np.sum(w ** 2))
 if which in ("all", "eval"):
     M = 200_000
     q = synthetic_scaled(M, seed=54321, wseed=1)[4]
-    k = TreeKDE(bw=bw).fit(data, w)
+    k = TreeKDE(bw=bw, dtype="float32").fit(data, w)
     dev = k._device_state()
     d_q = _lib.to_dev(q)
     for _ in range(3):
         k.evaluate_device(d_q, M, dev)
+    t.cuda.synchronize()
+if which in ("all", "evalx2"):
+    M = 200_000
+    q = synthetic_scaled(M, seed=54321, wseed=1)[4]
+    k2 = TreeKDE(bw=bw, dtype="float32x2").fit(data, w)
+    dev2 = k2._device_state()
+    d_q2 = _lib.to_dev(q)
+    for _ in range(3):
+        k2.evaluate_device(d_q2, M, dev2)
     t.cuda.synchronize()
 if which in ("all", "mlcv"):
     plan = kde.MLCVPlan(data, w, bw, np.logspace(-0.3, 0.3, 32), n_splits=10)
