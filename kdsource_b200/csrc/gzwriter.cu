@@ -7,6 +7,8 @@
 // generator, the PCIe copy and the file system work concurrently.  Small host-side
 // pieces (the MCPL header) go through zlib as a gzip member of their own.
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
@@ -46,7 +48,8 @@ struct kdsb200_gz_writer_s {
   uint64_t* d_hist = nullptr;
   uint64_t* h_small = nullptr;  // pinned: [0] total, [1..258] histogram
   cudaEvent_t ev[2] = {nullptr, nullptr};
-  int next_slot = 0, write_threads = 4;
+  int next_slot = 0, write_threads = 8;
+  bool use_mmap = true;
   // worker
   std::thread worker;
   std::mutex mu;
@@ -70,6 +73,31 @@ static bool pwrite_all(int fd, const unsigned char* p, uint64_t n, uint64_t off)
   return true;
 }
 
+// Copy a finished batch into the file through a shared mapping: the file is extended to
+// its new length and the slices are memcpy'd by several threads.  Unlike pwrite(), which
+// holds the inode lock for the whole copy (measured on tmpfs: 2.6 GB/s whatever the number
+// of threads), page faults on a mapping are served in parallel.  Returns false when the
+// file system does not support it (the caller falls back to pwrite).
+static bool mmap_write(int fd, const unsigned char* src, uint64_t n, uint64_t off, int nthreads) {
+  const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+  struct stat sb;  // extend only: a later host member may already lie behind this batch
+  if (fstat(fd, &sb) != 0) return false;
+  if ((uint64_t)sb.st_size < off + n && ftruncate(fd, (off_t)(off + n)) != 0) return false;
+  const uint64_t a0 = off / page * page;
+  const size_t len = (size_t)(off + n - a0);
+  void* m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)a0);
+  if (m == MAP_FAILED) return false;
+  unsigned char* dst = (unsigned char*)m + (off - a0);
+  const uint64_t per = ((n + nthreads - 1) / nthreads + page - 1) / page * page;
+  std::vector<std::thread> ths;
+  for (int i = 0; i < nthreads; i++) {
+    const uint64_t lo = std::min<uint64_t>(n, per * i), hi = std::min<uint64_t>(n, per * (i + 1));
+    if (hi > lo) ths.emplace_back([=] { memcpy(dst + lo, src + lo, hi - lo); });
+  }
+  for (auto& t : ths) t.join();
+  return munmap(m, len) == 0;
+}
+
 static void writer_loop(kdsb200_gz_writer_s* w) {
   cudaSetDevice(w->device);  // a new thread starts on device 0; the events live on w->device
   for (;;) {
@@ -82,6 +110,12 @@ static void writer_loop(kdsb200_gz_writer_s* w) {
       w->queue.erase(w->queue.begin());
     }
     bool ok = cudaEventSynchronize(job.ev) == cudaSuccess;
+    if (ok && w->use_mmap && job.bytes > (8u << 20)) {
+      if (!mmap_write(w->fd, w->h_out[job.slot], job.bytes, job.file_off, w->write_threads))
+        w->use_mmap = false;  // not supported here: pwrite from now on (this batch included)
+      else
+        goto written;
+    }
     if (ok) {
       const int nt = job.bytes > (8u << 20) ? w->write_threads : 1;
       const uint64_t per = ((job.bytes + nt - 1) / nt + 4095) / 4096 * 4096;
@@ -98,6 +132,7 @@ static void writer_loop(kdsb200_gz_writer_s* w) {
       for (auto& t : ths) t.join();
       for (char c : oks) ok = ok && c;
     }
+  written:
     {
       std::lock_guard<std::mutex> lk(w->mu);
       w->busy[job.slot] = false;
@@ -128,7 +163,7 @@ kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_b
     return nullptr;
   }
   kdsb200_gz_writer_s* w = new kdsb200_gz_writer_s();
-  w->fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  w->fd = open(path, O_RDWR | O_CREAT | O_TRUNC, 0644);  // read access: shared mapping
   if (w->fd < 0) {
     set_error("gz_writer_open: cannot create %s", path);
     delete w;
@@ -160,12 +195,14 @@ kdsb200_gz_writer* kdsb200_gz_writer_open(const char* path, uint64_t max_batch_b
     kdsb200_gz_writer_close(w, &dummy);
     return nullptr;
   }
-  // pwrite of slices on KDSB200_WRITE_THREADS threads (default 4).  Measured on tmpfs
-  // (1e9 particles, 22.5 GB): 2, 8 and 16 threads give the same 2.6 GB/s -- writes to one
-  // file serialise on its inode lock -- so this only helps file systems that stripe.
+  // batches are copied into the file by KDSB200_WRITE_THREADS threads (default 8) through a
+  // shared mapping: 22.5 GB in 3.1 s on tmpfs (4 threads: 4.4 s, 16: no further gain); with
+  // pwrite() 2, 8 and 16 threads all gave 2.6 GB/s (one file, one inode lock)
   const char* e = getenv("KDSB200_WRITE_THREADS");
-  const int nt = e ? atoi(e) : 4;
+  const int nt = e ? atoi(e) : 8;
   w->write_threads = nt < 1 ? 1 : (nt > 64 ? 64 : nt);
+  const char* mode = getenv("KDSB200_WRITE_MODE");  // "pwrite" disables the mapped copy
+  w->use_mmap = !(mode && strcmp(mode, "pwrite") == 0);
   w->worker = std::thread(writer_loop, w);
   return w;
 }
