@@ -459,3 +459,43 @@ def test_gzip_table_builder_inflates_with_zlib():
     rec2[17, 99] ^= 1  # one record whose tail differs
     assert roundtrip(rec2.tobytes(), rec=100, tail=60) < 0.55 * rec2.size
     roundtrip(rec2.tobytes(), rec=100, tail=4)
+
+
+def test_plot_methods_host_logic(workdir):
+    """Argument handling of the plot back-ends that runs before any kernel: fitted check,
+    variable names, the [vec0, vec1] sample mask and its empty-range error (reference
+    kdsource.py:447-471, 552-571), and the kernel names / roughness table."""
+    import kdsource_b200.api as kds
+    from kdsource_b200.kdsource import R
+
+    pl = kds.PList("samples.mcpl.gz")
+    geo = kds.geom.Geometry([kds.geom.Lethargy(10), kds.geom.SurfXY(), kds.geom.PolarMu()])
+    for kern, r in (("gaussian", 1 / (2 * np.sqrt(np.pi))), ("epa", 3 / 5), ("box", 1 / 3)):
+        s = kds.KDSource(pl, geo, bw=0.5, kernel=kern)
+        assert s.R == pytest.approx(r) and s.R == R[kern[0]] and s.kde.kernel == kern
+        for call in (lambda: s.plot_integr("x", np.linspace(-1, 1, 3)),
+                     lambda: s.plot_E(np.logspace(-3, 0, 3)),
+                     lambda: s.plot_t(np.linspace(0, 1, 3)),
+                     lambda: s.plot2D_integr(["x", "y"], [np.zeros(2), np.zeros(2)]),
+                     lambda: s.plot2D_point(["x", "y"], [np.zeros(2), np.zeros(2)], np.zeros(7))):
+            with pytest.raises(Exception, match="Must fit"):
+                call()
+    s = kds.KDSource(pl, geo, bw=0.5)
+    s.fit()
+    data = s.kde.data
+    assert s._range_mask(None, None).all() and len(s._range_mask(None, None)) == len(data)
+    lo = np.full(5, -np.inf)
+    lo[1] = np.median(data[:, 1] * s.scaling[1])
+    m = s._range_mask(lo, None)
+    assert np.array_equal(m, data[:, 1] >= lo[1] / s.scaling[1]) and 0 < m.sum() < len(data)
+    hi = np.full(5, np.inf)
+    hi[1] = lo[1]
+    assert not (s._range_mask(lo, hi) & ~(data[:, 1] * s.scaling[1] == lo[1])).any()
+    with pytest.raises(Exception, match="No particles"):
+        s.plot_E(np.logspace(-3, 0, 3), vec0=np.full(5, 1e9), vec1=np.full(5, 2e9))
+    with pytest.raises(Exception, match="No particles"):
+        s.plot2D_integr(["x", "y"], [np.zeros(2), np.zeros(2)], vec0=np.full(5, 1e9))
+    with pytest.raises(KeyError):
+        s.plot_integr("no_such_variable", np.zeros(3))
+    with pytest.raises(ValueError):
+        kds.KDSource(pl, geo, bw=np.zeros((2, 2)))
