@@ -13,7 +13,12 @@
  *     the reference's own C functions compiled in place (oracle/_ref).
  *   - the Gaussian kernel sum itself restates KDEpy's published formula
  *     (KDEpy>=1.1.12, pinned in pyproject.toml:13; source not in the tree):
- *     PARITY UNPINNED for that arithmetic except through analytic checks.
+ *     PARITY UNPINNED against KDEpy itself; the formula is cross-checked
+ *     against scikit-learn's exact weighted KernelDensity and scipy's
+ *     gaussian_kde (tests/test_oracle.py::test_kde_sum_vs_independent_libraries)
+ *     and through analytic checks.
+ *   - KDSource.fit / evaluate / plot marginals around that sum: pinned by the
+ *     reference's own kdsource.py + plist.py run in place (ref_kdsource.npz).
  *   - index pick by prefix-sum + binary search and the Philox counter layout
  *     are this project's own contract (the reference walks the list
  *     sequentially, clib/src/kdsource.c:282-330); agreement with the

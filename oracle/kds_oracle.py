@@ -14,9 +14,11 @@ Two layers:
   reference's own C sources compiled in place -- used to pin the restatement.
 
 Parity status: see the header of ``kds_oracle.c``.  The Gaussian kernel sum
-restates KDEpy (absent from the reference tree): parity unpinned for that
-arithmetic; everything around it is pinned by the reference's own code run in
-place (``tests/golden/make_golden.py``) or by ``oracle/_ref``.
+restates KDEpy (absent from the reference tree): parity unpinned against KDEpy
+itself (cross-checked against scikit-learn's and scipy's estimators);
+everything around it -- including the reference's whole ``KDSource`` object --
+is pinned by the reference's own code run in place
+(``tests/golden/make_golden.py``) or by ``oracle/_ref``.
 """
 
 import ctypes
