@@ -943,7 +943,8 @@ void kdsource_resample_to_mcpl(double (*rng_stateless)(void), const char* kds_so
   printf("Resampling...\n");
   // records are produced, gzip-compressed (gzip.cu) and staged on the device; a worker
   // thread writes the previous batch while the next one is generated
-  const uint64_t B = nout < (1ull << 22) ? nout : (1ull << 22);
+  const uint64_t Bmax = nout > (1ull << 27) ? (1ull << 22) : (1ull << 20);  // see resample.py
+  const uint64_t B = nout < Bmax ? nout : Bmax;
   kdsb200_gz_writer* w = kdsb200_gz_writer_open(out.c_str(), B * 36, 36, 12, (void*)I->stream);
   if (!w) kds_error(kdsb200_last_error());
   const std::vector<unsigned char> hdr =
