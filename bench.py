@@ -128,6 +128,17 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+def mlcv_config(n_mlcv):
+    """The `config` object of the headline line -- the same for both arms."""
+    return {"workload": "mlcv_1e6x6d_g32_k10" if n_mlcv == N_MLCV else
+            "mlcv_{}x6d_g32_k10".format(n_mlcv),
+            "N": n_mlcv, "d": D_MLCV, "G": G_MLCV, "n_splits": K_MLCV,
+            "l2": "flushed between timed steps (256 MiB write, untimed)",
+            "sharding": "test rows over ranks, each rank uploads its rows and the list is "
+                        "all-gathered over NVLink, device reduction + NCCL all-reduce of the G "
+                        "partial log-likelihoods inside the timed step"}
+
+
 def cpu_mlcv_baseline(data, w, bw, grid, nthreads=0):
     """Oracle port (C + OpenMP, all host threads) on a bounded sample."""
     from oracle import kds_oracle as O
@@ -143,34 +154,49 @@ def cpu_mlcv_baseline(data, w, bw, grid, nthreads=0):
     return evals / dt, dt, n
 
 
-def cpu_mlcv_tree_baseline(data, w, bw, grid):
-    """The reference's algorithm as it runs on a CPU -- one process per grid point
-    (joblib), K tree builds + truncated ball-query sums each (oracle.mlcv_scores_tree,
-    SURVEY appendix D) -- on a bounded sample, in dense-equivalent evaluations/s.  At
-    sample sizes that finish in seconds it is slower than the dense OpenMP port used for
-    `cpu_baseline`; its cost grows like N log N instead of N^2, so it would overtake the
-    port somewhere above 1e5 particles."""
+def cpu_mlcv_tree_baseline(n=100_000):
+    """The reference's ALGORITHM as it runs on a CPU (kde.py:134-151, 204-211): one joblib
+    process per grid point, each building a kd-tree over the training folds and summing the
+    truncated Gaussian over an approximate ball query per test point
+    (oracle.mlcv_scores_tree) -- at N = 1e5 on all cores, bounded to ONE
+    of the ten folds per grid point (a fold costs the same as any other), reported in
+    dense-equivalent evaluations/s.  In six dimensions the ball query visits most of the
+    tree, so this is slower than the dense OpenMP port, not faster."""
+    from kdsource_b200 import kde
     from oracle import kds_oracle as O
 
-    n = min(12_000, len(data))
     cores = os.cpu_count() or 1
+    _, w, _, _, data = synthetic_scaled(n)
+    bw = kde.bw_silv(D_MLCV, np.sum(w) ** 2 / np.sum(w ** 2))
+    grid = np.logspace(-0.3, 0.3, G_MLCV)
     g = grid[::max(1, len(grid) // min(cores, len(grid)))][:cores]
     fb = O.kfold_bounds(n, K_MLCV)
-    nf = np.diff(fb)
-    evals = float(np.sum(nf * (n - nf))) * len(g)
+    n0 = int(fb[1] - fb[0])
+    evals = float(n0) * (n - n0) * len(g)
+    from joblib import Parallel, delayed
+
+    def one_fold(gf):
+        train = np.r_[fb[1]:n]
+        return O.kde_sum_tree(data[train], w[train], gf * bw, data[:fb[1]])
+
     t0 = time.perf_counter()
-    O.mlcv_scores_tree(data[:n], w[:n], bw, g, K_MLCV, n_jobs=-1)
+    Parallel(n_jobs=-1)(delayed(one_fold)(gf) for gf in g)
     dt = time.perf_counter() - t0
     return {"value": evals / dt, "unit": UNIT + " (dense-equivalent)", "cores": cores,
-            "kind": "port", "sample": "cKDTree ball query + numpy per fold, joblib over {} grid "
-            "points, first {} particles ({:.1f} s)".format(len(g), n, dt)}
+            "kind": "port", "N": n,
+            "sample": "cKDTree ball query + numpy, fold 0 of 10 for {} grid points in {} joblib "
+                      "processes, N = {} ({:.1f} s)".format(len(g), cores, n, dt)}
 
 
 def run_reference(args):
     """`--impl reference`: the CPU implementation of the path on the host cores.
     The reference's MLCV is Python + KDEpy + joblib, none of which can run on the
     GPU box (KDEpy is not installable; /root/reference does not travel), so this
-    arm times the oracle port of the same arithmetic (C, OpenMP on all cores)."""
+    arm times restatements of it.  `value` is the FASTER of the two: the dense O(N^2)
+    sum in C + OpenMP on all cores (size-independent rate, timed on the first 24 000
+    particles each step).  `cpu_baseline.reference_algorithm` is the reference's own
+    algorithm (kd-tree ball queries, one joblib process per grid point) timed once at
+    N = 1e5 on all cores -- in six dimensions it is the slower one."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -187,15 +213,20 @@ def run_reference(args):
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals]) * 1e3)
-    sample = "first {} particles of the 1e6 list, G={}, K={}".format(CPU_SAMPLE_N, G_MLCV, K_MLCV)
+    sample = ("dense fp64 sum (C + OpenMP, {} threads) over the first {} particles of the 1e6 "
+              "list, G={}, K={}, per step".format(cores, CPU_SAMPLE_N, G_MLCV, K_MLCV))
+    try:
+        tree = cpu_mlcv_tree_baseline()
+    except Exception as e:  # joblib workers unavailable: keep the dense baseline
+        tree = {"unavailable": str(e)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "mlcv_1e6x6d_g32_k10", "sample": sample},
+        "config": mlcv_config(args.n or N_MLCV),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "reference_algorithm": tree},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -424,15 +455,31 @@ def cpu_resample_baseline(ps, ws_, bws, sc_, cores):
             dt = time.perf_counter() - t0
         kind = "reference"
         what = "KDS_rand_sample2 loop of the reference C library"
+        # the same loop as `kdsource-resample` really drives it: one ctypes callback into
+        # random.Random(seed).random per uniform (python/kdsource/resample.py:33-43)
+        ncli = 1_000_000
+        with tempfile.NamedTemporaryFile(suffix="_bws") as fh:
+            bws[:Nl].astype(np.float32).tofile(fh)
+            fh.flush()
+            t0 = time.perf_counter()
+            O.ref_sampler_cli(ps[:Nl], ws_[:Nl], 2112, metrics, "g", 1.0, ncli, seed=5,
+                              bwfile=fh.name)
+            dtc = time.perf_counter() - t0
+        cli = {"value": ncli / dtc, "unit": "particles/s", "cores": 1, "kind": "reference",
+               "sample": "the same C loop with the CLI's per-uniform Python callback "
+                         "(random.Random(seed).random through ctypes), {} particles "
+                         "({:.1f} s)".format(ncli, dtc)}
     else:
         t0 = time.perf_counter()
         O.resample(ps[:Nl], ws_[:Nl], bws[:Nl], O.make_geom(metrics), n, seed=5)
         dt = time.perf_counter() - t0
         kind = "port"
         what = "oracle C restatement"
+        cli = None
     return {"value": n / dt, "unit": "particles/s", "cores": 1, "kind": kind,
-            "sample": "{}: {} particles from a {}-particle in-memory list, no file output "
-                      "({:.1f} s)".format(what, n, Nl, dt)}
+            "sample": "{}: {} particles from a {}-particle in-memory list, inlined xorshift "
+                      "generator, no file output ({:.1f} s)".format(what, n, Nl, dt),
+            "cli_faithful": cli}
 
 
 def resample_e2e(ps, ws_, bws, gs_, sc_, quick):
@@ -505,6 +552,7 @@ def run_ours(args):
     flush = t.empty(256 << 20, dtype=t.uint8, device="cuda")
     for _ in range(args.warmup):
         plan.launch()
+        plan.collect(allreduce=True)
     t.cuda.synchronize()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -517,6 +565,8 @@ def run_ours(args):
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         e0.record()
         plan.launch()
+        # device reduction, NCCL all-reduce of the G partial sums and their download
+        scores = plan.collect(allreduce=True)
         e1.record()
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
@@ -533,9 +583,6 @@ def run_ours(args):
     nf = np.diff(fb).astype(np.float64)
     evals_step = float(np.sum(nf * (n_mlcv - nf))) * G_MLCV
     value = evals_step * args.steps / (tot_ms * 1e-3)
-    scores = plan.collect()
-    if world > 1:
-        scores = dist.allreduce_sum_numpy(scores)
 
     # end to end through the public API: host arrays in, scores out
     e2e_t = []
@@ -589,18 +636,14 @@ def run_ours(args):
                "sample": "first {} particles, G={}, K={} ({:.1f} s)".format(n, G_MLCV, K_MLCV, dt)}
         if not args.no_sub:
             try:
-                cpu["tree_variant"] = cpu_mlcv_tree_baseline(data, w, bw, grid)
+                cpu["reference_algorithm"] = cpu_mlcv_tree_baseline()
             except Exception as e:  # joblib workers unavailable: keep the dense baseline
-                cpu["tree_variant"] = {"unavailable": str(e)[:200]}
+                cpu["reference_algorithm"] = {"unavailable": str(e)[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "mlcv_1e6x6d_g32_k10" if n_mlcv == N_MLCV else
-                   "mlcv_{}x6d_g32_k10".format(n_mlcv),
-                   "N": n_mlcv, "d": D_MLCV, "G": G_MLCV, "n_splits": K_MLCV,
-                   "l2": "flushed between timed steps (256 MiB write, untimed)",
-                   "sharding": "test rows over ranks, sources replicated, allreduce of G scores"},
+        "config": mlcv_config(n_mlcv),
         "clocks": clk,
         "e2e": {"value": evals_step / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": int(plan.h2d_bytes), "d2h_bytes_per_step":
@@ -619,6 +662,7 @@ def run_ours(args):
         "calibration": cal,
         "hbm_peak_source": hbm_src,
         "scores_argmax": int(np.nanargmax(scores)),
+        "rows_recomputed_fp64": int(plan.n_flagged()),
         "cpu_baseline": cpu,
         "sub": sub,
     }

@@ -100,12 +100,45 @@ int kdsb200_mlcv_poly_slots(int G);
  * coefficient coefw = w_i / (n_fold * K) and lwtr = ln(sum of train weights).
  * h_nk[g] = -log2(e) / (2 grid[g]^2), G <= 32 per call.
  * d_partial[(Mpad/256)][gtile]: per-CTA sums of coefw*(ln S_ig - lwtr), in fixed
- * order (deterministic).  d_sbuf: nsplit*Mpad*gtile doubles, needed if nsplit>1. */
+ * order (deterministic).  d_sbuf: nsplit*Mpad*gtile doubles, needed if nsplit>1.
+ * d_flagmask (Mpad uint32, may be NULL): bit g of entry m is set when S_mg fell into
+ * the window where ex2.approx.ftz has flushed terms to zero (S < 2^-70 in the scaled
+ * units, i.e. the nearest training source is ~10 bandwidths or more away); such a
+ * (row, g) adds 0 to d_partial and must be recomputed by kdsb200_mlcv_rows_f64. */
 int kdsb200_mlcv_scores_f32(const float* d_packed, uint64_t N, int D, const float* d_qT,
                             uint64_t M, uint64_t Mpad, const int32_t* d_excl_lo,
                             const int32_t* d_excl_hi, const double* d_coefw,
                             const double* d_lwtr, const float* h_nk, int G, int nsplit,
-                            double* d_sbuf, double* d_partial, void* stream);
+                            double* d_sbuf, double* d_partial, uint32_t* d_flagmask,
+                            void* stream);
+/* fp64 rows (kde.py:106-153 is fp64 in the reference): the 1e-12 mode of the search and
+ * the recomputation of flagged rows.  Test rows are rows [row0, row0+M) of d_data (N,D);
+ * S_mg = sum_{j not in [lo_m,hi_m)} w_j w_scale h_j^-D exp(-|x_m-x_j|^2/(2 grid_g^2 h_j^2));
+ * d_partial[kdsb200_mlcv_f64_blocks(M)][kdsb200_mlcv_f64_gtile(G)] receives per-CTA sums
+ * of coefw_m (ln S_mg + log_shift - lwtr_m), restricted to the bits of d_rowmask[m] when
+ * d_rowmask != NULL.  d_coef2n: 2N doubles filled by kdsb200_mlcv_coef_f64 (w_j w_scale h_j^-D,
+ * then 1/(2 h_j^2)). */
+uint64_t kdsb200_mlcv_f64_blocks(uint64_t M);
+int kdsb200_mlcv_f64_gtile(int G);
+int kdsb200_mlcv_coef_f64(const double* d_w, const double* d_bw, double bw_scalar, uint64_t N,
+                          int D, double w_scale, double* d_coef2n, void* stream);
+int kdsb200_mlcv_rows_f64(const double* d_data, const double* d_coef2n, uint64_t N, int D,
+                          uint64_t row0, uint64_t M, const int32_t* d_excl_lo,
+                          const int32_t* d_excl_hi, const double* d_coefw, const double* d_lwtr,
+                          const double* h_grid, int G, double log_shift,
+                          const uint32_t* d_rowmask, double* d_partial, void* stream);
+/* Fold bookkeeping of the test rows [row0, row0+M) built on the device: sklearn
+ * KFold(n_splits=K) without shuffle (kde.py:134-136).  d_cwf[f] = 1/(n_f K),
+ * d_lwt[f] = ln(training weight of fold f), d_w (N) or NULL.  Outputs have Mpad entries. */
+int kdsb200_mlcv_rows_setup(uint64_t N, uint64_t K, uint64_t row0, uint64_t M, uint64_t Mpad,
+                            const double* d_w, const double* d_cwf, const double* d_lwt,
+                            int32_t* d_lo, int32_t* d_hi, double* d_coefw, double* d_lwtr,
+                            void* stream);
+/* d_out[g] (g < G) = sum of the rows of d_a[na][gt_a] and, if given, d_b[nb][gt_b]; one
+ * CTA, fixed summation order: the on-stream reduction ahead of the NCCL all-reduce of
+ * the G partial log-likelihoods. */
+int kdsb200_mlcv_reduce(const double* d_a, uint64_t na, int gt_a, const double* d_b, uint64_t nb,
+                        int gt_b, int G, double* d_out, void* stream);
 
 /* ---- kNN: NearestNeighbors(k+1).kneighbors inside batches (kde.py:91-98) -- */
 /* d_data (N,D) fp64 row-major; d_batch_off: nb+1 int64 offsets (np.array_split
@@ -126,6 +159,15 @@ int kdsb200_knn(const double* d_data, uint64_t N, int D, const int64_t* d_batch_
 int kdsb200_geom_transform(const double* d_parts, uint64_t M, const struct kdsb200_geom_s* h_geom,
                            const double* h_rot_inv, const double* h_inv_scaling, double* d_vecs,
                            double* d_jac, void* stream);
+
+/* Weighted column moments on the device (Metric.mean / Metric.std, geom.py:61-70; N_eff,
+ * plist.py:349-395): d_out[k] = sum_i w_i (v_ik - c_k)^power (power 1 or 2; h_center NULL:
+ * c = 0), d_out[D] = sum w_i, d_out[D+1] = sum w_i^2; d_w NULL: unit weights.  Fixed grid
+ * and summation order (reproducible).  d_scratch: kdsb200_moments_scratch() doubles. */
+uint64_t kdsb200_moments_scratch(void);
+int kdsb200_weighted_moments(const double* d_vecs, const double* d_w, uint64_t N, int D,
+                             const double* h_center, int power, double* d_scratch, double* d_out,
+                             void* stream);
 
 /* ---- resampling: KDS_rand_sample2 loop (kdsource.c:282-330, resamplemcpl.c:40-43)
  * with the metric perturbations of geom.c:192-650 ------------------------- */
@@ -164,6 +206,11 @@ int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void
  * d_ext_uniforms (count x slots doubles) replaces Philox (test mode).
  * Outputs (each may be NULL): 36-byte MCPL-3 single-precision records, picked
  * source index, full-precision particle (8 doubles). */
+/* 1 if the geometry has a specialised fp32 kernel (Lethargy+SurfXY+Isotrop or
+ * Energy+Vol+Isotrop, Gaussian kernel, no translation/rotation) whose maps hold every
+ * coordinate within 1e-5 of its scale; other geometries go through acos/atan2-based
+ * maps that fp32-rounded sources cannot hold to 1e-5 and should use the fp64 store. */
+int kdsb200_resample_fp32_ok(const kdsb200_geom* h_geom);
 int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
                      const uint32_t* d_guide, int guide_bits, const float* d_bw, double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
                      uint64_t seed, uint64_t first, uint64_t count, int64_t seq_start,

@@ -14,8 +14,13 @@
  *    (kdsource.c:282-330): same marginal distribution, different sequence;
  *  - the non-`rand` functions use counter-based Philox (seed: KDSB200_SEED,
  *    default 0) instead of rand(); the `rand` variants draw ONE number from
- *    the caller's generator per batch to key Philox;
- *  - WeightFun bias callbacks run on the host and are not supported (KDS_error).
+ *    the caller's generator per batch of 65536 particles and mix it into the
+ *    Philox key (the counter is the source's running output index);
+ *  - a WeightFun bias is evaluated once per list entry (on the host); particles
+ *    are then picked with probability ~ w * bias and carry weight 1 / bias, the
+ *    distribution the reference's accept/advance walk samples (kdsource.c:294-325).
+ * The single-particle functions (X_perturb, Geom_perturb, kds_rand_*, PList_get/next,
+ * traslv, rotv) run on the host, as in the reference.
  */
 #ifndef KDSOURCE_COMPAT_H
 #define KDSOURCE_COMPAT_H
@@ -65,6 +70,9 @@ typedef struct PList {
 } PList;
 PList* PList_create(char pt, const char* filename, const double* trasl, const double* rot,
                     int switch_x2z);
+PList* PList_copy(const PList* from);
+int PList_get(const PList* plist, mcpl_particle_t* part);
+int PList_next(PList* plist, int loop);
 void PList_destroy(PList* plist);
 
 /* ---- geom.h:20-97 ---- */
@@ -80,6 +88,7 @@ struct Metric {
 };
 Metric* Metric_create(int dim, const double* scaling, PerturbFun perturb, int nps,
                       const double* params);
+Metric* Metric_copy(const Metric* from);
 void Metric_destroy(Metric* metric);
 typedef struct Geometry {
   int ord;
@@ -92,12 +101,17 @@ typedef struct Geometry {
   double* rot;
   float* bws;         /* extension: per-particle bandwidths (NULL if constant) */
   long long nbws;
+  long long bwpos;    /* extension: position of Geom_next in bws */
 } Geometry;
 Geometry* Geom_create(int ord, Metric** metrics, double bw, const char* bwfilename, char kernel,
                       const double* trasl, const double* rot);
+Geometry* Geom_copy(const Geometry* from);
+int Geom_perturb(kds_rng_fct_t, void* rngstate, const Geometry* geom, mcpl_particle_t* part);
+int Geom_next(Geometry* geom, int loop);
 void Geom_destroy(Geometry* geom);
-/* Metric identity tokens with the reference's names and signature.  They select
- * the device perturbation; calling them directly is not supported. */
+/* The 14 metric perturbations (geom.c:192-650).  The batched sampler identifies a metric
+ * by its function and perturbs on the device; called directly they perturb ONE particle on
+ * the host with the caller's rng, the same templated maps compiled for the host. */
 #define KDS_DECL_PERTURB(name)                                                            \
   int name(kds_rng_fct_t, void* rngstate, const Metric* metric, mcpl_particle_t* part, \
            double bw, char kernel)
@@ -119,7 +133,13 @@ extern const int _n_metrics;
 extern const char* _metric_names[];
 extern const PerturbFun _metric_perturbs[];
 
-/* ---- utils.h:27-31 ---- */
+/* ---- utils.h:22-31 ---- */
+double kds_rand_norm(kds_rng_fct_t, void* rngstate);
+double kds_rand_epan(kds_rng_fct_t, void* rngstate);
+double kds_rand_box(kds_rng_fct_t, void* rngstate);
+double kds_rand_type(kds_rng_fct_t, void* rngstate, char kernel);
+double* traslv(double* vect, const double* trasl, int inverse);
+double* rotv(double* vect, const double* rotvec, int inverse);
 int pt2pdg(char pt);
 char pdg2pt(int pdgcode);
 

@@ -126,7 +126,22 @@ _SIGNATURES = {
     "kdsb200_mlcv_poly_slots": (c_int, [c_int]),
     "kdsb200_mlcv_scores_f32": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_u64, c_u64, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_float_p, c_int, c_int,
-                                        c_void_p, c_void_p, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kdsb200_mlcv_f64_blocks": (c_u64, [c_u64]),
+    "kdsb200_mlcv_f64_gtile": (c_int, [c_int]),
+    "kdsb200_mlcv_coef_f64": (c_int, [c_void_p, c_void_p, c_double, c_u64, c_int, c_double,
+                                      c_void_p, c_void_p]),
+    "kdsb200_mlcv_rows_f64": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_u64, c_u64, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_double_p, c_int, c_double,
+                                      c_void_p, c_void_p, c_void_p]),
+    "kdsb200_mlcv_rows_setup": (c_int, [c_u64, c_u64, c_u64, c_u64, c_u64, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
+    "kdsb200_mlcv_reduce": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_u64, c_int, c_int,
+                                    c_void_p, c_void_p]),
+    "kdsb200_moments_scratch": (c_u64, []),
+    "kdsb200_weighted_moments": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_double_p, c_int,
+                                         c_void_p, c_void_p, c_void_p]),
     "kdsb200_knn": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_int, c_i64, c_int, c_int,
                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kdsb200_cdf_scratch_words": (c_u64, [c_u64]),
@@ -135,6 +150,7 @@ _SIGNATURES = {
     "kdsb200_geom_transform": (c_int, [c_void_p, c_u64, ctypes.POINTER(Geom), c_double_p,
                                        c_double_p, c_void_p, c_void_p, c_void_p]),
     "kdsb200_cdf_guide": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_void_p]),
+    "kdsb200_resample_fp32_ok": (c_int, [ctypes.POINTER(Geom)]),
     "kdsb200_resample": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_double,
                                  c_i64,
                                  ctypes.POINTER(Geom), c_i32, c_u64, c_u64, c_u64, c_i64, c_void_p,

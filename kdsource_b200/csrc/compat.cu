@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "kdsb200.h"
 #include "kdsource_compat.h"
+#include "perturb.cuh"
 
 namespace {
 
@@ -174,8 +175,15 @@ XNode* parse_xml_file(const char* fn) {
 // ---------------------------------------------------------------------------
 struct McplList {
   std::vector<mcpl_particle_t> parts;
+  int refs = 1;  // PList_copy shares the decoded list; every PList has its own cursor
+};
+// what PList.file.internal points to: the list and the read position of this PList
+// (index of the next record mcpl_read would return, plist.c:91-109)
+struct McplCursor {
+  McplList* list;
   uint64_t pos = 0;
 };
+McplList* list_of(const PList* pl) { return ((McplCursor*)pl->file.internal)->list; }
 
 void unpack_dir(double p0, double p1, double sek, double* d) {
   const double sg = signbit(sek) ? -1.0 : 1.0;
@@ -375,6 +383,7 @@ struct Impl {
   std::vector<uint32_t> src_index;       // valid -> index in the raw list
   std::vector<double> w;                 // weights of the valid particles
   void* d_src = nullptr;
+  int src_f32 = 1;
   uint64_t* d_cdf = nullptr;
   uint32_t* d_guide = nullptr;
   int guide_bits = 0;
@@ -389,6 +398,14 @@ struct Impl {
   uint64_t seed = 0, counter = 0;        // Philox key and global output index
   uint64_t cursor = 0;                   // list cursor (sequential mode, w_mean)
   cudaStream_t stream = nullptr;
+  // WeightFun bias (kdsource.c:294-325): the pick follows w_i * bias(part_i); the CDF of
+  // the most recently used bias function is kept
+  WeightFun bias_fn = nullptr;
+  std::vector<double> bias_vals;         // bias(part_i) of the valid particles
+  uint64_t* d_cdf_bias = nullptr;
+  uint32_t* d_guide_bias = nullptr;
+  WeightFun batch_bias = nullptr;        // bias the pending host batch was drawn with
+  std::vector<double> parts8;            // valid particles after PList_get (host copy)
 };
 
 int metric_type_of(PerturbFun f) {
@@ -397,13 +414,15 @@ int metric_type_of(PerturbFun f) {
   kds_error("unknown metric perturbation function");
 }
 
+void build_cdf(Impl* I, const std::vector<double>& w, uint64_t** d_cdf, uint32_t** d_guide);
+
 Impl* ensure_impl(KDSource* kds) {
   if (kds->impl) return (Impl*)kds->impl;
   Impl* I = new Impl;
   PList* pl = kds->plist;
   Geometry* g = kds->geom;
-  McplList* L = (McplList*)pl->file.internal;
-  std::vector<double> parts8;
+  McplList* L = list_of(pl);
+  std::vector<double>& parts8 = I->parts8;
   for (size_t i = 0; i < L->parts.size(); i++) {
     const mcpl_particle_t& p = L->parts[i];
     if (!(p.weight > 0 && p.pdgcode == pl->pdgcode)) continue;  // PList_next plist.c:105
@@ -427,34 +446,6 @@ Impl* ensure_impl(KDSource* kds) {
   }
   I->N = (int64_t)I->w.size();
   if (I->N == 0) kds_error("Error in PList_next: Could not get particle");
-  cu(cudaStreamCreate(&I->stream));
-  void* st = (void*)I->stream;
-  double* d_tmp;
-  cu(cudaMalloc(&d_tmp, parts8.size() * sizeof(double)));
-  cu(cudaMemcpy(d_tmp, parts8.data(), parts8.size() * sizeof(double), cudaMemcpyHostToDevice));
-  cu(cudaMalloc(&I->d_src, (size_t)I->N * 8 * sizeof(float)));
-  cuda_or_die(kdsb200_convert_particles(d_tmp, I->N, 1, I->d_src, st));
-  double sum_w = 0.0;
-  for (double v : I->w) sum_w += v;
-  double* d_w;
-  uint64_t* d_scratch;
-  cu(cudaMalloc(&d_w, (size_t)I->N * sizeof(double)));
-  cu(cudaMemcpy(d_w, I->w.data(), (size_t)I->N * sizeof(double), cudaMemcpyHostToDevice));
-  cu(cudaMalloc(&d_scratch, kdsb200_cdf_scratch_words(I->N) * sizeof(uint64_t)));
-  cu(cudaMalloc(&I->d_cdf, (size_t)I->N * sizeof(uint64_t)));
-  cuda_or_die(kdsb200_weights_cdf(d_w, I->N, sum_w, d_scratch, I->d_cdf, st));
-  I->guide_bits = 4;
-  while (I->guide_bits < 24 && (1ll << I->guide_bits) * 8 < I->N) I->guide_bits++;
-  cu(cudaMalloc(&I->d_guide, ((1ull << I->guide_bits) + 1) * sizeof(uint32_t)));
-  cuda_or_die(kdsb200_cdf_guide(I->d_cdf, I->N, I->guide_bits, I->d_guide, st));
-  if (g->bws) {
-    if (g->nbws != I->N)
-      printf("Warning: Particle list and bandwidths file have different size.\n");
-    std::vector<float> bw((size_t)I->N);
-    for (int64_t i = 0; i < I->N; i++) bw[i] = g->bws[i % g->nbws];  // Geom_next rewinds
-    cu(cudaMalloc(&I->d_bw, (size_t)I->N * sizeof(float)));
-    cu(cudaMemcpy(I->d_bw, bw.data(), (size_t)I->N * sizeof(float), cudaMemcpyHostToDevice));
-  }
   memset(&I->geom, 0, sizeof(I->geom));
   if (g->ord > KDSB200_MAX_METRICS) kds_error("too many metrics in geometry");
   I->geom.order = g->ord;
@@ -474,6 +465,25 @@ Impl* ensure_impl(KDSource* kds) {
     I->geom.trasl[k] = g->trasl ? g->trasl[k] : 0.0;
     I->geom.rot[k] = g->rot ? g->rot[k] : 0.0;
   }
+  cu(cudaStreamCreate(&I->stream));
+  void* st = (void*)I->stream;
+  double* d_tmp;
+  cu(cudaMalloc(&d_tmp, parts8.size() * sizeof(double)));
+  cu(cudaMemcpy(d_tmp, parts8.data(), parts8.size() * sizeof(double), cudaMemcpyHostToDevice));
+  I->src_f32 = kdsb200_resample_fp32_ok(&I->geom);  // else the fp64 store (see kdsb200.h)
+  cu(cudaMalloc(&I->d_src, (size_t)I->N * 8 * (I->src_f32 ? sizeof(float) : sizeof(double))));
+  cuda_or_die(kdsb200_convert_particles(d_tmp, I->N, I->src_f32, I->d_src, st));
+  I->guide_bits = 4;
+  while (I->guide_bits < 24 && (1ll << I->guide_bits) * 8 < I->N) I->guide_bits++;
+  build_cdf(I, I->w, &I->d_cdf, &I->d_guide);
+  if (g->bws) {
+    if (g->nbws != I->N)
+      printf("Warning: Particle list and bandwidths file have different size.\n");
+    std::vector<float> bw((size_t)I->N);
+    for (int64_t i = 0; i < I->N; i++) bw[i] = g->bws[i % g->nbws];  // Geom_next rewinds
+    cu(cudaMalloc(&I->d_bw, (size_t)I->N * sizeof(float)));
+    cu(cudaMemcpy(I->d_bw, bw.data(), (size_t)I->N * sizeof(float), cudaMemcpyHostToDevice));
+  }
   cu(cudaMalloc(&I->d_parts, BATCH * 8 * sizeof(double)));
   cu(cudaMalloc(&I->d_idx, BATCH * sizeof(int64_t)));
   I->h_parts.resize(BATCH * 8);
@@ -482,14 +492,63 @@ Impl* ensure_impl(KDSource* kds) {
   I->seed = e ? strtoull(e, nullptr, 10) : 0;
   cu(cudaStreamSynchronize(I->stream));
   cudaFree(d_tmp);
-  cudaFree(d_w);
-  cudaFree(d_scratch);
   kds->impl = I;
   return I;
 }
 
+// weights -> device CDF + guide table
+void build_cdf(Impl* I, const std::vector<double>& w, uint64_t** d_cdf, uint32_t** d_guide) {
+  void* st = (void*)I->stream;
+  double sum_w = 0.0;
+  for (double v : w) sum_w += v;
+  if (!(sum_w > 0)) kds_error("all particles have zero weight");
+  double* d_w;
+  uint64_t* d_scratch;
+  cu(cudaMalloc(&d_w, (size_t)I->N * sizeof(double)));
+  cu(cudaMemcpy(d_w, w.data(), (size_t)I->N * sizeof(double), cudaMemcpyHostToDevice));
+  cu(cudaMalloc(&d_scratch, kdsb200_cdf_scratch_words(I->N) * sizeof(uint64_t)));
+  if (!*d_cdf) cu(cudaMalloc(d_cdf, (size_t)I->N * sizeof(uint64_t)));
+  cuda_or_die(kdsb200_weights_cdf(d_w, I->N, sum_w, d_scratch, *d_cdf, st));
+  if (!*d_guide) cu(cudaMalloc(d_guide, ((1ull << I->guide_bits) + 1) * sizeof(uint32_t)));
+  cuda_or_die(kdsb200_cdf_guide(*d_cdf, I->N, I->guide_bits, *d_guide, st));
+  cu(cudaStreamSynchronize(I->stream));
+  cudaFree(d_w);
+  cudaFree(d_scratch);
+}
+
+// the particle PList_get would hand out for valid entry i (transformed, with its weight)
+void valid_particle(const KDSource* kds, const Impl* I, int64_t i, mcpl_particle_t* part) {
+  *part = list_of(kds->plist)->parts[I->src_index[i]];
+  const double* o = &I->parts8[(size_t)i * 8];
+  part->ekin = o[0];
+  for (int k = 0; k < 3; k++) {
+    part->position[k] = o[1 + k];
+    part->direction[k] = o[4 + k];
+  }
+  part->time = o[7];
+}
+
+// CDF of w_i * bias(part_i) (the distribution the reference's accept/advance walk with a
+// bias function converges to, kdsource.c:294-321)
+void ensure_bias(KDSource* kds, Impl* I, WeightFun bias) {
+  if (I->bias_fn == bias) return;
+  I->bias_vals.resize((size_t)I->N);
+  std::vector<double> wb((size_t)I->N);
+  mcpl_particle_t part;
+  for (int64_t i = 0; i < I->N; i++) {
+    valid_particle(kds, I, i, &part);
+    const double b = bias(&part);
+    I->bias_vals[i] = b;
+    wb[i] = b > 0 ? I->w[i] * b : 0.0;
+  }
+  build_cdf(I, wb, &I->d_cdf_bias, &I->d_guide_bias);
+  I->bias_fn = bias;
+}
+
 void free_impl(Impl* I) {
   if (!I) return;
+  cudaFree(I->d_cdf_bias);
+  cudaFree(I->d_guide_bias);
   cudaFree(I->d_src);
   cudaFree(I->d_cdf);
   cudaFree(I->d_guide);
@@ -502,19 +561,35 @@ void free_impl(Impl* I) {
 
 double default_rng(void*) { return rand() / (RAND_MAX + 1.0); }  // kdsource.c:37-41
 
-void fill_batch(KDSource* kds, Impl* I, kds_rng_fct_t rng, void* st, int perturb, bool seq) {
-  uint64_t seed = I->seed, first = I->counter;
-  if (rng != default_rng) {  // caller-controlled stream: one draw keys this batch
-    seed = (uint64_t)(rng(st) * 9007199254740992.0);
-    first = 0;
+uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+void fill_batch(KDSource* kds, Impl* I, kds_rng_fct_t rng, void* st, int perturb, bool seq,
+                WeightFun bias) {
+  // Philox counter = global output index of this source (never reused); a caller-supplied
+  // generator contributes one draw per batch to the key
+  uint64_t seed = I->seed;
+  const uint64_t first = I->counter;
+  if (rng != default_rng) {
+    const double u = rng(st);
+    uint64_t bits;
+    memcpy(&bits, &u, sizeof(bits));
+    seed ^= splitmix64(bits);
   }
-  const int64_t seq_start = seq ? (int64_t)(I->cursor % (uint64_t)I->N) - (int64_t)(first % (uint64_t)I->N)
-                                : -1;
+  int64_t seq_start = -1;
+  if (seq) {
+    seq_start = (int64_t)(I->cursor % (uint64_t)I->N) - (int64_t)(first % (uint64_t)I->N);
+    if (seq_start < 0) seq_start += I->N;
+  }
+  const bool biased = bias && !seq;
   cuda_or_die(kdsb200_resample(
-      I->d_src, 1, I->d_cdf, I->d_guide, I->guide_bits, I->d_bw, kds->geom->bw, I->N, &I->geom,
-      kds->plist->pdgcode, seed, first, BATCH,
-      seq ? (seq_start < 0 ? seq_start + I->N : seq_start) : -1, nullptr, 0, perturb, nullptr,
-      I->d_idx, I->d_parts, (void*)I->stream));
+      I->d_src, I->src_f32, biased ? I->d_cdf_bias : I->d_cdf, biased ? I->d_guide_bias : I->d_guide,
+      I->guide_bits, I->d_bw, kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed, first,
+      BATCH, seq_start, nullptr, 0, perturb, nullptr, I->d_idx, I->d_parts, (void*)I->stream));
   cu(cudaMemcpyAsync(I->h_parts.data(), I->d_parts, BATCH * 8 * sizeof(double),
                      cudaMemcpyDeviceToHost, I->stream));
   cu(cudaMemcpyAsync(I->h_idx.data(), I->d_idx, BATCH * sizeof(int64_t), cudaMemcpyDeviceToHost,
@@ -525,6 +600,47 @@ void fill_batch(KDSource* kds, Impl* I, kds_rng_fct_t rng, void* st, int perturb
   I->used = 0;
   I->batch_perturb = perturb;
   I->batch_seq = seq;
+  I->batch_bias = biased ? bias : nullptr;
+}
+
+// uniforms from the caller's generator, for the single-particle host entry points
+struct HostStream {
+  static constexpr bool EXT = true;
+  kds_rng_fct_t rng;
+  void* st;
+  // __host__ __device__ only so that the shared templates compile without warnings;
+  // this stream exists on the host alone
+  __host__ __device__ double ext_next() { return rng(st); }
+  __host__ __device__ int kint() { return 0; }  // Philox-only member, never reached with EXT
+};
+
+// X_perturb on the host (geom.c:192-650): the same templated maps the device sampler
+// runs (perturb.cuh), in fp64, fed by rng(rngstate) one uniform at a time
+int host_perturb(int type, kds_rng_fct_t rng, void* st, const Metric* m, mcpl_particle_t* part,
+                 double bw, char kernel) {
+  kdsb200_metric km;
+  memset(&km, 0, sizeof(km));
+  km.type = type;
+  km.dim = m->dim;
+  for (int k = 0; k < m->dim && k < 6; k++) km.scaling[k] = m->scaling[k];
+  km.nps = m->nps;
+  for (int k = 0; k < m->nps && k < 8; k++) km.params[k] = m->params[k];
+  kdsb::Part<double> p;
+  p.ekin = part->ekin;
+  p.time = part->time;
+  for (int k = 0; k < 3; k++) {
+    p.pos[k] = part->position[k];
+    p.dir[k] = part->direction[k];
+  }
+  HostStream s{rng ? rng : default_rng, st};
+  kdsb::metric_perturb<double, HostStream, -1, false>(s, km, p, bw, kernel);
+  part->ekin = p.ekin;
+  part->time = p.time;
+  for (int k = 0; k < 3; k++) {
+    part->position[k] = p.pos[k];
+    part->direction[k] = p.dir[k];
+  }
+  return 0;
 }
 
 }  // namespace
@@ -539,28 +655,58 @@ const char* _metric_names[] = {"Energy", "Lethargy", "Wavelength", "Vol", "SurfX
                                "SurfR2", "SurfCircle", "Guide", "Isotrop", "Polar", "PolarMu",
                                "Time", "Decade"};
 
-#define KDS_TOKEN(name)                                                                   \
-  int name(kds_rng_fct_t, void*, const Metric*, mcpl_particle_t*, double, char) {         \
-    kds_error(#name ": per-particle perturbation is done on the device; use KDS_sample2"); \
+#define KDS_PERTURB(name, type)                                                           \
+  int name(kds_rng_fct_t rng, void* rngstate, const Metric* metric, mcpl_particle_t* part, \
+           double bw, char kernel) {                                                       \
+    return host_perturb(type, rng, rngstate, metric, part, bw, kernel);                    \
   }
-KDS_TOKEN(E_perturb)
-KDS_TOKEN(Let_perturb)
-KDS_TOKEN(wl_perturb)
-KDS_TOKEN(t_perturb)
-KDS_TOKEN(Dec_perturb)
-KDS_TOKEN(Vol_perturb)
-KDS_TOKEN(SurfXY_perturb)
-KDS_TOKEN(SurfR_perturb)
-KDS_TOKEN(SurfR2_perturb)
-KDS_TOKEN(SurfCircle_perturb)
-KDS_TOKEN(Guide_perturb)
-KDS_TOKEN(Isotrop_perturb)
-KDS_TOKEN(Polar_perturb)
-KDS_TOKEN(PolarMu_perturb)
+KDS_PERTURB(E_perturb, kdsb::M_ENERGY)
+KDS_PERTURB(Let_perturb, kdsb::M_LETHARGY)
+KDS_PERTURB(wl_perturb, kdsb::M_WAVELENGTH)
+KDS_PERTURB(t_perturb, kdsb::M_TIME)
+KDS_PERTURB(Dec_perturb, kdsb::M_DECADE)
+KDS_PERTURB(Vol_perturb, kdsb::M_VOL)
+KDS_PERTURB(SurfXY_perturb, kdsb::M_SURFXY)
+KDS_PERTURB(SurfR_perturb, kdsb::M_SURFR)
+KDS_PERTURB(SurfR2_perturb, kdsb::M_SURFR2)
+KDS_PERTURB(SurfCircle_perturb, kdsb::M_SURFCIRCLE)
+KDS_PERTURB(Guide_perturb, kdsb::M_GUIDE)
+KDS_PERTURB(Isotrop_perturb, kdsb::M_ISOTROP)
+KDS_PERTURB(Polar_perturb, kdsb::M_POLAR)
+KDS_PERTURB(PolarMu_perturb, kdsb::M_POLARMU)
 const PerturbFun _metric_perturbs[] = {
     E_perturb, Let_perturb, wl_perturb, Vol_perturb, SurfXY_perturb, SurfR_perturb,
     SurfR2_perturb, SurfCircle_perturb, Guide_perturb, Isotrop_perturb, Polar_perturb,
     PolarMu_perturb, t_perturb, Dec_perturb};
+
+// ---- utils.c:25-103 ------------------------------------------------------------
+double kds_rand_norm(kds_rng_fct_t rng, void* rngstate) {
+  HostStream s{rng ? rng : default_rng, rngstate};
+  return kdsb::rand_norm<double, HostStream, false>(s);
+}
+double kds_rand_epan(kds_rng_fct_t rng, void* rngstate) {
+  HostStream s{rng ? rng : default_rng, rngstate};
+  return kdsb::rand_epan<double, HostStream>(s);
+}
+double kds_rand_box(kds_rng_fct_t rng, void* rngstate) {
+  return (rng ? rng : default_rng)(rngstate) * 2.0 - 1.0;
+}
+double kds_rand_type(kds_rng_fct_t rng, void* rngstate, char kernel) {
+  if (kernel != 'g' && kernel != 'e' && kernel != 'b') {
+    printf("Cannot perturbate with current kernel. \n");
+    return 0;
+  }
+  HostStream s{rng ? rng : default_rng, rngstate};
+  return kdsb::rand_type<double, HostStream, false>(s, kernel);
+}
+double* traslv(double* vect, const double* trasl, int inverse) {
+  for (int i = 0; i < 3; i++) vect[i] += inverse ? -trasl[i] : trasl[i];
+  return vect;
+}
+double* rotv(double* vect, const double* rotvec, int inverse) {
+  kdsb::rotv<double>(vect, rotvec, inverse);
+  return vect;
+}
 
 int pt2pdg(char pt) { return pt == 'n' ? 2112 : pt == 'p' ? 22 : pt == 'e' ? 11 : 0; }
 char pdg2pt(int pdg) { return pdg == 2112 ? 'n' : pdg == 22 ? 'p' : pdg == 11 ? 'e' : '0'; }
@@ -571,28 +717,82 @@ PList* PList_create(char pt, const char* filename, const double* trasl, const do
   PList* pl = (PList*)calloc(1, sizeof(PList));
   pl->pt = pt;
   pl->pdgcode = pt2pdg(pt);
-  McplList* L = mcpl_load(filename);
-  pl->npts = (long long)L->parts.size();
+  McplCursor* c = new McplCursor;
+  c->list = mcpl_load(filename);
+  pl->npts = (long long)c->list->parts.size();
   pl->filename = (char*)malloc(NAME_MAX_LEN);
   strncpy(pl->filename, filename, NAME_MAX_LEN - 1);
   pl->filename[NAME_MAX_LEN - 1] = 0;
-  pl->file.internal = L;
+  pl->file.internal = c;
   pl->trasl = dup3(trasl);
   pl->rot = dup3(rot);
   pl->x2z = switch_x2z;
   pl->part = nullptr;
-  for (auto& p : L->parts)
-    if (p.weight > 0 && p.pdgcode == pl->pdgcode) {
-      pl->part = &p;
-      break;
-    }
-  if (!pl->part) kds_error("Error in PList_next: Could not get particle");
+  PList_next(pl, 1);
   return pl;
+}
+
+PList* PList_copy(const PList* from) {  // plist.c:47-67: same file, its own cursor
+  PList* pl = (PList*)calloc(1, sizeof(PList));
+  *pl = *from;
+  pl->filename = (char*)malloc(NAME_MAX_LEN);
+  strncpy(pl->filename, from->filename, NAME_MAX_LEN - 1);
+  pl->filename[NAME_MAX_LEN - 1] = 0;
+  McplCursor* c = new McplCursor;
+  c->list = list_of(from);
+  c->list->refs++;
+  pl->file.internal = c;
+  pl->trasl = dup3(from->trasl);
+  pl->rot = dup3(from->rot);
+  pl->part = nullptr;
+  PList_next(pl, 1);
+  return pl;
+}
+
+int PList_get(const PList* plist, mcpl_particle_t* part) {  // plist.c:69-89
+  *part = *plist->part;
+  if (plist->trasl) traslv(part->position, plist->trasl, 0);
+  if (plist->rot) {
+    rotv(part->position, plist->rot, 0);
+    rotv(part->direction, plist->rot, 0);
+  }
+  if (plist->x2z) {
+    const double x = part->position[0], y = part->position[1], z = part->position[2];
+    part->position[0] = y;
+    part->position[1] = z;
+    part->position[2] = x;
+    const double dx = part->direction[0], dy = part->direction[1], dz = part->direction[2];
+    part->direction[0] = dy;
+    part->direction[1] = dz;
+    part->direction[2] = dx;
+  }
+  return 0;
+}
+
+int PList_next(PList* plist, int loop) {  // plist.c:91-109
+  McplCursor* c = (McplCursor*)plist->file.internal;
+  const std::vector<mcpl_particle_t>& parts = c->list->parts;
+  int ret = 0, resamples = 0;
+  while (resamples++ < MAX_RESAMPLES) {
+    if (c->pos >= parts.size()) {  // end of file: rewind
+      if (!loop) kds_end("PList_next: End of particle list reached.");
+      ret = 1;
+      c->pos = 0;
+      if (parts.empty()) kds_error("Error in PList_next: Could not get particle");
+    }
+    plist->part = &parts[c->pos++];
+    if (plist->part->weight > 0 && plist->part->pdgcode == plist->pdgcode) return ret;
+  }
+  kds_error("Error in PList_next: MAX_RESAMPLES reached.");
 }
 
 void PList_destroy(PList* pl) {
   if (!pl) return;
-  delete (McplList*)pl->file.internal;
+  McplCursor* c = (McplCursor*)pl->file.internal;
+  if (c) {
+    if (--c->list->refs == 0) delete c->list;
+    delete c;
+  }
   free(pl->filename);
   free(pl->trasl);
   free(pl->rot);
@@ -611,6 +811,16 @@ Metric* Metric_create(int dim, const double* scaling, PerturbFun perturb, int np
   m->nps = nps;
   m->params = (double*)calloc(nps ? nps : 1, sizeof(double));
   for (int i = 0; i < nps; i++) m->params[i] = params[i];
+  return m;
+}
+
+Metric* Metric_copy(const Metric* from) {  // geom.c:50-61
+  Metric* m = (Metric*)calloc(1, sizeof(Metric));
+  *m = *from;
+  m->scaling = (float*)calloc(from->dim ? from->dim : 1, sizeof(float));
+  for (int i = 0; i < from->dim; i++) m->scaling[i] = from->scaling[i];
+  m->params = (double*)calloc(from->nps ? from->nps : 1, sizeof(double));
+  for (int i = 0; i < from->nps; i++) m->params[i] = from->params[i];
   return m;
 }
 
@@ -647,11 +857,65 @@ Geometry* Geom_create(int ord, Metric** metrics, double bw, const char* bwfilena
     g->bwfilename = (char*)malloc(NAME_MAX_LEN);
     strncpy(g->bwfilename, bwfilename, NAME_MAX_LEN - 1);
     g->bwfilename[NAME_MAX_LEN - 1] = 0;
-    g->bw = g->bws[0];
+    Geom_next(g, 1);  // geom.c:96: the first bandwidth is read at creation
   }
   g->trasl = dup3(trasl);
   g->rot = dup3(rot);
   return g;
+}
+
+// geom.c:108-137.  The reference's copy loses a variable bandwidth (it tests the file
+// handle it has just cleared); here the copy keeps the bandwidth list and restarts it.
+Geometry* Geom_copy(const Geometry* from) {
+  Geometry* g = (Geometry*)calloc(1, sizeof(Geometry));
+  *g = *from;
+  g->ms = (Metric**)calloc(from->ord > 0 ? from->ord : 1, sizeof(Metric*));
+  for (int i = 0; i < from->ord; i++) g->ms[i] = Metric_copy(from->ms[i]);
+  g->bwfilename = nullptr;
+  g->bwfile = nullptr;
+  g->bws = nullptr;
+  g->bwpos = 0;
+  if (from->bws) {
+    g->bws = (float*)malloc((size_t)from->nbws * sizeof(float));
+    memcpy(g->bws, from->bws, (size_t)from->nbws * sizeof(float));
+    g->bwfilename = (char*)malloc(NAME_MAX_LEN);
+    memcpy(g->bwfilename, from->bwfilename, NAME_MAX_LEN);
+    Geom_next(g, 1);
+  }
+  g->trasl = dup3(from->trasl);
+  g->rot = dup3(from->rot);
+  return g;
+}
+
+int Geom_perturb(kds_rng_fct_t rng, void* rngstate, const Geometry* geom,
+                 mcpl_particle_t* part) {  // geom.c:139-158
+  int ret = 0;
+  if (geom->trasl) traslv(part->position, geom->trasl, 1);
+  if (geom->rot) {
+    rotv(part->position, geom->rot, 1);
+    rotv(part->direction, geom->rot, 1);
+  }
+  for (int i = 0; i < geom->ord; i++)
+    ret += geom->ms[i]->perturb(rng, rngstate, geom->ms[i], part, geom->bw, geom->kernel);
+  if (geom->rot) {
+    rotv(part->position, geom->rot, 0);
+    rotv(part->direction, geom->rot, 0);
+  }
+  if (geom->trasl) traslv(part->position, geom->trasl, 0);
+  return ret;
+}
+
+// geom.c:160-177: next bandwidth of the variable-bandwidth list (loaded at creation)
+int Geom_next(Geometry* geom, int loop) {
+  if (!geom->bws) return 0;
+  if (geom->bwpos < geom->nbws) {
+    geom->bw = geom->bws[geom->bwpos++];
+    return 0;
+  }
+  if (!loop) kds_end("Geom_next: End of BW file reached.");
+  geom->bwpos = 0;
+  geom->bw = geom->bws[geom->bwpos++];
+  return 1;
 }
 
 void Geom_destroy(Geometry* g) {
@@ -793,18 +1057,20 @@ KDSource* KDS_open(const char* xmlfilename) {
 
 int KDS_rand_sample2(kds_rng_fct_t rng, void* rngstate, KDSource* kds, mcpl_particle_t* part,
                      int perturb, double w_crit, WeightFun bias, int loop) {
-  if (bias) kds_error("bias functions are not supported by the GPU sampler");
   Impl* I = ensure_impl(kds);
   const bool seq = !(w_crit > 0);
+  if (seq) bias = nullptr;  // the list walk ignores the bias (kdsource.c:286-292)
   perturb = perturb ? 1 : 0;
   if (seq && !loop && I->cursor >= (uint64_t)I->N)
     kds_end("PList_next: End of particle list reached.");
-  if (I->used >= I->have || I->batch_perturb != perturb || I->batch_seq != (int)seq)
-    fill_batch(kds, I, rng ? rng : default_rng, rngstate, perturb, seq);
+  if (bias) ensure_bias(kds, I, bias);
+  if (I->used >= I->have || I->batch_perturb != perturb || I->batch_seq != (int)seq ||
+      I->batch_bias != bias)
+    fill_batch(kds, I, rng ? rng : default_rng, rngstate, perturb, seq, bias);
   const uint64_t b = I->used++;
   const int64_t idx = I->h_idx[b];
   const double* o = &I->h_parts[b * 8];
-  const McplList* L = (const McplList*)kds->plist->file.internal;
+  const McplList* L = list_of(kds->plist);
   *part = L->parts[I->src_index[idx]];  // polarisation, userflags, pdgcode of the source entry
   part->ekin = o[0];
   for (int k = 0; k < 3; k++) {
@@ -818,7 +1084,8 @@ int KDS_rand_sample2(kds_rng_fct_t rng, void* rngstate, KDSource* kds, mcpl_part
     I->cursor++;
     if (I->cursor % (uint64_t)I->N == 0 && loop) ret = 1;
   } else {
-    part->weight = 1.0;  // 1/bias with bias == NULL (kdsource.c:325)
+    // particles are picked with probability ~ w * bias and carry 1 / bias (kdsource.c:325)
+    part->weight = bias ? 1.0 / I->bias_vals[idx] : 1.0;
   }
   return ret;
 }
@@ -836,12 +1103,22 @@ int KDS_sample(KDSource* kds, mcpl_particle_t* part) {
   return KDS_rand_sample(default_rng, nullptr, kds, part);
 }
 
-// mean weight of the next N list entries; advances the list cursor (kdsource.c:353-367)
+// mean of w (times bias) over the next N list entries; advances the list cursor
+// (kdsource.c:353-367)
 double KDS_rand_w_mean(kds_rng_fct_t, void*, KDSource* kds, int N, WeightFun bias) {
-  if (bias) kds_error("bias functions are not supported by the GPU sampler");
   Impl* I = ensure_impl(kds);
   double s = 0;
-  for (int i = 0; i < N; i++) s += I->w[(I->cursor + (uint64_t)i) % (uint64_t)I->N];
+  mcpl_particle_t part;
+  for (int i = 0; i < N; i++) {
+    const int64_t j = (int64_t)((I->cursor + (uint64_t)i) % (uint64_t)I->N);
+    if (bias) {
+      valid_particle(kds, I, j, &part);
+      part.weight = I->w[j];
+      s += I->w[j] * bias(&part);
+    } else {
+      s += I->w[j];
+    }
+  }
   I->cursor += (uint64_t)(N > 0 ? N : 0);
   I->have = I->used = 0;  // a pending sequential batch no longer matches the cursor
   return N > 0 ? s / N : 0.0;
@@ -954,7 +1231,7 @@ void kdsource_resample_to_mcpl(double (*rng_stateless)(void), const char* kds_so
   cu(cudaMalloc(&d_rec, B * 36));
   for (uint64_t first = 0; first < nout; first += B) {
     const uint64_t n = nout - first < B ? nout - first : B;
-    cuda_or_die(kdsb200_resample(I->d_src, 1, I->d_cdf, I->d_guide, I->guide_bits, I->d_bw,
+    cuda_or_die(kdsb200_resample(I->d_src, I->src_f32, I->d_cdf, I->d_guide, I->guide_bits, I->d_bw,
                                  kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed, first,
                                  n, -1, nullptr, 0, 1, d_rec, nullptr, nullptr, (void*)I->stream));
     cuda_or_die(kdsb200_gz_writer_put_device(w, d_rec, n * 36));

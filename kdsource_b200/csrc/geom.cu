@@ -144,9 +144,90 @@ __global__ void __launch_bounds__(256)
   if (jac) jac[m] = J;
 }
 
+// ---------------------------------------------------------------------------
+// weighted column moments (Metric.mean / Metric.std, python/kdsource/geom.py:61-70,
+// and N_eff = (sum w)^2 / sum w^2, plist.py:349-395) on the device
+// ---------------------------------------------------------------------------
+constexpr int MOM_BLOCKS = 592;  // 4 per SM on 148 SMs; fixed, so the sums are reproducible
+constexpr int MOM_THREADS = 256;
+
+struct MomCenter {
+  double c[8];
+};
+
+__global__ void __launch_bounds__(MOM_THREADS)
+    moments_partial_kernel(const double* __restrict__ vecs, const double* __restrict__ w,
+                           uint64_t N, int D, MomCenter cen, int power,
+                           double* __restrict__ scratch) {
+  double acc[10];
+#pragma unroll
+  for (int k = 0; k < 10; k++) acc[k] = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * MOM_THREADS + threadIdx.x; i < N;
+       i += (uint64_t)MOM_BLOCKS * MOM_THREADS) {
+    const double wi = w ? w[i] : 1.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < D) {
+        const double d = vecs[i * D + k] - cen.c[k];
+        acc[k] += wi * (power == 2 ? d * d : d);
+      }
+    acc[8] += wi;
+    acc[9] += wi * wi;
+  }
+  __shared__ double sm[10][MOM_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 10; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) sm[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    double t = 0.0;
+#pragma unroll
+    for (int e = 0; e < MOM_THREADS / 32; e++) t += sm[threadIdx.x][e];
+    scratch[blockIdx.x * 10 + threadIdx.x] = t;
+  }
+}
+
+__global__ void moments_final_kernel(const double* __restrict__ scratch, int D,
+                                     double* __restrict__ out) {
+  // thread k sums column k of the per-block partials in block order
+  const int k = threadIdx.x;
+  if (k >= 10) return;
+  double t = 0.0;
+  for (int b = 0; b < MOM_BLOCKS; b++) t += scratch[b * 10 + k];
+  if (k < D) out[k] = t;
+  if (k == 8) out[D] = t;
+  if (k == 9) out[D + 1] = t;
+}
+
 }  // namespace kdsb
 
 using namespace kdsb;
+
+extern "C" uint64_t kdsb200_moments_scratch(void) { return (uint64_t)MOM_BLOCKS * 10; }
+
+extern "C" int kdsb200_weighted_moments(const double* d_vecs, const double* d_w, uint64_t N, int D,
+                                        const double* h_center, int power, double* d_scratch,
+                                        double* d_out, void* stream) {
+  if (D < 1 || D > 8 || (power != 1 && power != 2)) {
+    set_error("weighted_moments: D=%d (1..8) power=%d (1|2)", D, power);
+    return 1;
+  }
+  MomCenter cen;
+  for (int k = 0; k < 8; k++) cen.c[k] = (h_center && k < D) ? h_center[k] : 0.0;
+  cudaStream_t st = (cudaStream_t)stream;
+  moments_partial_kernel<<<MOM_BLOCKS, MOM_THREADS, 0, st>>>(d_vecs, d_w, N, D, cen, power,
+                                                             d_scratch);
+  KDSB_CUDA(cudaGetLastError());
+  moments_final_kernel<<<1, 32, 0, st>>>(d_scratch, D, d_out);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 
 extern "C" int kdsb200_geom_transform(const double* d_parts, uint64_t M,
                                       const struct kdsb200_geom_s* h_geom,

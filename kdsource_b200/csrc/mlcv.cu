@@ -25,6 +25,13 @@ namespace kdsb {
 
 constexpr int CV_THREADS = 256;
 constexpr int CV_STAGES = 3;
+// ex2.approx.ftz returns 0 below 2^-126, so a test point whose nearest training source
+// is 13 < r/h < 38 bandwidths away gets a sum that is too small or zero, where fp64
+// (the reference) still has a finite logarithm.  The coefficients are scaled so that
+// the largest is 1 and at most 2^31 terms of < 2^-126 can have been lost, hence a sum
+// above 2^-70 is accurate to 2^-25; anything below is flagged (bit g of flagmask[row])
+// and recomputed in fp64 by mlcv_rows_f64_kernel.
+constexpr double CV_FLAG_BELOW = 8.470329472543003e-22;  // 2^-70
 
 template <int GT>
 struct NkParams {
@@ -62,8 +69,8 @@ __global__ void __launch_bounds__(CV_THREADS, 2)
                       const float* __restrict__ qT, uint64_t M, uint64_t Mpad,
                       const int32_t* __restrict__ excl_lo, const int32_t* __restrict__ excl_hi,
                       const double* __restrict__ coefw, const double* __restrict__ lwtr,
-                      NkParams<GT> P, int fused, double* __restrict__ sbuf,
-                      double* __restrict__ partial) {
+                      NkParams<GT> P, int G, int fused, double* __restrict__ sbuf,
+                      double* __restrict__ partial, uint32_t* __restrict__ flagmask) {
   constexpr int ROWS = D + 2;
   constexpr int TILE_FLOATS = ROWS * TS;
   constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
@@ -192,11 +199,15 @@ __global__ void __launch_bounds__(CV_THREADS, 2)
   }
   const bool live = m < M;
   const double cw = live ? coefw[m] : 0.0, lw = live ? lwtr[m] : 0.0;
+  uint32_t mask = 0;
 #pragma unroll
   for (int g = 0; g < GT; g++) {
     const double Sg = S2[g * CV_THREADS + tid];
-    S2[g * CV_THREADS + tid] = live ? cw * (log(Sg) - lw) : 0.0;
+    const bool bad = flagmask && live && g < G && !(Sg >= CV_FLAG_BELOW);
+    if (bad) mask |= 1u << g;
+    S2[g * CV_THREADS + tid] = (live && !bad) ? cw * (log(Sg) - lw) : 0.0;
   }
+  if (flagmask) flagmask[m] = mask;
   __syncthreads();
   block_reduce_store<GT>(S2, partial + (uint64_t)blockIdx.x * GT);
 }
@@ -204,21 +215,201 @@ __global__ void __launch_bounds__(CV_THREADS, 2)
 template <int GT>
 __global__ void __launch_bounds__(CV_THREADS)
     mlcv_finalize_kernel(const double* __restrict__ sbuf, int nsplit, uint64_t M, uint64_t Mpad,
-                         const double* __restrict__ coefw, const double* __restrict__ lwtr,
-                         double* __restrict__ partial) {
+                         const double* __restrict__ coefw, const double* __restrict__ lwtr, int G,
+                         double* __restrict__ partial, uint32_t* __restrict__ flagmask) {
   extern __shared__ __align__(16) unsigned char fin_raw[];
   double* S2 = reinterpret_cast<double*>(fin_raw);
   const int tid = threadIdx.x;
   const uint64_t m = (uint64_t)blockIdx.x * CV_THREADS + tid;
   const bool live = m < M;
   const double cw = live ? coefw[m] : 0.0, lw = live ? lwtr[m] : 0.0;
+  uint32_t mask = 0;
   for (int g = 0; g < GT; g++) {
     double s = 0.0;
     for (int p = 0; p < nsplit; p++) s += sbuf[((uint64_t)p * Mpad + m) * GT + g];
-    S2[g * CV_THREADS + tid] = live ? cw * (log(s) - lw) : 0.0;
+    const bool bad = flagmask && live && g < G && !(s >= CV_FLAG_BELOW);
+    if (bad) mask |= 1u << g;
+    S2[g * CV_THREADS + tid] = (live && !bad) ? cw * (log(s) - lw) : 0.0;
   }
+  if (flagmask) flagmask[m] = mask;
   __syncthreads();
   block_reduce_store<GT>(S2, partial + (uint64_t)blockIdx.x * GT);
+}
+
+// ---------------------------------------------------------------------------
+// fp64 rows: the 1e-12 mode of the search, and the recomputation of the rows the fp32
+// kernel flagged.  One warp per test row (lanes stride over the sources, G fp64
+// accumulators per lane, fixed-order shuffle reduction), 8 rows per CTA sharing the
+// source tiles staged in shared memory.  rowmask == NULL: every row, every g;
+// otherwise only the (row, g) pairs whose bit is set contribute (the others add 0).
+// ---------------------------------------------------------------------------
+constexpr int R64_WARPS = 8;
+constexpr int R64_THREADS = R64_WARPS * 32;
+constexpr int R64_TILE = 128;
+
+template <int GT>
+struct GridParams {
+  double inv_g2[GT];  // 1 / grid[g]^2
+};
+
+template <int D, int GT>
+__global__ void __launch_bounds__(R64_THREADS)
+    mlcv_rows_f64_kernel(const double* __restrict__ data, const double* __restrict__ coef,
+                         const double* __restrict__ ih2, uint64_t N, uint64_t row0, uint64_t M,
+                         const int32_t* __restrict__ excl_lo, const int32_t* __restrict__ excl_hi,
+                         const double* __restrict__ coefw, const double* __restrict__ lwtr,
+                         GridParams<GT> P, int G, double log_shift,
+                         const uint32_t* __restrict__ rowmask, double* __restrict__ partial) {
+  __shared__ double sx[D * R64_TILE];
+  __shared__ double sc[R64_TILE];
+  __shared__ double sh[R64_TILE];
+  __shared__ double contrib[R64_WARPS][GT];
+  __shared__ int any_live;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t m = (uint64_t)blockIdx.x * R64_WARPS + warp;
+  uint32_t mask = 0;
+  if (m < M) mask = rowmask ? rowmask[m] : 0xffffffffu;
+  if (G < 32) mask &= (1u << G) - 1u;
+  if (threadIdx.x == 0) any_live = 0;
+  __syncthreads();
+  if (mask && lane == 0) any_live = 1;
+  __syncthreads();
+  if (!any_live) {  // CTA-uniform: nothing flagged among these rows
+    if (threadIdx.x < GT) partial[(uint64_t)blockIdx.x * GT + threadIdx.x] = 0.0;
+    return;
+  }
+  double q[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) q[k] = mask ? data[(row0 + m) * D + k] : 0.0;
+  const int64_t lo = mask ? excl_lo[m] : 0, hi = mask ? excl_hi[m] : 0;
+  double acc[GT];
+#pragma unroll
+  for (int g = 0; g < GT; g++) acc[g] = 0.0;
+
+  for (uint64_t base = 0; base < N; base += R64_TILE) {
+    const int cnt = (int)min((uint64_t)R64_TILE, N - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < cnt * D; e += R64_THREADS)
+      sx[(e % D) * R64_TILE + e / D] = data[base * D + e];
+    for (int e = threadIdx.x; e < cnt; e += R64_THREADS) {
+      sc[e] = coef[base + e];
+      sh[e] = ih2[base + e];
+    }
+    __syncthreads();
+    if (!mask) continue;
+    for (int j = lane; j < cnt; j += 32) {
+      const int64_t gj = (int64_t)(base + j);
+      if (gj >= lo && gj < hi) continue;  // the row's own fold
+      double r2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; k++) {
+        const double t = q[k] - sx[k * R64_TILE + j];
+        r2 += t * t;
+      }
+      const double u = r2 * sh[j], c = sc[j];
+#pragma unroll
+      for (int g = 0; g < GT; g++)
+        if (g < G) acc[g] += c * exp(-u * P.inv_g2[g]);
+    }
+  }
+  const double cw = mask ? coefw[m] : 0.0, lw = mask ? lwtr[m] : 0.0;
+#pragma unroll
+  for (int g = 0; g < GT; g++) {
+    double v = acc[g];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) contrib[warp][g] = ((mask >> g) & 1u) ? cw * (log(v) + log_shift - lw) : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < GT) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < R64_WARPS; w++) t += contrib[w][threadIdx.x];
+    partial[(uint64_t)blockIdx.x * GT + threadIdx.x] = t;
+  }
+}
+
+// coef_j = w_j * w_scale * h_j^-D, ih2_j = 1 / (2 h_j^2)
+__global__ void mlcv_coef_f64_kernel(const double* __restrict__ w, const double* __restrict__ bw,
+                                     double bw_scalar, uint64_t N, int D, double w_scale,
+                                     double* __restrict__ coef, double* __restrict__ ih2) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double h = bw ? bw[i] : bw_scalar;
+  coef[i] = (w ? w[i] : 1.0) * w_scale * exp(-D * log(h));
+  ih2[i] = 0.5 / (h * h);
+}
+
+// lo/hi: fold interval of each test row; coefw = w_i * cwf[f] (cwf[f] = 1/(n_f K));
+// lwtr = lwt[f] (log of the training weight of fold f).  Padding rows get an empty
+// interval and zero coefficient.
+__global__ void mlcv_rows_setup_kernel(uint64_t N, uint64_t K, uint64_t row0, uint64_t M,
+                                       uint64_t Mpad, const double* __restrict__ w,
+                                       const double* __restrict__ cwf,
+                                       const double* __restrict__ lwt, int32_t* __restrict__ lo,
+                                       int32_t* __restrict__ hi, double* __restrict__ coefw,
+                                       double* __restrict__ lwtr) {
+  const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mpad) return;
+  if (m >= M) {
+    lo[m] = 0;
+    hi[m] = 0;
+    coefw[m] = 0.0;
+    lwtr[m] = 0.0;
+    return;
+  }
+  const uint64_t i = row0 + m, base = N / K, big = N % K, cut = big * (base + 1);
+  uint64_t f, a;
+  if (i < cut) {
+    f = i / (base + 1);
+    a = f * (base + 1);
+    lo[m] = (int32_t)a;
+    hi[m] = (int32_t)(a + base + 1);
+  } else {
+    f = big + (i - cut) / base;
+    a = cut + (f - big) * base;
+    lo[m] = (int32_t)a;
+    hi[m] = (int32_t)(a + base);
+  }
+  coefw[m] = (w ? w[i] : 1.0) * cwf[f];
+  lwtr[m] = lwt[f];
+}
+
+// out[g] = sum over the rows of a[na][gt_a] and b[nb][gt_b], g < G, in a fixed order (one CTA)
+__global__ void __launch_bounds__(256)
+    mlcv_reduce_kernel(const double* __restrict__ a, uint64_t na, int gt_a,
+                       const double* __restrict__ b, uint64_t nb, int gt_b, int G,
+                       double* __restrict__ out) {
+  __shared__ double sm[256];
+  for (int g = 0; g < G; g++) {
+    double s = 0.0;
+    for (uint64_t r = threadIdx.x; r < na; r += 256) s += a[r * gt_a + g];
+    if (b)
+      for (uint64_t r = threadIdx.x; r < nb; r += 256) s += b[r * gt_b + g];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[g] = sm[0];
+    __syncthreads();
+  }
+}
+
+template <int D, int GT>
+static int launch_rows_f64(const double* data, const double* coef, const double* ih2, uint64_t N,
+                           uint64_t row0, uint64_t M, const int32_t* lo, const int32_t* hi,
+                           const double* coefw, const double* lwtr, const double* h_grid, int G,
+                           double log_shift, const uint32_t* rowmask, double* partial,
+                           cudaStream_t st) {
+  GridParams<GT> P;
+  for (int g = 0; g < GT; g++) P.inv_g2[g] = g < G ? 1.0 / (h_grid[g] * h_grid[g]) : 0.0;
+  const unsigned blocks = (unsigned)((M + R64_WARPS - 1) / R64_WARPS);
+  mlcv_rows_f64_kernel<D, GT><<<blocks, R64_THREADS, 0, st>>>(
+      data, coef, ih2, N, row0, M, lo, hi, coefw, lwtr, P, G, log_shift, rowmask, partial);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 static int poly_mode() {
@@ -235,7 +426,8 @@ template <int D, int GT, int PM>
 static int launch_mlcv(const float* packed, uint32_t ntl, uint32_t tps, int nsplit,
                        const float* qT, uint64_t M, uint64_t Mpad, const int32_t* lo,
                        const int32_t* hi, const double* coefw, const double* lwtr,
-                       const float* h_nk, int G, double* sbuf, double* partial, cudaStream_t st) {
+                       const float* h_nk, int G, double* sbuf, double* partial, uint32_t* flagmask,
+                       cudaStream_t st) {
   NkParams<GT> P;
   for (int g = 0; g < GT; g++) P.nk[g] = g < G ? h_nk[g] : -1e30f;  // unused slots -> 2^-inf = 0
   const size_t smem = (size_t)CV_STAGES * (D + 2) * TS * sizeof(float) +
@@ -245,26 +437,27 @@ static int launch_mlcv(const float* packed, uint32_t ntl, uint32_t tps, int nspl
   dim3 grid((unsigned)(Mpad / CV_THREADS), (unsigned)nsplit);
   const int fused = nsplit == 1;
   mlcv_pairs_kernel<D, GT, PM><<<grid, CV_THREADS, smem, st>>>(
-      packed, ntl, tps, qT, M, Mpad, lo, hi, coefw, lwtr, P, fused, sbuf, partial);
+      packed, ntl, tps, qT, M, Mpad, lo, hi, coefw, lwtr, P, G, fused, sbuf, partial, flagmask);
   KDSB_CUDA(cudaGetLastError());
   if (!fused) {
     const size_t fsm = (size_t)GT * CV_THREADS * sizeof(double);
     KDSB_CUDA(cudaFuncSetAttribute(mlcv_finalize_kernel<GT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
     mlcv_finalize_kernel<GT><<<(unsigned)(Mpad / CV_THREADS), CV_THREADS, fsm, st>>>(
-        sbuf, nsplit, M, Mpad, coefw, lwtr, partial);
+        sbuf, nsplit, M, Mpad, coefw, lwtr, G, partial, flagmask);
     KDSB_CUDA(cudaGetLastError());
   }
   return 0;
 }
 
-#define KDSB_MLCV_ARGS packed, ntl, tps, nsplit, qT, M, Mpad, lo, hi, coefw, lwtr, h_nk, G, sbuf, partial, st
+#define KDSB_MLCV_ARGS packed, ntl, tps, nsplit, qT, M, Mpad, lo, hi, coefw, lwtr, h_nk, G, sbuf, partial, flagmask, st
 
 template <int D>
 static int dispatch_gt(int GT, const float* packed, uint32_t ntl, uint32_t tps, int nsplit,
                        const float* qT, uint64_t M, uint64_t Mpad, const int32_t* lo,
                        const int32_t* hi, const double* coefw, const double* lwtr,
-                       const float* h_nk, int G, double* sbuf, double* partial, cudaStream_t st) {
+                       const float* h_nk, int G, double* sbuf, double* partial, uint32_t* flagmask,
+                       cudaStream_t st) {
   const int pm = poly_mode();
   switch (GT) {
     case 8:
@@ -353,7 +546,8 @@ int kdsb200_mlcv_scores_f32(const float* d_packed, uint64_t N, int D, const floa
                             uint64_t M, uint64_t Mpad, const int32_t* d_excl_lo,
                             const int32_t* d_excl_hi, const double* d_coefw,
                             const double* d_lwtr, const float* h_nk, int G, int nsplit,
-                            double* d_sbuf, double* d_partial, void* stream) {
+                            double* d_sbuf, double* d_partial, uint32_t* d_flagmask,
+                            void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) return 0;
   if (G < 1 || G > 32) {
@@ -382,7 +576,7 @@ int kdsb200_mlcv_scores_f32(const float* d_packed, uint64_t N, int D, const floa
 #define KDSB_CASE(d)                                                                          \
   case d:                                                                                     \
     return dispatch_gt<d>(GT, d_packed, ntl, tps, nsplit, d_qT, M, Mpad, d_excl_lo, d_excl_hi, \
-                          d_coefw, d_lwtr, h_nk, G, d_sbuf, d_partial, st);
+                          d_coefw, d_lwtr, h_nk, G, d_sbuf, d_partial, d_flagmask, st);
     KDSB_CASE(1)
     KDSB_CASE(2)
     KDSB_CASE(3)
@@ -395,6 +589,90 @@ int kdsb200_mlcv_scores_f32(const float* d_packed, uint64_t N, int D, const floa
   }
   set_error("mlcv: D=%d out of range 1..8", D);
   return 1;
+}
+
+uint64_t kdsb200_mlcv_f64_blocks(uint64_t M) { return (M + R64_WARPS - 1) / R64_WARPS; }
+
+int kdsb200_mlcv_coef_f64(const double* d_w, const double* d_bw, double bw_scalar, uint64_t N,
+                          int D, double w_scale, double* d_coef2n, void* stream) {
+  if (N == 0) return 0;
+  mlcv_coef_f64_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_w, d_bw, bw_scalar, N, D, w_scale, d_coef2n, d_coef2n + N);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kdsb200_mlcv_rows_f64(const double* d_data, const double* d_coef2n, uint64_t N, int D,
+                          uint64_t row0, uint64_t M, const int32_t* d_excl_lo,
+                          const int32_t* d_excl_hi, const double* d_coefw, const double* d_lwtr,
+                          const double* h_grid, int G, double log_shift,
+                          const uint32_t* d_rowmask, double* d_partial, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0 || N == 0) return 0;
+  if (G < 1 || G > 32) {
+    set_error("mlcv_rows_f64: G=%d out of range 1..32 per call", G);
+    return 1;
+  }
+  if (row0 + M > N) {
+    set_error("mlcv_rows_f64: rows [%llu, %llu) outside the list", (unsigned long long)row0,
+              (unsigned long long)(row0 + M));
+    return 1;
+  }
+  const double* coef = d_coef2n;
+  const double* ih2 = d_coef2n + N;
+  const int GT = G <= 8 ? 8 : G <= 16 ? 16 : 32;
+#define KDSB_R64(d, gt)                                                                        \
+  return launch_rows_f64<d, gt>(d_data, coef, ih2, N, row0, M, d_excl_lo, d_excl_hi, d_coefw, \
+                                d_lwtr, h_grid, G, log_shift, d_rowmask, d_partial, st)
+#define KDSB_CASE(d)                 \
+  case d:                            \
+    if (GT == 8) KDSB_R64(d, 8);     \
+    if (GT == 16) KDSB_R64(d, 16);   \
+    KDSB_R64(d, 32);
+  switch (D) {
+    KDSB_CASE(1)
+    KDSB_CASE(2)
+    KDSB_CASE(3)
+    KDSB_CASE(4)
+    KDSB_CASE(5)
+    KDSB_CASE(6)
+    KDSB_CASE(7)
+    KDSB_CASE(8)
+  }
+#undef KDSB_CASE
+#undef KDSB_R64
+  set_error("mlcv_rows_f64: D=%d out of range 1..8", D);
+  return 1;
+}
+
+// fold bookkeeping of the test rows [row0, row0+M) on the device: contiguous KFold
+// without shuffle (kde.py:134-136), the first N % K folds one longer
+int kdsb200_mlcv_rows_setup(uint64_t N, uint64_t K, uint64_t row0, uint64_t M, uint64_t Mpad,
+                            const double* d_w, const double* d_cwf, const double* d_lwt,
+                            int32_t* d_lo, int32_t* d_hi, double* d_coefw, double* d_lwtr,
+                            void* stream) {
+  if (Mpad == 0) return 0;
+  if (K < 1 || K > N || N >= (1ull << 31)) {
+    set_error("mlcv_rows_setup: need 1 <= K <= N < 2^31");
+    return 1;
+  }
+  mlcv_rows_setup_kernel<<<(unsigned)((Mpad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      N, K, row0, M, Mpad, d_w, d_cwf, d_lwt, d_lo, d_hi, d_coefw, d_lwtr);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int kdsb200_mlcv_f64_gtile(int G) { return G <= 8 ? 8 : G <= 16 ? 16 : 32; }
+
+int kdsb200_mlcv_reduce(const double* d_a, uint64_t na, int gt_a, const double* d_b, uint64_t nb,
+                        int gt_b, int G, double* d_out, void* stream) {
+  if (G < 1 || G > gt_a || (d_b && G > gt_b)) {
+    set_error("mlcv_reduce: G=%d does not fit the partial rows (%d, %d)", G, gt_a, gt_b);
+    return 1;
+  }
+  mlcv_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_a, na, gt_a, d_b, nb, gt_b, G, d_out);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

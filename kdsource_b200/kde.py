@@ -59,34 +59,28 @@ def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_
     rank, world = _dist.rank_world()
     b_lo, b_hi = _dist.shard_range(nb, rank, world)
     r_lo, r_hi = int(batch_off[b_lo]), int(batch_off[b_hi])
-    kth = np.zeros(N)
-    dist = np.zeros((N, kk)) if want_dist else None
-    idx = np.zeros((N, kk), dtype=np.int32) if want_idx else None
     n_loc = r_hi - r_lo
+    t_kth = _lib.empty(n_loc, t.float64)
+    t_dist = _lib.empty(n_loc * kk, t.float64) if want_dist else None
+    t_idx = _lib.empty(n_loc * kk, t.int32) if want_idx else None
     if n_loc > 0:
         loc_off = batch_off[b_lo:b_hi + 1] - r_lo
         d_data = _lib.to_dev(data[r_lo:r_hi])
         d_off = _lib.to_dev(loc_off, np.int64)
         use_f64 = precision == "float64"
         scratch = _lib.empty(n_loc * D, t.float64 if use_f64 else t.float32)
-        d_kth = _lib.empty(n_loc, t.float64)
-        d_dist = _lib.empty(n_loc * kk, t.float64) if want_dist else None
-        d_idx = _lib.empty(n_loc * kk, t.int32) if want_idx else None
         _lib.check(L.kdsb200_knn(
             _lib.ptr(d_data), n_loc, D, _lib.ptr(d_off), b_hi - b_lo,
             int(np.max(np.diff(loc_off))), kk, int(use_f64), _lib.ptr(scratch),
-            _lib.ptr(d_kth), _lib.ptr(d_dist), _lib.ptr(d_idx), _lib.stream()))
-        kth[r_lo:r_hi] = d_kth.cpu().numpy()
-        if want_dist:
-            dist[r_lo:r_hi] = d_dist.cpu().numpy().reshape(n_loc, kk)
-        if want_idx:
-            idx[r_lo:r_hi] = d_idx.cpu().numpy().reshape(n_loc, kk)
-    if world > 1:
-        kth = _dist.allreduce_sum_numpy(kth)
-        if want_dist:
-            dist = _dist.allreduce_sum_numpy(dist)
-        if want_idx:
-            idx = _dist.allreduce_sum_numpy(idx.astype(np.int64)).astype(np.int32)
+            _lib.ptr(t_kth), _lib.ptr(t_dist), _lib.ptr(t_idx), _lib.stream()))
+    # the ranks' disjoint slices are all-gathered on the device (batches are contiguous,
+    # so rank order is row order), then downloaded once
+    kth = _dist.allgather_concat_tensor(t_kth).cpu().numpy()
+    dist = idx = None
+    if want_dist:
+        dist = _dist.allgather_concat_tensor(t_dist.view(n_loc, kk)).cpu().numpy()
+    if want_idx:
+        idx = _dist.allgather_concat_tensor(t_idx.view(n_loc, kk)).cpu().numpy()
     return kth, dist, idx
 
 
@@ -141,19 +135,30 @@ class MLCVPlan:
     """Device-resident state of one MLCV grid search: packed sources, the test
     rows of this rank with their fold intervals, and the output buffers.
 
-    ``launch()`` enqueues the pair kernel(s) for the whole grid on the current
-    stream (no host work, no synchronisation); ``collect()`` downloads the
-    per-CTA partial sums and assembles the scores of the rows of this rank.
+    ``launch()`` enqueues the kernels for the whole grid on the current stream (no host
+    work, no synchronisation): the fp32 pair kernel, the fp64 recomputation of the rows
+    it flagged (sums inside the flush-to-zero window of ``ex2.approx``), and the
+    fixed-order reduction to one partial log-likelihood per grid point.  ``collect()``
+    all-reduces those G doubles over the ranks on the device (NCCL) when asked to, and
+    downloads them.  ``dtype="float64"`` evaluates every row with the fp64 kernel
+    (1e-12 against the reference's fp64 arithmetic, kde.py:106-153).
+
+    With torch.distributed initialised and ``rows=None`` every rank uploads only its own
+    share of the list; the shares are all-gathered on the device (NVLink).
     """
 
-    def __init__(self, data, weights, seed, grid, n_splits=10, rows=None, nsplit=None):
+    def __init__(self, data, weights, seed, grid, n_splits=10, rows=None, nsplit=None,
+                 dtype="float32"):
         L = _lib.load()
         t = _lib.torch()
+        if dtype not in ("float32", "float64"):
+            raise ValueError("dtype must be 'float32' or 'float64'")
+        self.dtype = dtype
         data = np.ascontiguousarray(data, dtype=np.float64)
         N, D = data.shape
         self.N, self.D = N, D
         self.grid = np.ascontiguousarray(grid, dtype=np.float64).reshape(-1)
-        K = int(min(n_splits, N))
+        K = self.K = int(min(n_splits, N))
         if K < 2:
             raise ValueError("n_splits must be at least 2")
         if np.ndim(seed) == 1:
@@ -169,86 +174,129 @@ class MLCVPlan:
         if not hmin > 0:
             raise ValueError("bandwidths must be positive")
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)[:N]
-        fb = kfold_bounds(N, K)
+        fb = self._fb = kfold_bounds(N, K)
         nf = np.diff(fb).astype(np.float64)
         wsum_all = float(np.sum(w)) if w is not None else float(N)
         wfold = np.add.reduceat(w, fb[:-1]) if w is not None else nf
         wtrain = wsum_all - wfold
-        fold_of = np.repeat(np.arange(K), np.diff(fb))
+        cwf = 1.0 / (nf * K)
+        self._sum_cw_all = float(np.sum(wfold * cwf))
+        rank, world = _dist.rank_world()
+        gather = rows is None and world > 1
         if rows is None:
-            rank, world = _dist.rank_world()
             rows = _dist.shard_range(N, rank, world)
-        r_lo, r_hi = rows
+        r_lo, r_hi = self.rows = (int(rows[0]), int(rows[1]))
         M = self.M = r_hi - r_lo
         wmax = float(np.max(w)) if w is not None else 1.0
         self.w_scale = 1.0 / wmax
         self.lc_ref = -D * np.log2(hmin)
         self.h2d_bytes = 0
-        self._acct = None
+        self.d2h_bytes = 0
+        self.sum_cw = 0.0
+        st = _lib.stream()
+
+        def up(a):
+            """Upload a per-sample array: only this rank's rows when the ranks share the
+            work, then all-gathered on the device."""
+            if a is None:
+                return None
+            if gather:
+                self.h2d_bytes += a[r_lo:r_hi].nbytes
+                return _dist.allgather_shards(_lib.to_dev(a[r_lo:r_hi]), N)
+            self.h2d_bytes += a.nbytes
+            return _lib.to_dev(a)
+
+        d_data = self.d_data = up(data)
+        d_w = self.d_w = up(w)
+        d_bw = self.d_bw = up(seed_arr)
         if M == 0:
+            self.chunks = []
+            self.n_launches = 0
             return
-        f_loc = fold_of[r_lo:r_hi]
-        wi = w[r_lo:r_hi] if w is not None else np.ones(M)
-        coefw = wi / (nf[f_loc] * K)
-        self.sum_cw = float(np.sum(coefw))
+        # centre of the packed fp32 coordinates: column means, computed on the device
+        mom_scr = _lib.empty(L.kdsb200_moments_scratch(), t.float64)
+        mom = _lib.empty(D + 2, t.float64)
+        _lib.check(L.kdsb200_weighted_moments(_lib.ptr(d_data), None, N, D, None, 1,
+                                              _lib.ptr(mom_scr), _lib.ptr(mom), st))
+        # fold bookkeeping of the rows, on the device from the K-entry fold tables
         Mpad = self.Mpad = L.kdsb200_mlcv_mpad(M)
-
-        def padded(a, dtype):
-            out = np.zeros(Mpad, dtype=dtype)
-            out[:M] = a
-            return out
-
-        host = [(padded(fb[f_loc], np.int32), np.int32), (padded(fb[f_loc + 1], np.int32), np.int32),
-                (padded(coefw, np.float64), np.float64),
-                (padded(np.log(wtrain[f_loc]), np.float64), np.float64)]
-        self.d_lo, self.d_hi, self.d_cw, self.d_lw = [_lib.to_dev(a, dt) for a, dt in host]
-        d_data = _lib.to_dev(data)
-        d_w = _lib.to_dev(w) if w is not None else None
-        d_bw = _lib.to_dev(seed_arr) if seed_arr is not None else None
-        self.h2d_bytes = (sum(a.nbytes for a, _ in host) + data.nbytes
-                          + (w.nbytes if w is not None else 0)
-                          + (seed_arr.nbytes if seed_arr is not None else 0))
-        cen_keep, cen_p = _lib.hostvec(data.mean(axis=0))
-        self.packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
-        _lib.check(L.kdsb200_pack_sources_f32(
-            _lib.ptr(d_data), _lib.ptr(d_w), _lib.ptr(d_bw), seed_scalar, N, D, cen_p,
-            self.w_scale, self.lc_ref, 1, _lib.ptr(self.packed), _lib.stream()))
-        self.qT = _lib.empty(Mpad * D, t.float32)
-        d_rows = d_data[r_lo:r_hi]  # contiguous row slice of the (N,D) tensor
-        _lib.check(L.kdsb200_pack_queries_f32(_lib.ptr(d_rows), M, Mpad, D, cen_p,
-                                              _lib.ptr(self.qT), _lib.stream()))
-        # source-dimension split (None: the library picks the one that fills whole waves)
-        self.nsplit = int(nsplit) if nsplit else L.kdsb200_mlcv_nsplit(N, M)
-        self.nsplit = max(1, min(self.nsplit, (N + 511) // 512))
+        with np.errstate(divide="ignore"):
+            lwt = np.log(wtrain)
+        d_cwf, d_lwt = _lib.to_dev(cwf), _lib.to_dev(lwt)
+        self.h2d_bytes += cwf.nbytes + lwt.nbytes
+        self.d_lo, self.d_hi = _lib.empty(Mpad, t.int32), _lib.empty(Mpad, t.int32)
+        self.d_cw, self.d_lw = _lib.empty(Mpad, t.float64), _lib.empty(Mpad, t.float64)
+        _lib.check(L.kdsb200_mlcv_rows_setup(N, K, r_lo, M, Mpad, _lib.ptr(d_w), _lib.ptr(d_cwf),
+                                             _lib.ptr(d_lwt), _lib.ptr(self.d_lo),
+                                             _lib.ptr(self.d_hi), _lib.ptr(self.d_cw),
+                                             _lib.ptr(self.d_lw), st))
+        mom_cw = _lib.empty(3, t.float64)
+        _lib.check(L.kdsb200_weighted_moments(_lib.ptr(self.d_cw), None, M, 1, None, 1,
+                                              _lib.ptr(mom_scr), _lib.ptr(mom_cw), st))
+        center = mom.cpu().numpy()[:D] / N
+        self.sum_cw = float(mom_cw.cpu()[0])
+        cen_keep, cen_p = _lib.hostvec(center)
+        # fp64 coefficients: used by the fp64 mode and by the recomputation of flagged rows
+        self.d_coef = _lib.empty(2 * N, t.float64)
+        _lib.check(L.kdsb200_mlcv_coef_f64(_lib.ptr(d_w), _lib.ptr(d_bw), seed_scalar, N, D,
+                                           self.w_scale, _lib.ptr(self.d_coef), st))
+        self.log_shift = -self.lc_ref * np.log(2.0)  # fp32 sums are in units of 2^lc_ref
+        if dtype == "float32":
+            self.packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
+            _lib.check(L.kdsb200_pack_sources_f32(
+                _lib.ptr(d_data), _lib.ptr(d_w), _lib.ptr(d_bw), seed_scalar, N, D, cen_p,
+                self.w_scale, self.lc_ref, 1, _lib.ptr(self.packed), st))
+            self.qT = _lib.empty(Mpad * D, t.float32)
+            d_rows = d_data[r_lo:r_hi]  # contiguous row slice of the (N,D) tensor
+            _lib.check(L.kdsb200_pack_queries_f32(_lib.ptr(d_rows), M, Mpad, D, cen_p,
+                                                  _lib.ptr(self.qT), st))
+            # source-dimension split (None: the library picks the one that fills whole waves)
+            self.nsplit = int(nsplit) if nsplit else L.kdsb200_mlcv_nsplit(N, M)
+            self.nsplit = max(1, min(self.nsplit, (N + 511) // 512))
+            self.flagmask = _lib.empty(Mpad, t.int32)
+        else:
+            self.nsplit = 1
+            self.flagmask = None
         self.nblk = Mpad // 256
+        self.nb64 = int(L.kdsb200_mlcv_f64_blocks(M))
+        self.d_scores = _lib.empty(len(self.grid), t.float64)
         self.chunks = []
         for g0 in range(0, len(self.grid), 32):
-            gsub = self.grid[g0:g0 + 32]
+            gsub = np.ascontiguousarray(self.grid[g0:g0 + 32])
             gt = L.kdsb200_mlcv_gtile(len(gsub))
+            gt64 = L.kdsb200_mlcv_f64_gtile(len(gsub))
             nk = np.ascontiguousarray(-_LOG2E / (2.0 * gsub ** 2), dtype=np.float32)
-            sbuf = (_lib.empty(self.nsplit * Mpad * gt, t.float64) if self.nsplit > 1 else None)
-            partial = _lib.empty(self.nblk * gt, t.float64)
-            self.chunks.append((g0, gsub, gt, nk, sbuf, partial))
+            f32 = dtype == "float32"
+            sbuf = _lib.empty(self.nsplit * Mpad * gt, t.float64) if self.nsplit > 1 else None
+            partial = _lib.empty(self.nblk * gt, t.float64) if f32 else None
+            partial64 = _lib.empty(self.nb64 * gt64, t.float64)
+            self.chunks.append((g0, gsub, gt, gt64, nk, sbuf, partial, partial64))
         #: kernel launches per launch() call
-        self.n_launches = len(self.chunks) * (2 if self.nsplit > 1 else 1)
-        self._acct = (nf, f_loc, fb)  # for the lazily computed work counters below
+        self.n_launches = len(self.chunks) * ((3 if self.nsplit == 1 else 4)
+                                              if dtype == "float32" else 2)
+
+    def _row_folds(self):
+        nf = np.diff(self._fb).astype(np.float64)
+        fold_of = np.repeat(np.arange(self.K), np.diff(self._fb))
+        return nf, fold_of[self.rows[0]:self.rows[1]]
 
     @property
     def n_evals(self):
         """Kernel evaluations (exponentials that enter a score) per launch() call."""
-        if self._acct is None:
+        if self.M == 0:
             return 0.0
-        nf, f_loc, _ = self._acct
+        nf, f_loc = self._row_folds()
         return float(np.sum(float(self.N) - nf[f_loc])) * len(self.grid)
 
     @property
     def n_slots(self):
-        """(row, source, g) slots the kernel executes per launch(): per CTA of 256 rows,
-        all source tiles except those inside the excluded interval shared by all its
-        rows (benchmark accounting; not needed to run the search)."""
-        if self._acct is None:
+        """(row, source, g) slots the fp32 kernel executes per launch(): per CTA of 256
+        rows, all source tiles except those inside the excluded interval shared by all
+        its rows (benchmark accounting; not needed to run the search)."""
+        if self.M == 0:
             return 0.0
-        _, f_loc, fb = self._acct
+        _, f_loc = self._row_folds()
+        fb = self._fb
         N, M, Mpad = self.N, self.M, self.Mpad
         TS = 512
         ntiles = (N + TS - 1) // TS
@@ -266,47 +314,78 @@ class MLCVPlan:
         if self.M == 0:
             return
         L = _lib.load()
-        for g0, gsub, gt, nk, sbuf, partial in self.chunks:
-            _lib.check(L.kdsb200_mlcv_scores_f32(
-                _lib.ptr(self.packed), self.N, self.D, _lib.ptr(self.qT), self.M, self.Mpad,
-                _lib.ptr(self.d_lo), _lib.ptr(self.d_hi), _lib.ptr(self.d_cw),
-                _lib.ptr(self.d_lw), nk.ctypes.data_as(_lib.c_float_p), len(gsub),
-                self.nsplit, _lib.ptr(sbuf), _lib.ptr(partial), _lib.stream()))
+        st = _lib.stream()
+        r_lo = self.rows[0]
+        for g0, gsub, gt, gt64, nk, sbuf, partial, partial64 in self.chunks:
+            G = len(gsub)
+            if self.dtype == "float32":
+                _lib.check(L.kdsb200_mlcv_scores_f32(
+                    _lib.ptr(self.packed), self.N, self.D, _lib.ptr(self.qT), self.M, self.Mpad,
+                    _lib.ptr(self.d_lo), _lib.ptr(self.d_hi), _lib.ptr(self.d_cw),
+                    _lib.ptr(self.d_lw), nk.ctypes.data_as(_lib.c_float_p), G,
+                    self.nsplit, _lib.ptr(sbuf), _lib.ptr(partial), _lib.ptr(self.flagmask), st))
+            _lib.check(L.kdsb200_mlcv_rows_f64(
+                _lib.ptr(self.d_data), _lib.ptr(self.d_coef), self.N, self.D, r_lo, self.M,
+                _lib.ptr(self.d_lo), _lib.ptr(self.d_hi), _lib.ptr(self.d_cw), _lib.ptr(self.d_lw),
+                gsub.ctypes.data_as(_lib.c_double_p), G, self.log_shift,
+                _lib.ptr(self.flagmask), _lib.ptr(partial64), st))
+            out = self.d_scores[g0:g0 + G]
+            if self.dtype == "float32":
+                _lib.check(L.kdsb200_mlcv_reduce(_lib.ptr(partial), self.nblk, gt,
+                                                 _lib.ptr(partial64), self.nb64, gt64, G,
+                                                 _lib.ptr(out), st))
+            else:
+                _lib.check(L.kdsb200_mlcv_reduce(_lib.ptr(partial64), self.nb64, gt64, None, 0, 0,
+                                                 G, _lib.ptr(out), st))
 
-    def collect(self):
-        """Scores contributed by the rows of this plan (sum over ranks = score)."""
-        scores = np.zeros(len(self.grid))
-        self.d2h_bytes = 0
-        if self.M == 0:
-            return scores
+    def n_flagged(self):
+        """Rows of the last launch() whose fp32 sums were recomputed in fp64 (synchronises)."""
+        if self.M == 0 or self.flagmask is None:
+            return 0
+        return int((self.flagmask[:self.M] != 0).sum().item())
+
+    def collect(self, allreduce=False):
+        """Scores contributed by the rows of this plan; ``allreduce=True`` sums the G
+        partial log-likelihoods over the ranks on the device first (the ranks' rows must
+        partition the list, as they do with ``rows=None``)."""
+        G = len(self.grid)
+        t = _lib.torch()
         D = self.D
-        for g0, gsub, gt, nk, sbuf, partial in self.chunks:
-            part = partial.cpu().numpy().reshape(self.nblk, gt)[:, :len(gsub)]
-            self.d2h_bytes += self.nblk * gt * 8
-            const_g = (self.lc_ref * np.log(2.0) - np.log(self.w_scale)
-                       - 0.5 * D * np.log(2 * np.pi) - D * np.log(gsub))
+        const_g = (self.lc_ref * np.log(2.0) - np.log(self.w_scale)
+                   - 0.5 * D * np.log(2 * np.pi) - D * np.log(self.grid))
+        if allreduce and _dist.rank_world()[1] > 1:
+            if self.M == 0:
+                self.d_scores = t.zeros(G, dtype=t.float64, device="cuda")
+            _dist.allreduce_sum_tensor(self.d_scores)
+            part = self.d_scores.cpu().numpy()
+            self.d2h_bytes = G * 8
             with np.errstate(invalid="ignore"):
-                scores[g0:g0 + 32] = part.sum(axis=0) + const_g * self.sum_cw
-        return scores
+                return part + const_g * self._sum_cw_all
+        if self.M == 0:
+            return np.zeros(G)
+        part = self.d_scores.cpu().numpy()
+        self.d2h_bytes = G * 8
+        with np.errstate(invalid="ignore"):
+            return part + const_g * self.sum_cw
 
 
-def mlcv_scores(data, weights, seed, grid, n_splits=10):
+def mlcv_scores(data, weights, seed, grid, n_splits=10, dtype="float32"):
     """Cross-validation scores of ``bw_grid[g] = grid[g] * seed`` for every g.
 
     ``score[g] == _kde_cv_score(grid[g] * seed, data, weights, n_splits)`` of
     the reference (kde.py:106-153), computed for the whole grid in one pass
     over the pair space.  ``seed`` is a scalar or one bandwidth per sample.
     Test rows are sharded over ranks when torch.distributed is initialised.
+    ``dtype="float32"`` is within 1e-5 of the reference's fp64 arithmetic (rows whose
+    sums fall into the fp32 underflow window are recomputed in fp64), ``"float64"``
+    within 1e-12.
     """
-    plan = MLCVPlan(data, weights, seed, grid, n_splits=n_splits)
+    plan = MLCVPlan(data, weights, seed, grid, n_splits=n_splits, dtype=dtype)
     plan.launch()
-    scores = plan.collect()
-    if _dist.rank_world()[1] > 1:
-        scores = _dist.allreduce_sum_numpy(scores)
-    return scores
+    return plan.collect(allreduce=True)
 
 
-def _kde_cv_score(bw, data, weights=None, n_splits=10, modelKDE=TreeKDE):
+def _kde_cv_score(bw, data, weights=None, n_splits=10, modelKDE=TreeKDE, dtype="float32"):
     """Cross-validation likelihood score (reference kde.py:106-153).
 
     ``modelKDE`` is accepted for signature compatibility; the score is always
@@ -317,7 +396,8 @@ def _kde_cv_score(bw, data, weights=None, n_splits=10, modelKDE=TreeKDE):
             raise ValueError("If bw is array, must have same len as data")
         if len(bw) > len(data):
             print("Warning: bw longer than data.")
-    return float(mlcv_scores(data, weights, bw, np.array([1.0]), n_splits=n_splits)[0])
+    return float(mlcv_scores(data, weights, bw, np.array([1.0]), n_splits=n_splits,
+                             dtype=dtype)[0])
 
 
 def _effective_n(n_rows, weights):
@@ -341,7 +421,7 @@ def _maybe_plot_scores(grid, scores):
     plt.show()
 
 
-def bw_mlcv(data, weights=None, n_splits=10, seed=None, grid=None, show=True):
+def bw_mlcv(data, weights=None, n_splits=10, seed=None, grid=None, show=True, dtype="float32"):
     """Maximum Likelihood Cross-Validation bandwidth (reference kde.py:156-226).
 
     ``bw_grid[g] = grid[g] * seed`` (seed scalar or per-sample, Silverman by
@@ -356,7 +436,8 @@ def bw_mlcv(data, weights=None, n_splits=10, seed=None, grid=None, show=True):
         print("If fitting fails, change the grid.")
         grid = np.logspace(-0.1, 0.1, 10)
     factors = np.asarray(grid, dtype=np.float64).reshape(-1)
-    scores = mlcv_scores(data, weights, seed, factors, n_splits=min(n_splits, len(data)))
+    scores = mlcv_scores(data, weights, seed, factors, n_splits=min(n_splits, len(data)),
+                         dtype=dtype)
     best = int(np.argmax(scores))
     if show:
         _maybe_plot_scores(factors, scores)

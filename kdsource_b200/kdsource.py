@@ -191,8 +191,8 @@ class KDSource:
         # query points are split contiguously over the ranks (sources replicated)
         rank, world = _dist.rank_world()
         lo, hi = _dist.shard_range(M, rank, world)
-        dens = np.zeros(M)
-        jacs = np.zeros(M)
+        dens = np.zeros(hi - lo)
+        jacs = np.zeros(hi - lo)
         for s in range(lo, hi, chunk):
             n = min(chunk, hi - s)
             d_parts = _lib.to_dev(parts[s:s + n])
@@ -202,11 +202,11 @@ class KDSource:
                                                 inv_p, _lib.ptr(d_vecs), _lib.ptr(d_jac),
                                                 _lib.stream()))
             d_out = self.kde.evaluate_device(d_vecs, n, dev)
-            dens[s:s + n] = d_out.cpu().numpy()
-            jacs[s:s + n] = d_jac.cpu().numpy()
-        if world > 1:
-            dens = _dist.allreduce_sum_numpy(dens)
-            jacs = _dist.allreduce_sum_numpy(jacs)
+            dens[s - lo:s - lo + n] = d_out.cpu().numpy()
+            jacs[s - lo:s - lo + n] = d_jac.cpu().numpy()
+        if world > 1:  # the ranks' disjoint slices, gathered in rank (= query) order
+            dens = _dist.allgather_rows(dens)
+            jacs = _dist.allgather_rows(jacs)
         return dens, jacs
 
     def save(self, xmlfilename=None, bwfile=None, adjust_N=True):
@@ -231,8 +231,9 @@ class KDSource:
                 self.plist.set_params()
             factor = bw_silv(dim, self.plist.N_eff) / bw_silv(dim, self.N_eff)
             if np.isscalar(bw):
+                # local only: `bw *= factor` on a float rebinds the name in the reference
+                # (kdsource.py:293), so self.kde.bw keeps its value
                 bw = bw * factor
-                self.kde.bw = bw
             else:
                 bw *= factor  # in place, like the reference (kdsource.py:293)
         root = Element("KDSource")
@@ -397,6 +398,31 @@ class KDSource:
         return self._plot_metric_axis(
             -1, grid_t, vec0, vec1, kwargs, r"$t$ [ms]",
             r"$J\ \left[ \frac{{{}}}{{s^2}} \right]$".format(self.plist.pt))
+
+    def plot_point(self, var, grid, part0, **kwargs):
+        """Full multivariate density along one particle variable, the others fixed at
+        `part0` (reference kdsource.py:324-395).  kwargs: xscale ('linear'), yscale
+        ('log'), fact, label.  Returns [fig, [scores, errs]]; `part0` is not modified
+        (the reference zeroes its `var` entry in place)."""
+        if self.fitted is False:
+            raise Exception("Must fit before plotting.")
+        if isinstance(var, str):
+            var = varmap[var]
+        grid = np.asarray(grid, dtype=np.float64)
+        parts = np.zeros((len(grid), 7))
+        parts[:, var] = grid
+        base = np.array(part0, dtype=np.float64)
+        base[var] = 0
+        parts += base
+        scores, errs = self.evaluate(parts)
+        if "fact" in kwargs:
+            scores *= kwargs["fact"]
+            errs *= kwargs["fact"]
+        fig = self._errorbar(
+            grid, scores, errs, kwargs.get("label", "KDE"), kwargs.get("xscale", "linear"),
+            kwargs.get("yscale", "log"), r"${}\ [{}]$".format(varnames[var], units[var]),
+            r"$J\ \left[ \frac{{{}}}{{{} s}} \right]$".format(self.plist.pt, self.geom.volunits))
+        return [fig, [scores, errs]]
 
     def plot2D_point(self, vrs, grids, part0, **kwargs):
         """Full multivariate density on a 2-D grid of two particle variables, the

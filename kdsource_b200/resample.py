@@ -21,7 +21,7 @@ from .geom import Geometry
 from .plist import PList
 from .sampler import DEFAULT_SLOTS, DeviceSampler, make_geom_struct
 from .utils import pt2pdg
-from .writemcpl import _check_new_mcpl_filename
+from .writemcpl import _check_new_mcpl_filename, _normalised_mcpl_filename
 
 
 def open_source(kds_sourcefile, precision="float32"):
@@ -96,21 +96,33 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
     if not ksrc.is_file():
         raise RuntimeError(f"Missing file: {kds_sourcefile}")
     rank, world = _dist.rank_world()
-    if rank == 0:
-        dst = _check_new_mcpl_filename(destination_mcpl, force=force)
-    else:
-        dst = _check_new_mcpl_filename(destination_mcpl, force=True)
+    # argument checks first: nothing on disk is touched before they have passed
     if nout <= 0 or nout > 1e16:
         raise RuntimeError("Invalid (or unreasonable) number of"
                            f" particles requested: {nout}")
+    if world > 1 and not isinstance(rng, int):
+        raise RuntimeError("multi-rank resampling needs an explicit integer seed")
     if rng is None:
         rng = int.from_bytes(os.urandom(8), byteorder="big")
         print("Warning: No explicit seed provided"
               f" (choosing arbitrarily seed={rng})")
-        if world > 1:
-            raise RuntimeError("multi-rank resampling needs an explicit integer seed")
-    if world > 1 and not isinstance(rng, int):
-        raise RuntimeError("multi-rank resampling needs an explicit integer seed")
+    # Only rank 0 looks at (and, with force, removes) an existing output file; its
+    # verdict is shared so that a refusal raises on every rank instead of leaving the
+    # others waiting at a barrier.
+    refusal = None
+    if rank == 0:
+        try:
+            dst = _check_new_mcpl_filename(destination_mcpl, force=force)
+        except RuntimeError as e:
+            refusal = e
+    else:
+        try:
+            dst = _normalised_mcpl_filename(destination_mcpl).absolute()
+        except RuntimeError as e:
+            refusal = e
+    if not _dist.all_agree(refusal is None):
+        raise refusal if refusal is not None else RuntimeError(
+            "resample_to_mcpl: rank 0 refused the output file " + str(destination_mcpl))
     import time
 
     timing = os.environ.get("KDSB200_TIMING")

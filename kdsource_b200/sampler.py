@@ -64,7 +64,11 @@ def make_geom_struct(geom, scaling, kernel="g"):
 
 
 class DeviceSampler:
-    """Resampler over one particle list resident on the current CUDA device."""
+    """Resampler over one particle list resident on the current CUDA device.
+
+    ``precision="float32"`` (default) keeps the list as fp32 and perturbs in fp32 for the
+    two geometries with specialised kernels (every coordinate within 1e-5 of its scale);
+    any other geometry, and ``precision="float64"``, use the fp64 store (1e-12)."""
 
     def __init__(self, parts, weights, bw, geom_struct, pdgcode=2112, precision="float32"):
         L = _lib.load()
@@ -92,7 +96,11 @@ class DeviceSampler:
         # the list was decoded)
         self.sum_w = float(np.sum(weights.cpu().numpy() if on_device else weights))
         d_parts = parts if on_device else _lib.to_dev(parts)
-        self.f32 = precision == "float32"
+        # fp32 store + arithmetic only for the geometries with a specialised kernel; the
+        # generic maps (acos / atan2 based metrics, rotations) run on the fp64 store, where
+        # fp32-rounded sources could not hold 1e-5 of the variable's scale
+        self.f32 = precision == "float32" and bool(
+            L.kdsb200_resample_fp32_ok(ctypes.byref(geom_struct)))
         self.src = _lib.empty(self.N * 8, t.float32 if self.f32 else t.float64)
         _lib.check(L.kdsb200_convert_particles(_lib.ptr(d_parts), self.N, int(self.f32),
                                                _lib.ptr(self.src), _lib.stream()))

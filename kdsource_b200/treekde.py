@@ -112,15 +112,15 @@ class TreeKDE:
 
         rank, world = _dist.rank_world()
         lo, hi = _dist.shard_range(len(pts), rank, world) if shard else (0, len(pts))
-        out = np.zeros(len(pts), dtype=np.float64)
+        out = np.zeros(hi - lo, dtype=np.float64)
         dev = self._device_state()
         for s in range(lo, hi, chunk):
             e = min(s + chunk, hi)
             d_pts = _lib.to_dev(pts[s:e])
             d_out = self.evaluate_device(d_pts, e - s, dev)
-            out[s:e] = d_out.cpu().numpy()
-        if shard and world > 1:
-            out = _dist.allreduce_sum_numpy(out)
+            out[s - lo:e - lo] = d_out.cpu().numpy()
+        if shard and world > 1:  # the ranks' disjoint slices, in rank (= query) order
+            out = _dist.allgather_rows(out)
         return out
 
     # -- device side ----------------------------------------------------------

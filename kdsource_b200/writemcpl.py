@@ -7,16 +7,22 @@ import pathlib
 from . import mcpl
 
 
-def _check_new_mcpl_filename(filename, force=False):
-    """Output-name policy of the reference (writemcpl.py:52-74): the file is
-    always ``*.mcpl.gz``; existing ``.mcpl`` / ``.mcpl.gz`` files are an error
-    unless `force`; the directory must exist."""
+def _normalised_mcpl_filename(filename):
+    """``*.mcpl`` -> ``*.mcpl.gz``; any other ending is an error.  No side effects."""
     dst = pathlib.Path(filename)
     if dst.name.endswith(".mcpl"):
         dst = dst.parent.joinpath(dst.name + ".gz")
     elif not dst.name.endswith(".mcpl.gz"):
         raise RuntimeError("Output name does not end with .mcpl or"
                            f" .mcpl.gz: {dst.name}")
+    return dst
+
+
+def _check_new_mcpl_filename(filename, force=False):
+    """Output-name policy of the reference (writemcpl.py:52-74): the file is
+    always ``*.mcpl.gz``; existing ``.mcpl`` / ``.mcpl.gz`` files are an error
+    unless `force`; the directory must exist."""
+    dst = _normalised_mcpl_filename(filename)
     for cand in (dst.parent.joinpath(dst.name[:-3]), dst):
         if cand.is_file():
             if not force:

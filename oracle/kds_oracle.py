@@ -568,6 +568,38 @@ def ref_sampler(parts8, weights, pdg, metrics, kernel, bw, nout, seed=1, pt="n",
     return out8, outw, wraps
 
 
+def ref_sampler_cli(parts8, weights, pdg, metrics, kernel, bw, nout, seed=1, pt="n",
+                    bwfile=None, nskip=1000):
+    """The reference's C sampler driven like ``kdsource-resample`` drives it
+    (python/kdsource/resample.py:33-43, _chooks.py:29-41): every uniform is a ctypes
+    callback into Python's ``random.Random(seed).random``.  Returns (parts, weights)."""
+    import random
+
+    R = ref_lib()
+    if R is None:
+        raise RuntimeError("oracle/_ref not built")
+    parts8 = np.ascontiguousarray(parts8, dtype=np.float64)
+    weights = np.ascontiguousarray(weights, dtype=np.float64)
+    pdg = np.ascontiguousarray(np.broadcast_to(pdg, (len(parts8),)), dtype=np.int32)
+    types = np.array([METRIC_ID[m[0]] for m in metrics], dtype=np.int32)
+    dims = np.array([len(m[1]) for m in metrics], dtype=np.int32)
+    scal = np.array(sum([list(m[1]) for m in metrics], []), dtype=np.float64)
+    npss = np.array([len(m[2]) for m in metrics], dtype=np.int32)
+    pars = np.array(sum([list(m[2]) for m in metrics], []) + [0.0], dtype=np.float64)
+    out8 = np.empty((nout, 8))
+    outw = np.empty(nout)
+    cb = ctypes.CFUNCTYPE(ctypes.c_double)(random.Random(seed).random)
+    R.ref_sampler_run_stateless.restype = ctypes.c_int
+    R.ref_sampler_run_stateless(
+        cb, _p(parts8, c_double_p), _p(weights, c_double_p), _p(pdg, c_i32_p),
+        ctypes.c_int64(len(parts8)), ctypes.c_char(pt.encode()), ctypes.c_int(len(metrics)),
+        _p(types, c_int_p), _p(dims, c_int_p), _p(scal, c_double_p), _p(npss, c_int_p),
+        _p(pars, c_double_p), ctypes.c_char(kernel.encode()[:1]), ctypes.c_double(float(bw)),
+        bwfile.encode() if bwfile else None, ctypes.c_int64(nout), ctypes.c_int(nskip),
+        _p(out8, c_double_p), _p(outw, c_double_p))
+    return out8, outw
+
+
 # ----------------------------------------------------------------------
 # synthetic data generator (SURVEY 8d; Verification.ipynb cell 4, seeded)
 # ----------------------------------------------------------------------

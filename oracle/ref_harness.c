@@ -136,15 +136,14 @@ const char *ref_metric_name(int i) { return _metric_names[i]; }
  * or the scripted uniforms when uniforms != NULL.
  * out8: nout x 8 doubles; out_w: nout weights.
  */
-int ref_sampler_run(const double *parts8, const double *weights,
-                    const int32_t *pdg, int64_t N, char pt, int order,
-                    const int *types, const int *dims, const double *scalings,
-                    const int *npss, const double *paramss, char kernel,
-                    double bw, const char *bwfile, const double *plist_trasl,
-                    const double *plist_rot, int x2z, const double *geom_trasl,
-                    const double *geom_rot, uint64_t seed,
-                    const double *uniforms, int nuni, int64_t nout,
-                    int nskip_wmean, double *out8, double *out_w) {
+static int run_sampler(kds_rng_fct_t rng, void *st, const double *parts8,
+                       const double *weights, const int32_t *pdg, int64_t N, char pt,
+                       int order, const int *types, const int *dims,
+                       const double *scalings, const int *npss, const double *paramss,
+                       char kernel, double bw, const char *bwfile,
+                       const double *plist_trasl, const double *plist_rot, int x2z,
+                       const double *geom_trasl, const double *geom_rot, int64_t nout,
+                       int nskip_wmean, double *out8, double *out_w) {
   mcpl_particle_t *arr =
       (mcpl_particle_t *)calloc((size_t)N, sizeof(mcpl_particle_t));
   for (int64_t i = 0; i < N; i++) {
@@ -165,10 +164,6 @@ int ref_sampler_run(const double *parts8, const double *weights,
   PList *pl = PList_create(pt, "mem", plist_trasl, plist_rot, x2z);
   Geometry *g = Geom_create(order, ms, bw, bwfile, kernel, geom_trasl, geom_rot);
   KDSource *k = KDS_create(1.0, kernel, pl, g);
-  xs_rng xr = {seed ? seed : 0x9E3779B97F4A7C15ULL};
-  script_rng sr = {uniforms, nuni, 0};
-  kds_rng_fct_t rng = uniforms ? script_next : xs_next;
-  void *st = uniforms ? (void *)&sr : (void *)&xr;
   double w_crit = KDS_rand_w_mean(rng, st, k, nskip_wmean, NULL);
   mcpl_particle_t part;
   int wraps = 0;
@@ -184,4 +179,40 @@ int ref_sampler_run(const double *parts8, const double *weights,
   g_parts = NULL;
   g_nparts = 0;
   return wraps;
+}
+
+int ref_sampler_run(const double *parts8, const double *weights,
+                    const int32_t *pdg, int64_t N, char pt, int order,
+                    const int *types, const int *dims, const double *scalings,
+                    const int *npss, const double *paramss, char kernel,
+                    double bw, const char *bwfile, const double *plist_trasl,
+                    const double *plist_rot, int x2z, const double *geom_trasl,
+                    const double *geom_rot, uint64_t seed,
+                    const double *uniforms, int nuni, int64_t nout,
+                    int nskip_wmean, double *out8, double *out_w) {
+  xs_rng xr = {seed ? seed : 0x9E3779B97F4A7C15ULL};
+  script_rng sr = {uniforms, nuni, 0};
+  kds_rng_fct_t rng = uniforms ? script_next : xs_next;
+  void *st = uniforms ? (void *)&sr : (void *)&xr;
+  return run_sampler(rng, st, parts8, weights, pdg, N, pt, order, types, dims, scalings,
+                     npss, paramss, kernel, bw, bwfile, plist_trasl, plist_rot, x2z,
+                     geom_trasl, geom_rot, nout, nskip_wmean, out8, out_w);
+}
+
+/* The same loop driven the way the command-line tool drives it: a STATELESS callback
+ * double(*)(void) -- python/kdsource/_chooks.py:29-41 hands random.Random(seed).random
+ * through ctypes, one C -> Python call per uniform -- wrapped as in
+ * clib/src/resamplemcpl.c:4-26. */
+typedef double (*stateless_rng_t)(void);
+static double stateless_next(void *st) { return (*(stateless_rng_t *)st)(); }
+int ref_sampler_run_stateless(stateless_rng_t rng0, const double *parts8,
+                              const double *weights, const int32_t *pdg, int64_t N, char pt,
+                              int order, const int *types, const int *dims,
+                              const double *scalings, const int *npss,
+                              const double *paramss, char kernel, double bw,
+                              const char *bwfile, int64_t nout, int nskip_wmean,
+                              double *out8, double *out_w) {
+  return run_sampler(stateless_next, (void *)&rng0, parts8, weights, pdg, N, pt, order,
+                     types, dims, scalings, npss, paramss, kernel, bw, bwfile, NULL, NULL, 0,
+                     NULL, NULL, nout, nskip_wmean, out8, out_w);
 }

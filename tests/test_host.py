@@ -477,6 +477,7 @@ def test_plot_methods_host_logic(workdir):
                      lambda: s.plot_E(np.logspace(-3, 0, 3)),
                      lambda: s.plot_t(np.linspace(0, 1, 3)),
                      lambda: s.plot2D_integr(["x", "y"], [np.zeros(2), np.zeros(2)]),
+                     lambda: s.plot_point("x", np.zeros(3), np.zeros(7)),
                      lambda: s.plot2D_point(["x", "y"], [np.zeros(2), np.zeros(2)], np.zeros(7))):
             with pytest.raises(Exception, match="Must fit"):
                 call()
