@@ -149,13 +149,14 @@ def case_resample(rng, worst):
     assert e64 < 1e-9, ("resample parts fp64", desc[1][0], kernel, e64)
     o32 = DeviceSampler(parts, w, bw, gs).sample(count, seed=seed, first=first, want=("idx", "parts"))
     assert np.array_equal(o32["idx"], ref["idx"]), ("resample idx fp32", n, count)
-    # fp32: compare against the variable's scale; a reflection / re-draw decision within
-    # rounding of its threshold may differ for isolated particles
+    # precision="float32": every coordinate of every particle within 1e-5 of the variable's
+    # scale (fp32 arithmetic for the two specialised geometries, the fp64 store otherwise)
     dev = np.abs(o32["parts"] - ref["parts"]) / (1 + np.abs(ref["parts"]))
-    frac_bad = float(np.mean(np.max(dev, axis=1) > 1e-4))
-    assert frac_bad < 5e-3, ("resample parts fp32", desc[1][0], kernel, frac_bad)
+    e32 = float(np.max(dev))
+    assert e32 < 1e-5, ("resample parts fp32", desc[1][0], kernel, e32,
+                        np.unravel_index(np.argmax(dev), dev.shape))
     worst["resample_fp64"] = max(worst.get("resample_fp64", 0), e64)
-    worst["resample_fp32_outlier_frac"] = max(worst.get("resample_fp32_outlier_frac", 0), frac_bad)
+    worst["resample_fp32"] = max(worst.get("resample_fp32", 0), e32)
 
 
 def main():
