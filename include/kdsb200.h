@@ -78,6 +78,50 @@ int kdsb200_pack_queries_split_f32(const double* d_pts, uint64_t M, uint64_t Mpa
 int kdsb200_kde_eval_split_f32(const float* d_packed, uint64_t N, int D, const float* d_qT,
                                uint64_t M, uint64_t Mpad, double out_scale, int nsplit,
                                double* d_partial, double* d_out, void* stream);
+/* ---- spatially ordered tiles: exact tile culling + tile-local coordinates --------------
+ * The work saving of the reference's TreeKDE (only the sources inside the support radius
+ * are summed, kdsource.py:238-240, kde.py:146-151) without its approximation: sources are
+ * ordered along a Hilbert curve, each tile of 512 keeps its bounding box and a centre,
+ * coordinates are stored relative to that centre, and the kernel skips every tile whose
+ * box is farther than the cutoff from the box of a CTA's 1024 (equally ordered) queries. */
+uint64_t kdsb200_minmax_scratch(void); /* doubles */
+/* d_minmax[0..D) = column minima, [D..2D) = maxima of d_data (N,D) */
+int kdsb200_column_minmax(const double* d_data, uint64_t N, int D, double* d_scratch,
+                          double* d_minmax, void* stream);
+uint64_t kdsb200_order_scratch_bytes(uint64_t N);
+int kdsb200_hilbert_bits(int D);
+/* d_perm[i] = index of the i-th point along the Hilbert curve over the box [h_lo, h_hi]
+ * quantised to kdsb200_hilbert_bits(D) bits per dimension (points outside are clamped);
+ * stable radix sort, ties keep the input order.  N < 2^32. */
+int kdsb200_hilbert_order(const double* d_data, uint64_t N, int D, const double* h_lo,
+                          const double* h_hi, void* d_scratch, uint32_t* d_perm, void* stream);
+/* Sources in d_perm order, tiles as kdsb200_pack_sources_f32 (same `mode`) but with
+ * coordinates relative to the tile centre d_tilecen[t][D] (multiples of 1/grid, grid a
+ * power of two); d_tilebox[t] = {lo[D], hi[D]} of x - h_center over the tile. */
+int kdsb200_pack_sources_sorted_f32(const double* d_data, const double* d_w, const double* d_bw,
+                                    double bw_scalar, uint64_t N, int D, const uint32_t* d_perm,
+                                    const double* h_center, double grid, double w_scale,
+                                    double lc_ref, int mode, float* d_packed, float* d_tilebox,
+                                    float* d_tilecen, void* stream);
+uint64_t kdsb200_sorted_qpad(uint64_t M); /* query count padded to the CTA tile (1024) */
+/* queries in d_perm order as hi + lo floats, hi on the grid: d_qT [2D][Mpad] */
+int kdsb200_pack_queries_sorted_f32(const double* d_pts, uint64_t M, uint64_t Mpad, int D,
+                                    const uint32_t* d_perm, const double* h_center, double grid,
+                                    float* d_qT, void* stream);
+int kdsb200_sorted_ctas(void);
+int kdsb200_sorted_nsplit(uint64_t N, uint64_t M);
+uint64_t kdsb200_sorted_scratch_bytes(uint64_t N, uint64_t Mpad, int nsplit);
+/* d_out[d_perm_q[m]] = out_scale * sum over sources, as kdsb200_kde_eval_kernel_f32.
+ * kernel 0 with cutoff > 0: hard radius, tiles beyond it skipped (exact: pairs inside
+ * visited tiles are still masked one by one); kernel 1/2: `cutoff` = the largest support
+ * radius (0: no culling); kernel 0 with cutoff <= 0: the exact sum over every tile.
+ * *d_tiles_visited (device, may be NULL) = tiles loaded, summed over (1024-query block,
+ * source split) work items: executed pairs = that * 512 * 1024. */
+int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
+                                const float* d_tilecen, uint64_t N, int D, const float* d_qT,
+                                const uint32_t* d_perm_q, uint64_t M, uint64_t Mpad, int kernel,
+                                double cutoff, double out_scale, int nsplit, void* d_scratch,
+                                double* d_out, uint64_t* d_tiles_visited, void* stream);
 /* fp64 mode (1e-12 parity).  d_scratch: 2N + nsplit*M doubles. */
 int kdsb200_kde_eval_kernel_f64(const double* d_data, const double* d_w, const double* d_bw,
                                 double bw_scalar, uint64_t N, int D, double w_scale,

@@ -12,11 +12,15 @@ Semantics: ``out[m] = sum_i w_i/sum(w) (2 pi)^(-d/2) h_i^-d exp(-|q_m - x_i|^2 /
 ``cutoff="treekde"`` applies the hard support radius KDEpy's TreeKDE derives
 from the largest bandwidth; a float is an explicit radius.
 
-``dtype``: ``"float32"`` (1e-5 while the smallest bandwidth is above ~0.28 of the
-data's spread: the coordinate rounding error grows like (spread / h)^2),
+``dtype``: ``"float32"`` -- sources ordered along a Hilbert curve and stored in tiles of
+512 with coordinates relative to the tile centre, so the fp32 rounding error scales with
+the tile size instead of the spread of the list; with a cutoff, tiles farther than the
+radius from a block of 1024 (equally ordered) query points are skipped, exactly;
 ``"float32x2"`` (Gaussian kernel; coordinates carried as hi + lo floats, error
-independent of spread / bandwidth, ~57 % of the fp32 rate), ``"float64"`` (1e-12), or
-``"auto"`` (default): float32, switching to float32x2 below that bandwidth ratio.
+independent of spread / bandwidth, ~57 % of the fp32 rate); ``"float32_dense"`` (the
+unordered fp32 kernel: 1e-5 only while the smallest bandwidth is above ~0.28 of the
+spread); ``"float64"`` (1e-12); ``"auto"`` (default): float32, switching to float32x2
+when the smallest bandwidth is below 0.07 of the largest tile half-extent.
 
 ``kernel="epa"`` / ``"box"`` (the other two names the reference passes to KDEpy,
 kdsource.py:60-65) are KDEpy's radially symmetric finite-support kernels scaled
@@ -56,8 +60,10 @@ def treekde_radius(bw_max, atol=1e-3):
 
 
 class TreeKDE:
-    #: below this bandwidth / spread ratio dtype="auto" switches to the split-coordinate kernel
-    AUTO_SPLIT_BELOW = 0.28
+    #: dtype="auto" switches to the split-coordinate kernel when the smallest bandwidth is
+    #: below this fraction of the largest half-extent of a source tile (the fp32 error of a
+    #: kernel value is ~ (extent / h) (r / h) 1.2e-7; 0.07 keeps it under 1e-5 out to r = 6 h)
+    AUTO_SPLIT_BELOW = 0.07
 
     def __init__(self, kernel="gaussian", bw=1.0, cutoff=None, dtype="auto"):
         if kernel not in _KERNEL_ALIASES:
@@ -67,8 +73,9 @@ class TreeKDE:
             raise ValueError("bw must be a scalar or a 1-D array")
         self.bw = bw
         self.cutoff = cutoff
-        if dtype not in ("auto", "float32", "float32x2", "float64"):
-            raise ValueError("dtype must be 'auto', 'float32', 'float32x2' or 'float64'")
+        if dtype not in ("auto", "float32", "float32x2", "float32_dense", "float64"):
+            raise ValueError("dtype must be 'auto', 'float32', 'float32x2', 'float32_dense' "
+                             "or 'float64'")
         self.dtype = dtype
         self.data = None
         self.weights = None
@@ -169,22 +176,64 @@ class TreeKDE:
             center = self.data.mean(axis=0)
         gauss = self.kernel == "gaussian"
         dtype = self.dtype
-        if dtype == "auto":
-            dtype = "float32"
-            if gauss and self.cutoff is None and N > 1:
-                spread = float(np.max(np.sqrt(np.average((self.data - center) ** 2, axis=0,
-                                                         weights=w))))
-                if hmin < self.AUTO_SPLIT_BELOW * spread:
-                    dtype = "float32x2"
         dev = {"N": N, "D": D, "center": center, "kernel": self.kernel, "dtype_spec": self.dtype,
                "cutoff": self._cutoff_radius(hmax) if gauss else 0.0,
-               "data_ref": self.data, "weights_ref": self.weights, "dtype": dtype,
+               "data_ref": self.data, "weights_ref": self.weights,
                "cutoff_spec": self.cutoff, "bw_scalar_snap": bw_scalar,
                "bw_snap": None if bw_arr is None else bw_arr.copy()}
         d_data = _lib.to_dev(self.data)
         d_w = _lib.to_dev(w) if w is not None else None
         d_bw = _lib.to_dev(bw_arr) if bw_arr is not None else None
         w_scale = 1.0 / sumw
+        st = _lib.stream()
+        if dtype in ("auto", "float32"):
+            # ordered tiles: column ranges -> Hilbert order -> tiles with boxes and centres
+            mm_scr = _lib.empty(L.kdsb200_minmax_scratch(), t.float64)
+            mm = _lib.empty(2 * D, t.float64)
+            _lib.check(L.kdsb200_column_minmax(_lib.ptr(d_data), N, D, _lib.ptr(mm_scr),
+                                               _lib.ptr(mm), st))
+            mmh = mm.cpu().numpy()
+            lo_keep, lo_p = _lib.hostvec(mmh[:D])
+            hi_keep, hi_p = _lib.hostvec(mmh[D:])
+            maxabs = float(max(np.max(np.abs(mmh[:D] - center)), np.max(np.abs(mmh[D:] - center)),
+                               1e-300))
+            # hi parts and tile centres live on the grid 2^-S with |x - c| 2^S < 2^20 (spare
+            # bits for query points outside the sources' bounding box)
+            grid = float(2.0 ** (20 - int(np.ceil(np.log2(maxabs)))))
+            perm = _lib.empty(N, t.int32)
+            scr = _lib.empty(L.kdsb200_order_scratch_bytes(N), t.uint8)
+            _lib.check(L.kdsb200_hilbert_order(_lib.ptr(d_data), N, D, lo_p, hi_p, _lib.ptr(scr),
+                                               _lib.ptr(perm), st))
+            del scr
+            ntl = (N + 511) // 512
+            sc = 1.0 if gauss else _SUPPORT_SCALE[self.kernel]
+            d_h = d_bw if gauss or d_bw is None else _lib.to_dev(bw_arr * sc)
+            lc_ref = np.log2(wmax * w_scale) - D * np.log2(hmin * sc)
+            packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
+            tilebox = _lib.empty(ntl * 2 * D, t.float32)
+            tilecen = _lib.empty(ntl * D, t.float32)
+            cen_keep, cen_p = _lib.hostvec(center)
+            _lib.check(L.kdsb200_pack_sources_sorted_f32(
+                _lib.ptr(d_data), _lib.ptr(d_w), _lib.ptr(d_h), bw_scalar * sc, N, D,
+                _lib.ptr(perm), cen_p, grid, w_scale, lc_ref, 0 if gauss else 1,
+                _lib.ptr(packed), _lib.ptr(tilebox), _lib.ptr(tilecen), st))
+            box = tilebox.cpu().numpy().reshape(ntl, 2, D)
+            extent = float(np.max(box[:, 1] - box[:, 0])) / 2 if N > 1 else 0.0
+            if (dtype == "auto" and gauss and self.cutoff is None
+                    and hmin < self.AUTO_SPLIT_BELOW * extent):
+                dtype = "float32x2"  # tiles too wide for this bandwidth: split coordinates
+            else:
+                dtype = "float32"
+                if gauss:
+                    norm = (2 * np.pi) ** (-D / 2)
+                else:
+                    norm = (0.5 * (D + 2) if self.kernel == "epa" else 1.0) / unit_ball_volume(D)
+                dev.update(packed=packed, tilebox=tilebox, tilecen=tilecen, grid=grid,
+                           lo=mmh[:D].copy(), hi=mmh[D:].copy(), tile_extent=extent,
+                           out_scale=float(2.0 ** lc_ref * norm),
+                           cull=dev["cutoff"] if gauss else hmax * sc)
+            del perm
+        dev["dtype"] = dtype
         if dtype == "float32x2":
             if not gauss:
                 raise ValueError("dtype='float32x2' is implemented for the gaussian kernel")
@@ -203,7 +252,9 @@ class TreeKDE:
                 w_scale, lc_ref, dev["grid"], _lib.ptr(packed), _lib.stream()))
             dev["packed"] = packed
             dev["out_scale"] = float(2.0 ** lc_ref * (2 * np.pi) ** (-D / 2))
-        elif dtype == "float32" and gauss:
+        elif dtype == "float32":
+            pass  # packed above
+        elif dtype == "float32_dense" and gauss:
             lc_ref = np.log2(wmax * w_scale) - D * np.log2(hmin)
             packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
             cen_keep, cen_p = _lib.hostvec(center)
@@ -212,7 +263,7 @@ class TreeKDE:
                 w_scale, lc_ref, 0, _lib.ptr(packed), _lib.stream()))
             dev["packed"] = packed
             dev["out_scale"] = float(2.0 ** lc_ref * (2 * np.pi) ** (-D / 2))
-        elif dtype == "float32":
+        elif dtype == "float32_dense":
             # finite-support kernels: linear coefficients w_i R_i^-D / 2^lc_ref (mode 1)
             # with the support radius R_i in place of the bandwidth
             sc = _SUPPORT_SCALE[self.kernel]
@@ -255,6 +306,32 @@ class TreeKDE:
                 _lib.ptr(dev["packed"]), N, D, _lib.ptr(qT), M, Mpad, dev["out_scale"], nsplit,
                 _lib.ptr(partial), _lib.ptr(d_out), _lib.stream()))
         elif dev["dtype"] == "float32":
+            st = _lib.stream()
+            Mpad = L.kdsb200_sorted_qpad(M)
+            lo_keep, lo_p = _lib.hostvec(dev["lo"])
+            hi_keep, hi_p = _lib.hostvec(dev["hi"])
+            cen_keep, cen_p = _lib.hostvec(dev["center"])
+            perm_q = _lib.empty(M, t.int32)
+            scr = _lib.empty(L.kdsb200_order_scratch_bytes(M), t.uint8)
+            _lib.check(L.kdsb200_hilbert_order(_lib.ptr(d_pts), M, D, lo_p, hi_p, _lib.ptr(scr),
+                                               _lib.ptr(perm_q), st))
+            qT = _lib.empty(Mpad * 2 * D, t.float32)
+            _lib.check(L.kdsb200_pack_queries_sorted_f32(_lib.ptr(d_pts), M, Mpad, D,
+                                                         _lib.ptr(perm_q), cen_p, dev["grid"],
+                                                         _lib.ptr(qT), st))
+            nsplit = L.kdsb200_sorted_nsplit(N, M)
+            scratch = _lib.empty(L.kdsb200_sorted_scratch_bytes(N, Mpad, nsplit), t.uint8)
+            visited = _lib.empty(1, t.int64)
+            _lib.check(L.kdsb200_kde_eval_sorted_f32(
+                _lib.ptr(dev["packed"]), _lib.ptr(dev["tilebox"]), _lib.ptr(dev["tilecen"]), N, D,
+                _lib.ptr(qT), _lib.ptr(perm_q), M, Mpad, _KERNEL_ID[dev["kernel"]], dev["cull"],
+                dev["out_scale"], nsplit, _lib.ptr(scratch), _lib.ptr(d_out), _lib.ptr(visited),
+                st))
+            #: device counter of the last call: tiles loaded, summed over the (1024-query
+            #: block, source split) work items; executed pairs = that * 512 * 1024
+            self.last_tiles_visited = visited
+            self.last_work_items_pairs = 512 * 1024
+        elif dev["dtype"] == "float32_dense":
             Mpad = L.kdsb200_eval_mpad(M)
             qT = _lib.empty(Mpad * D, t.float32)
             cen_keep, cen_p = _lib.hostvec(dev["center"])

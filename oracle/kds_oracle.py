@@ -600,6 +600,46 @@ def ref_sampler_cli(parts8, weights, pdg, metrics, kernel, bw, nout, seed=1, pt=
     return out8, outw
 
 
+def hilbert_keys(data, lo, hi, bits):
+    """Hilbert-curve index of every row of `data` over the box [lo, hi] quantised to `bits`
+    per dimension (Skilling, "Programming the Hilbert curve", 2004: axes -> transpose,
+    then bit interleave).  Checker for the ordering the sorted-tile layout uses; the
+    ordering has no counterpart in the reference (it only changes the summation order)."""
+    data = np.asarray(data, dtype=np.float64)
+    n, D = data.shape
+    span = np.asarray(hi, dtype=np.float64) - np.asarray(lo, dtype=np.float64)
+    scale = np.where(span > 0, float(1 << bits) / np.where(span > 0, span, 1.0), 0.0)
+    X = np.clip(np.floor((data - lo) * scale), 0, (1 << bits) - 1).astype(np.uint64)
+    M = np.uint64(1) << np.uint64(bits - 1)
+    one = np.uint64(1)
+    Q = M
+    while Q > one:
+        P = Q - one
+        for i in range(D):
+            bit = (X[:, i] & Q) != 0
+            X[bit, 0] ^= P
+            t = (X[:, 0] ^ X[:, i]) & P
+            t[bit] = 0
+            X[:, 0] ^= t
+            X[:, i] ^= t
+        Q >>= one
+    for i in range(1, D):
+        X[:, i] ^= X[:, i - 1]
+    t = np.zeros(n, dtype=np.uint64)
+    Q = M
+    while Q > one:
+        sel = (X[:, D - 1] & Q) != 0
+        t[sel] ^= Q - one
+        Q >>= one
+    for i in range(D):
+        X[:, i] ^= t
+    key = np.zeros(n, dtype=np.uint64)
+    for b in range(bits - 1, -1, -1):
+        for i in range(D):
+            key = (key << one) | ((X[:, i] >> np.uint64(b)) & one)
+    return key
+
+
 # ----------------------------------------------------------------------
 # synthetic data generator (SURVEY 8d; Verification.ipynb cell 4, seeded)
 # ----------------------------------------------------------------------

@@ -72,9 +72,14 @@ def test_evaluate_cutoff_and_dims(oracle):
     ref = oracle.kde_sum_c(data, None, 0.4, q, cutoff=r)
     got = TreeKDE(bw=0.4, cutoff=r).fit(data).evaluate(q)
     ok = ref > 0
-    # a pair exactly at the radius may fall on either side in fp32: compare sums
+    # a pair within fp32 rounding of the radius may fall on either side; every query
+    # without such a pair is held to 1e-5
+    dist = np.sqrt(((q[:, None, :] - data[None, :, :]) ** 2).sum(axis=2))
+    clear = ok & (np.min(np.abs(dist - r), axis=1) > 1e-5 * r)
+    assert clear.sum() > 0.9 * ok.sum()
+    assert np.max(np.abs(got[clear] / ref[clear] - 1)) < 1e-5
     assert np.max(np.abs(got[ok] / ref[ok] - 1)) < 1e-3
-    assert np.median(np.abs(got[ok] / ref[ok] - 1)) < 1e-5
+    assert np.array_equal(got[~ok], ref[~ok])
     # ragged / tiny inputs
     assert len(TreeKDE(bw=0.4).fit(data).evaluate(np.zeros((0, 6)))) == 0
     one = TreeKDE(bw=0.4).fit(data[:1]).evaluate(data[:1])
@@ -95,11 +100,14 @@ def test_evaluate_split_precision_small_bandwidth(oracle, scaled):
     for name, bw in (("scalar", 0.03), ("adaptive", rng.uniform(0.02, 0.05, len(data)))):
         ref = oracle.kde_sum_c(data, w, bw, q)
         ok = ref > 1e-12 * ref.max()
-        for dt in ("float32", "float32x2"):
+        for dt in ("float32_dense", "float32", "float32x2"):
             got = TreeKDE(bw=bw, dtype=dt).fit(data, w).evaluate(q)
             errs[name, dt] = float(np.max(np.abs(got[ok] / ref[ok] - 1)))
         assert errs[name, "float32x2"] < 4e-6, errs
-        assert errs[name, "float32x2"] < 0.2 * errs[name, "float32"], errs
+        assert errs[name, "float32x2"] < 0.2 * errs[name, "float32_dense"], errs
+        # tile-local coordinates: better than the unordered kernel (the tiles of a
+        # 20000-point list are still wide, so not yet the split kernel's accuracy)
+        assert errs[name, "float32"] < errs[name, "float32_dense"], errs
     for d in (1, 2, 3, 5, 7, 8):
         X = rng.normal(size=(3000, d)) * 3 + 50.0  # far from the origin: recentring matters
         Q = X[:700] + rng.normal(scale=0.1, size=(700, d))
@@ -172,6 +180,93 @@ def test_evaluate_linearity_at_scale(oracle):
     dB = TreeKDE(bw=0.3).fit(B).evaluate(q)
     dAB = TreeKDE(bw=0.3).fit(np.concatenate((A, B))).evaluate(q)
     assert np.allclose(dAB, 0.6 * dA + 0.4 * dB, rtol=1e-5)
+
+
+def test_hilbert_order_matches_oracle(oracle):
+    """kdsb200_hilbert_order: the device keys + stable radix sort give exactly the
+    permutation of a stable argsort of the oracle's keys (D = 1..8, ragged sizes)."""
+    from kdsource_b200 import _lib
+
+    L = _lib.load()
+    t = _lib.torch()
+    rng = np.random.default_rng(17)
+    for D, N in ((1, 1000), (2, 1), (3, 1025), (6, 70001), (7, 4096), (8, 33)):
+        data = rng.normal(size=(N, D))
+        if N > 10:
+            data[5] = data[3]  # equal keys: the sort must be stable
+        lo, hi = data.min(axis=0), data.max(axis=0)
+        if N > 40:  # points outside the quantisation box are clamped
+            lo, hi = np.quantile(data, 0.02, axis=0), np.quantile(data, 0.98, axis=0)
+        bits = int(L.kdsb200_hilbert_bits(D))
+        keys = oracle.hilbert_keys(data, lo, hi, bits)
+        d_data = _lib.to_dev(data)
+        perm = _lib.empty(N, t.int32)
+        scr = _lib.empty(L.kdsb200_order_scratch_bytes(N), t.uint8)
+        lo_k, lo_p = _lib.hostvec(lo)
+        hi_k, hi_p = _lib.hostvec(hi)
+        _lib.check(L.kdsb200_hilbert_order(_lib.ptr(d_data), N, D, lo_p, hi_p, _lib.ptr(scr),
+                                           _lib.ptr(perm), _lib.stream()))
+        assert np.array_equal(perm.cpu().numpy(), np.argsort(keys, kind="stable")), (D, N)
+    # column min / max
+    mm = _lib.empty(12, t.float64)
+    scr = _lib.empty(L.kdsb200_minmax_scratch(), t.float64)
+    data = rng.normal(size=(70001, 6))
+    _lib.check(L.kdsb200_column_minmax(_lib.ptr(_lib.to_dev(data)), len(data), 6, _lib.ptr(scr),
+                                       _lib.ptr(mm), _lib.stream()))
+    assert np.array_equal(mm.cpu().numpy(), np.r_[data.min(axis=0), data.max(axis=0)])
+
+
+@pytest.mark.parametrize("bwkind", ["scalar", "adaptive"])
+def test_evaluate_tile_culling_is_exact(oracle, bwkind):
+    """cutoff mode on the ordered tiles: tiles beyond the radius are skipped (most of them,
+    for a compact query block) and the result is the hard-cutoff sum of the oracle to 1e-5
+    for every query without a pair within rounding of the radius; the KDEpy-like bracket
+    S(r / (1 + eps)) <= S(r) <= S(r (1 + eps)) holds on the GPU path."""
+    from kdsource_b200.treekde import TreeKDE, treekde_radius
+
+    rng = np.random.default_rng(33)
+    N, M, D = 150_000, 3000, 6
+    data = rng.normal(size=(N, D))
+    w = rng.uniform(0.5, 1.5, N)
+    q = rng.normal(size=(M, D)) * 0.8
+    q[:20] += 30.0  # far outside: no tile within the radius, density exactly 0
+    bw = 0.3 if bwkind == "scalar" else rng.uniform(0.2, 0.3, N)
+    r = treekde_radius(0.3)
+    k = TreeKDE(bw=bw, cutoff=r).fit(data, w)
+    got = k.evaluate(q)
+    ref = oracle.kde_sum_c(data, w, bw, q, cutoff=r)
+    visited = int(k.last_tiles_visited.item())
+    dense = -(-N // 512) * -(-M // 1024)
+    assert 0 < visited < 0.7 * dense, (visited, dense)
+    assert np.all(got[:20] == 0) and np.all(ref[:20] == 0)
+    sub = rng.choice(np.arange(20, M), 400, replace=False)
+    gap = np.array([np.min(np.abs(np.sqrt(((data - q[m]) ** 2).sum(axis=1)) - r)) for m in sub])
+    idx = sub[(gap > 1e-5 * r) & (ref[sub] > 0)]
+    assert len(idx) > 300
+    assert np.max(np.abs(got[idx] / ref[idx] - 1)) < 1e-5
+    pos = ref > 0
+    assert np.max(np.abs(got[pos] / ref[pos] - 1)) < 2e-3
+    # bracket (tests/test_oracle.py checks the same on the CPU tree variant)
+    eps = 1e-3
+    lo = TreeKDE(bw=bw, cutoff=r / (1 + eps)).fit(data, w).evaluate(q)
+    hi = TreeKDE(bw=bw, cutoff=r * (1 + eps)).fit(data, w).evaluate(q)
+    assert np.all(lo <= got * (1 + 1e-6)) and np.all(got <= hi * (1 + 1e-6))
+    exact = TreeKDE(bw=bw).fit(data, w).evaluate(q)
+    assert np.all(hi <= exact * (1 + 1e-6))
+    # the exact sum over the ordered tiles against the oracle
+    ref_x = oracle.kde_sum_c(data, w, bw, q[20:600])
+    assert np.max(np.abs(exact[20:600] / ref_x - 1)) < 1e-5
+    # finite-support kernels are culled at their support radius
+    for kern in ("epa", "box"):
+        ke = TreeKDE(kernel=kern, bw=0.3).fit(data[:60000], w[:60000])
+        g = ke.evaluate(q[:1500])
+        rf = oracle.kde_sum(data[:60000], w[:60000], 0.3, q[:1500], kernel=kern)
+        assert int(ke.last_tiles_visited.item()) < 0.8 * (-(-60000 // 512)) * 2
+        big = rf > 1e-2 * rf.max()
+        if kern == "epa":
+            assert np.max(np.abs(g[big] / rf[big] - 1)) < 1e-4
+        else:
+            assert np.mean(np.abs(g[big] - rf[big]) <= 1e-5 * rf[big]) > 0.98
 
 
 # ---------------------------------------------------------------------- MLCV

@@ -317,3 +317,16 @@ def test_oracle_evaluate_vs_reference_kdsource(oracle, golden_kdsource, tmp_path
                              float(g["g_bw"]), scaling, 3.5, float(g["g_N_eff"]), 6)
     assert np.allclose(ev, g["g_evaluate"], rtol=1e-12)
     assert np.allclose(er, g["g_evaluate_err"], rtol=1e-12)
+
+
+def test_hilbert_keys_visit_neighbouring_cells(oracle):
+    """The ordering used by the sorted-tile layout is a Hilbert curve: consecutive keys are
+    face-adjacent cells (checked exhaustively on small grids)."""
+    import itertools
+
+    for D, b in ((1, 5), (2, 4), (3, 3), (6, 2)):
+        cells = np.array(list(itertools.product(range(2 ** b), repeat=D)), dtype=np.float64)
+        k = oracle.hilbert_keys(cells + 0.5, np.zeros(D), np.full(D, 2.0 ** b), b)
+        assert len(np.unique(k)) == len(k) and k.max() == len(k) - 1
+        walk = cells[np.argsort(k)]
+        assert np.all(np.abs(np.diff(walk, axis=0)).sum(axis=1) == 1)
