@@ -225,19 +225,20 @@ def test_evaluate_tile_culling_is_exact(oracle, bwkind, D):
     from kdsource_b200.treekde import TreeKDE, treekde_radius
 
     rng = np.random.default_rng(33)
-    N, M = 150_000, 30_000
+    N, M = 150_000, (100_000 if D == 3 else 30_000)
+    h = 0.1 if D == 3 else 0.3
     data = rng.normal(size=(N, D))
     w = rng.uniform(0.5, 1.5, N)
     q = rng.normal(size=(M, D)) * 0.8
     q[:20] += 30.0  # far outside: no tile within the radius, density exactly 0
-    bw = 0.3 if bwkind == "scalar" else rng.uniform(0.2, 0.3, N)
-    r = treekde_radius(0.3)
+    bw = h if bwkind == "scalar" else rng.uniform(0.7 * h, h, N)
+    r = treekde_radius(h)
     k = TreeKDE(bw=bw, cutoff=r).fit(data, w)
     got = k.evaluate(q)
     ref = oracle.kde_sum_c(data, w, bw, q, cutoff=r)
     visited = int(k.last_tiles_visited.item())
     dense = -(-N // 512) * -(-M // 1024)
-    # three dimensions: 293 tiles and 30 query blocks are compact against the radius and
+    # three dimensions: 293 tiles and 98 query blocks are compact against the radius and
     # most tile visits are skipped; in six dimensions a list of this size has tiles as wide
     # as the radius and little can be skipped (the saving grows with N and M)
     assert 0 < visited <= dense
@@ -265,11 +266,12 @@ def test_evaluate_tile_culling_is_exact(oracle, bwkind, D):
         return
     # finite-support kernels are culled at their support radius
     for kern in ("epa", "box"):
-        ke = TreeKDE(kernel=kern, bw=0.3).fit(data[:60000], w[:60000])
+        ke = TreeKDE(kernel=kern, bw=h).fit(data[:60000], w[:60000])
         g = ke.evaluate(q[:4096])
-        rf = oracle.kde_sum(data[:60000], w[:60000], 0.3, q[:4096], kernel=kern)
+        rf = oracle.kde_sum(data[:60000], w[:60000], h, q[:4096], kernel=kern)
         if D == 3:
-            assert int(ke.last_tiles_visited.item()) < 0.6 * (-(-60000 // 512)) * 4
+            ke.evaluate(q)
+            assert int(ke.last_tiles_visited.item()) < 0.5 * (-(-60000 // 512)) * -(-M // 1024)
         big = rf > 1e-2 * rf.max()
         if kern == "epa":
             assert np.max(np.abs(g[big] / rf[big] - 1)) < 1e-4
