@@ -166,11 +166,16 @@ uint64_t kdsb200_mlcv_f64_blocks(uint64_t M);
 int kdsb200_mlcv_f64_gtile(int G);
 int kdsb200_mlcv_coef_f64(const double* d_w, const double* d_bw, double bw_scalar, uint64_t N,
                           int D, double w_scale, double* d_coef2n, void* stream);
+/* d_fix_scratch: kdsb200_mlcv_fix_scratch_bytes(M) bytes, needed when d_rowmask != NULL
+ * (the first 256 row blocks with flagged rows are recomputed by 64 CTAs each, over
+ * slices of the list, and combined in slice order). */
+uint64_t kdsb200_mlcv_fix_scratch_bytes(uint64_t M);
 int kdsb200_mlcv_rows_f64(const double* d_data, const double* d_coef2n, uint64_t N, int D,
                           uint64_t row0, uint64_t M, const int32_t* d_excl_lo,
                           const int32_t* d_excl_hi, const double* d_coefw, const double* d_lwtr,
                           const double* h_grid, int G, double log_shift,
-                          const uint32_t* d_rowmask, double* d_partial, void* stream);
+                          const uint32_t* d_rowmask, void* d_fix_scratch, double* d_partial,
+                          void* stream);
 /* Fold bookkeeping of the test rows [row0, row0+M) built on the device: sklearn
  * KFold(n_splits=K) without shuffle (kde.py:134-136).  d_cwf[f] = 1/(n_f K),
  * d_lwt[f] = ln(training weight of fold f), d_w (N) or NULL.  Outputs have Mpad entries. */
@@ -178,11 +183,13 @@ int kdsb200_mlcv_rows_setup(uint64_t N, uint64_t K, uint64_t row0, uint64_t M, u
                             const double* d_w, const double* d_cwf, const double* d_lwt,
                             int32_t* d_lo, int32_t* d_hi, double* d_coefw, double* d_lwtr,
                             void* stream);
-/* d_out[g] (g < G) = sum of the rows of d_a[na][gt_a] and, if given, d_b[nb][gt_b]; one
- * CTA, fixed summation order: the on-stream reduction ahead of the NCCL all-reduce of
- * the G partial log-likelihoods. */
+/* d_out[g] (g < G) = sum of the rows of d_a[na][gt_a] and, if given, d_b[nb][gt_b]; fixed
+ * summation order (128 CTAs over contiguous shares, then one): the on-stream reduction
+ * ahead of the NCCL all-reduce of the G partial log-likelihoods.  d_tmp:
+ * kdsb200_mlcv_reduce_scratch() doubles. */
+uint64_t kdsb200_mlcv_reduce_scratch(void);
 int kdsb200_mlcv_reduce(const double* d_a, uint64_t na, int gt_a, const double* d_b, uint64_t nb,
-                        int gt_b, int G, double* d_out, void* stream);
+                        int gt_b, int G, double* d_tmp, double* d_out, void* stream);
 
 /* ---- kNN: NearestNeighbors(k+1).kneighbors inside batches (kde.py:91-98) -- */
 /* d_data (N,D) fp64 row-major; d_batch_off: nb+1 int64 offsets (np.array_split

@@ -150,14 +150,16 @@ _SIGNATURES = {
     "kdsb200_mlcv_f64_gtile": (c_int, [c_int]),
     "kdsb200_mlcv_coef_f64": (c_int, [c_void_p, c_void_p, c_double, c_u64, c_int, c_double,
                                       c_void_p, c_void_p]),
+    "kdsb200_mlcv_fix_scratch_bytes": (c_u64, [c_u64]),
     "kdsb200_mlcv_rows_f64": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_u64, c_u64, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_double_p, c_int, c_double,
-                                      c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kdsb200_mlcv_reduce_scratch": (c_u64, []),
     "kdsb200_mlcv_rows_setup": (c_int, [c_u64, c_u64, c_u64, c_u64, c_u64, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p]),
     "kdsb200_mlcv_reduce": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_u64, c_int, c_int,
-                                    c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p]),
     "kdsb200_moments_scratch": (c_u64, []),
     "kdsb200_weighted_moments": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_double_p, c_int,
                                          c_void_p, c_void_p, c_void_p]),

@@ -252,31 +252,100 @@ struct GridParams {
   double inv_g2[GT];  // 1 / grid[g]^2
 };
 
-template <int D, int GT>
+// Rows flagged by the fp32 kernel are usually a handful of isolated tail points, and one
+// warp walking the whole list for each of them would take ~0.1 ms per 1000 sources.  The
+// row blocks that hold flagged rows therefore get a slot each (ordered, so the result does
+// not depend on scheduling); the first R64_CAP of them are recomputed by R64_NSPLIT CTAs
+// per block, each over a slice of the sources, and combined in a fixed order.
+constexpr int R64_CAP = 256;
+constexpr int R64_NSPLIT = 64;
+
+// slots[b] = rank of row block b among the blocks with a flagged row (-1: none);
+// slot_block[slot] = b for slot < R64_CAP; *count = number of such blocks.  One CTA.
+__global__ void __launch_bounds__(256)
+    mlcv_assign_slots_kernel(const uint32_t* __restrict__ rowmask, uint64_t M, int G,
+                             uint64_t nblocks, int32_t* __restrict__ slots,
+                             int32_t* __restrict__ slot_block, int32_t* __restrict__ count) {
+  __shared__ uint32_t wcnt[8];
+  __shared__ uint32_t run;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t gm = G < 32 ? (1u << G) - 1u : 0xffffffffu;
+  if (threadIdx.x == 0) run = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < nblocks; base += 256) {
+    const uint64_t b = base + threadIdx.x;
+    bool any = false;
+    if (b < nblocks)
+      for (int r = 0; r < R64_WARPS; r++) {
+        const uint64_t m = b * R64_WARPS + r;
+        if (m < M && (rowmask[m] & gm)) any = true;
+      }
+    const uint32_t bal = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t off = run;
+    for (int w = 0; w < warp; w++) off += wcnt[w];
+    if (b < nblocks) {
+      const int32_t slot = any ? (int32_t)(off + __popc(bal & ((1u << lane) - 1u))) : -1;
+      slots[b] = slot;
+      if (slot >= 0 && slot < R64_CAP) slot_block[slot] = (int32_t)b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+      for (int w = 0; w < 8; w++) tot += wcnt[w];
+      run += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = (int32_t)run;
+}
+
+// MODE 0: every row block b = blockIdx.x over the whole list (the fp64 mode, and in the
+//         recomputation the blocks beyond R64_CAP; blocks with a slot below the cap are
+//         left to MODE 1; blocks without flagged rows write zeros).
+// MODE 1: blockIdx.x = slot, blockIdx.y = source slice; raw partial sums go to sfix.
+template <int D, int GT, int MODE>
 __global__ void __launch_bounds__(R64_THREADS)
     mlcv_rows_f64_kernel(const double* __restrict__ data, const double* __restrict__ coef,
                          const double* __restrict__ ih2, uint64_t N, uint64_t row0, uint64_t M,
                          const int32_t* __restrict__ excl_lo, const int32_t* __restrict__ excl_hi,
                          const double* __restrict__ coefw, const double* __restrict__ lwtr,
                          GridParams<GT> P, int G, double log_shift,
-                         const uint32_t* __restrict__ rowmask, double* __restrict__ partial) {
+                         const uint32_t* __restrict__ rowmask, const int32_t* __restrict__ slots,
+                         const int32_t* __restrict__ slot_block,
+                         const int32_t* __restrict__ slot_count, double* __restrict__ sfix,
+                         double* __restrict__ partial) {
   __shared__ double sx[D * R64_TILE];
   __shared__ double sc[R64_TILE];
   __shared__ double sh[R64_TILE];
   __shared__ double contrib[R64_WARPS][GT];
   __shared__ int any_live;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint64_t m = (uint64_t)blockIdx.x * R64_WARPS + warp;
+  uint64_t blk = blockIdx.x;
+  uint64_t j0 = 0, j1 = N;
+  if (MODE == 1) {
+    const int cnt = min(*slot_count, R64_CAP);
+    if ((int)blockIdx.x >= cnt) return;
+    blk = (uint64_t)slot_block[blockIdx.x];
+    const uint64_t per = (N + R64_NSPLIT - 1) / R64_NSPLIT;
+    j0 = min(N, (uint64_t)blockIdx.y * per);
+    j1 = min(N, j0 + per);
+  }
+  const uint64_t m = blk * R64_WARPS + warp;
   uint32_t mask = 0;
   if (m < M) mask = rowmask ? rowmask[m] : 0xffffffffu;
   if (G < 32) mask &= (1u << G) - 1u;
-  if (threadIdx.x == 0) any_live = 0;
-  __syncthreads();
-  if (mask && lane == 0) any_live = 1;
-  __syncthreads();
-  if (!any_live) {  // CTA-uniform: nothing flagged among these rows
-    if (threadIdx.x < GT) partial[(uint64_t)blockIdx.x * GT + threadIdx.x] = 0.0;
-    return;
+  if (MODE == 0) {
+    if (threadIdx.x == 0) any_live = 0;
+    __syncthreads();
+    if (mask && lane == 0) any_live = 1;
+    __syncthreads();
+    if (!any_live) {  // CTA-uniform: nothing flagged among these rows
+      if (threadIdx.x < GT) partial[blk * GT + threadIdx.x] = 0.0;
+      return;
+    }
+    if (slots && slots[blk] < R64_CAP) return;  // recomputed by the sliced launch
   }
   double q[D];
 #pragma unroll
@@ -286,8 +355,8 @@ __global__ void __launch_bounds__(R64_THREADS)
 #pragma unroll
   for (int g = 0; g < GT; g++) acc[g] = 0.0;
 
-  for (uint64_t base = 0; base < N; base += R64_TILE) {
-    const int cnt = (int)min((uint64_t)R64_TILE, N - base);
+  for (uint64_t base = j0; base < j1; base += R64_TILE) {
+    const int cnt = (int)min((uint64_t)R64_TILE, j1 - base);
     __syncthreads();
     for (int e = threadIdx.x; e < cnt * D; e += R64_THREADS)
       sx[(e % D) * R64_TILE + e / D] = data[base * D + e];
@@ -318,14 +387,53 @@ __global__ void __launch_bounds__(R64_THREADS)
     double v = acc[g];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if (lane == 0) contrib[warp][g] = ((mask >> g) & 1u) ? cw * (log(v) + log_shift - lw) : 0.0;
+    if (lane == 0) {
+      if (MODE == 1)
+        sfix[(((uint64_t)blockIdx.x * R64_NSPLIT + blockIdx.y) * R64_WARPS + warp) * GT + g] = v;
+      else
+        contrib[warp][g] = ((mask >> g) & 1u) ? cw * (log(v) + log_shift - lw) : 0.0;
+    }
+  }
+  if (MODE == 1) return;
+  __syncthreads();
+  if (threadIdx.x < GT) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < R64_WARPS; w++) t += contrib[w][threadIdx.x];
+    partial[blk * GT + threadIdx.x] = t;
+  }
+}
+
+// sums the source slices of the sliced launch in slice order and writes the row blocks'
+// contributions; grid = R64_CAP CTAs of R64_THREADS threads
+template <int GT>
+__global__ void __launch_bounds__(R64_THREADS)
+    mlcv_combine_slices_kernel(const double* __restrict__ sfix, const int32_t* __restrict__ slot_block,
+                               const int32_t* __restrict__ slot_count,
+                               const uint32_t* __restrict__ rowmask, uint64_t M, int G,
+                               const double* __restrict__ coefw, const double* __restrict__ lwtr,
+                               double log_shift, double* __restrict__ partial) {
+  __shared__ double contrib[R64_WARPS][GT];
+  const int cnt = min(*slot_count, R64_CAP);
+  if ((int)blockIdx.x >= cnt) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t blk = (uint64_t)slot_block[blockIdx.x];
+  const uint64_t m = blk * R64_WARPS + warp;
+  uint32_t mask = m < M ? rowmask[m] : 0u;
+  if (G < 32) mask &= (1u << G) - 1u;
+  const double cw = mask ? coefw[m] : 0.0, lw = mask ? lwtr[m] : 0.0;
+  for (int g = lane; g < GT; g += 32) {
+    double S = 0.0;
+    for (int sl = 0; sl < R64_NSPLIT; sl++)
+      S += sfix[(((uint64_t)blockIdx.x * R64_NSPLIT + sl) * R64_WARPS + warp) * GT + g];
+    contrib[warp][g] = ((mask >> g) & 1u) ? cw * (log(S) + log_shift - lw) : 0.0;
   }
   __syncthreads();
   if (threadIdx.x < GT) {
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < R64_WARPS; w++) t += contrib[w][threadIdx.x];
-    partial[(uint64_t)blockIdx.x * GT + threadIdx.x] = t;
+    partial[blk * GT + threadIdx.x] = t;
   }
 }
 
@@ -375,39 +483,78 @@ __global__ void mlcv_rows_setup_kernel(uint64_t N, uint64_t K, uint64_t row0, ui
   lwtr[m] = lwt[f];
 }
 
-// out[g] = sum over the rows of a[na][gt_a] and b[nb][gt_b], g < G, in a fixed order (one CTA)
+// out[g] = sum over the rows of a[na][gt_a] and b[nb][gt_b], g < G, in a fixed order:
+// RED_CTAS CTAs each sum a contiguous share of the rows into tmp[cta][32], then one CTA
+// adds the shares in order
+constexpr int RED_CTAS = 128;
 __global__ void __launch_bounds__(256)
-    mlcv_reduce_kernel(const double* __restrict__ a, uint64_t na, int gt_a,
-                       const double* __restrict__ b, uint64_t nb, int gt_b, int G,
-                       double* __restrict__ out) {
+    mlcv_reduce_stage1_kernel(const double* __restrict__ a, uint64_t na, int gt_a,
+                              const double* __restrict__ b, uint64_t nb, int gt_b, int G,
+                              double* __restrict__ tmp) {
   __shared__ double sm[256];
+  const uint64_t pa = (na + RED_CTAS - 1) / RED_CTAS, pb = (nb + RED_CTAS - 1) / RED_CTAS;
+  const uint64_t a0 = min(na, blockIdx.x * pa), a1 = min(na, a0 + pa);
+  const uint64_t b0 = min(nb, blockIdx.x * pb), b1 = min(nb, b0 + pb);
   for (int g = 0; g < G; g++) {
     double s = 0.0;
-    for (uint64_t r = threadIdx.x; r < na; r += 256) s += a[r * gt_a + g];
+    for (uint64_t r = a0 + threadIdx.x; r < a1; r += 256) s += a[r * gt_a + g];
     if (b)
-      for (uint64_t r = threadIdx.x; r < nb; r += 256) s += b[r * gt_b + g];
+      for (uint64_t r = b0 + threadIdx.x; r < b1; r += 256) s += b[r * gt_b + g];
     sm[threadIdx.x] = s;
     __syncthreads();
     for (int off = 128; off > 0; off >>= 1) {
       if ((int)threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
       __syncthreads();
     }
-    if (threadIdx.x == 0) out[g] = sm[0];
+    if (threadIdx.x == 0) tmp[blockIdx.x * 32 + g] = sm[0];
     __syncthreads();
   }
+}
+
+__global__ void mlcv_reduce_stage2_kernel(const double* __restrict__ tmp, int G,
+                                          double* __restrict__ out) {
+  const int g = threadIdx.x;
+  if (g >= G) return;
+  double s = 0.0;
+  for (int c = 0; c < RED_CTAS; c++) s += tmp[c * 32 + g];
+  out[g] = s;
 }
 
 template <int D, int GT>
 static int launch_rows_f64(const double* data, const double* coef, const double* ih2, uint64_t N,
                            uint64_t row0, uint64_t M, const int32_t* lo, const int32_t* hi,
                            const double* coefw, const double* lwtr, const double* h_grid, int G,
-                           double log_shift, const uint32_t* rowmask, double* partial,
-                           cudaStream_t st) {
+                           double log_shift, const uint32_t* rowmask, void* fix_scratch,
+                           double* partial, cudaStream_t st) {
   GridParams<GT> P;
   for (int g = 0; g < GT; g++) P.inv_g2[g] = g < G ? 1.0 / (h_grid[g] * h_grid[g]) : 0.0;
   const unsigned blocks = (unsigned)((M + R64_WARPS - 1) / R64_WARPS);
-  mlcv_rows_f64_kernel<D, GT><<<blocks, R64_THREADS, 0, st>>>(
-      data, coef, ih2, N, row0, M, lo, hi, coefw, lwtr, P, G, log_shift, rowmask, partial);
+  if (!rowmask) {  // fp64 mode: every row, one warp each
+    mlcv_rows_f64_kernel<D, GT, 0><<<blocks, R64_THREADS, 0, st>>>(
+        data, coef, ih2, N, row0, M, lo, hi, coefw, lwtr, P, G, log_shift, nullptr, nullptr,
+        nullptr, nullptr, nullptr, partial);
+    KDSB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  // recomputation of flagged rows: slots, sliced launch for the first R64_CAP row blocks,
+  // whole-list launch for the rest (and the zero fill), combine
+  unsigned char* p = (unsigned char*)fix_scratch;
+  int32_t* count = (int32_t*)p;
+  int32_t* slot_block = (int32_t*)(p + 64);
+  int32_t* slots = slot_block + R64_CAP;
+  double* sfix = (double*)(p + 64 + ((((uint64_t)R64_CAP + blocks) * 4 + 63) / 64) * 64);
+  mlcv_assign_slots_kernel<<<1, 256, 0, st>>>(rowmask, M, G, blocks, slots, slot_block, count);
+  KDSB_CUDA(cudaGetLastError());
+  mlcv_rows_f64_kernel<D, GT, 0><<<blocks, R64_THREADS, 0, st>>>(
+      data, coef, ih2, N, row0, M, lo, hi, coefw, lwtr, P, G, log_shift, rowmask, slots,
+      slot_block, count, sfix, partial);
+  KDSB_CUDA(cudaGetLastError());
+  mlcv_rows_f64_kernel<D, GT, 1><<<dim3(R64_CAP, R64_NSPLIT), R64_THREADS, 0, st>>>(
+      data, coef, ih2, N, row0, M, lo, hi, coefw, lwtr, P, G, log_shift, rowmask, slots,
+      slot_block, count, sfix, partial);
+  KDSB_CUDA(cudaGetLastError());
+  mlcv_combine_slices_kernel<GT><<<R64_CAP, R64_THREADS, 0, st>>>(
+      sfix, slot_block, count, rowmask, M, G, coefw, lwtr, log_shift, partial);
   KDSB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -602,11 +749,18 @@ int kdsb200_mlcv_coef_f64(const double* d_w, const double* d_bw, double bw_scala
   return 0;
 }
 
+uint64_t kdsb200_mlcv_fix_scratch_bytes(uint64_t M) {
+  const uint64_t blocks = (M + R64_WARPS - 1) / R64_WARPS;
+  return 64 + (((uint64_t)R64_CAP + blocks) * 4 + 63) / 64 * 64 +
+         (uint64_t)R64_CAP * R64_NSPLIT * R64_WARPS * 32 * sizeof(double);
+}
+
 int kdsb200_mlcv_rows_f64(const double* d_data, const double* d_coef2n, uint64_t N, int D,
                           uint64_t row0, uint64_t M, const int32_t* d_excl_lo,
                           const int32_t* d_excl_hi, const double* d_coefw, const double* d_lwtr,
                           const double* h_grid, int G, double log_shift,
-                          const uint32_t* d_rowmask, double* d_partial, void* stream) {
+                          const uint32_t* d_rowmask, void* d_fix_scratch, double* d_partial,
+                          void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0 || N == 0) return 0;
   if (G < 1 || G > 32) {
@@ -618,12 +772,17 @@ int kdsb200_mlcv_rows_f64(const double* d_data, const double* d_coef2n, uint64_t
               (unsigned long long)(row0 + M));
     return 1;
   }
+  if (d_rowmask && !d_fix_scratch) {
+    set_error("mlcv_rows_f64: the recomputation of flagged rows needs its scratch buffer");
+    return 1;
+  }
   const double* coef = d_coef2n;
   const double* ih2 = d_coef2n + N;
   const int GT = G <= 8 ? 8 : G <= 16 ? 16 : 32;
 #define KDSB_R64(d, gt)                                                                        \
   return launch_rows_f64<d, gt>(d_data, coef, ih2, N, row0, M, d_excl_lo, d_excl_hi, d_coefw, \
-                                d_lwtr, h_grid, G, log_shift, d_rowmask, d_partial, st)
+                                d_lwtr, h_grid, G, log_shift, d_rowmask, d_fix_scratch,       \
+                                d_partial, st)
 #define KDSB_CASE(d)                 \
   case d:                            \
     if (GT == 8) KDSB_R64(d, 8);     \
@@ -664,13 +823,18 @@ int kdsb200_mlcv_rows_setup(uint64_t N, uint64_t K, uint64_t row0, uint64_t M, u
 
 int kdsb200_mlcv_f64_gtile(int G) { return G <= 8 ? 8 : G <= 16 ? 16 : 32; }
 
+uint64_t kdsb200_mlcv_reduce_scratch(void) { return (uint64_t)RED_CTAS * 32; }
+
 int kdsb200_mlcv_reduce(const double* d_a, uint64_t na, int gt_a, const double* d_b, uint64_t nb,
-                        int gt_b, int G, double* d_out, void* stream) {
-  if (G < 1 || G > gt_a || (d_b && G > gt_b)) {
+                        int gt_b, int G, double* d_tmp, double* d_out, void* stream) {
+  if (G < 1 || G > 32 || G > gt_a || (d_b && G > gt_b)) {
     set_error("mlcv_reduce: G=%d does not fit the partial rows (%d, %d)", G, gt_a, gt_b);
     return 1;
   }
-  mlcv_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_a, na, gt_a, d_b, nb, gt_b, G, d_out);
+  cudaStream_t st = (cudaStream_t)stream;
+  mlcv_reduce_stage1_kernel<<<RED_CTAS, 256, 0, st>>>(d_a, na, gt_a, d_b, nb, gt_b, G, d_tmp);
+  KDSB_CUDA(cudaGetLastError());
+  mlcv_reduce_stage2_kernel<<<1, 32, 0, st>>>(d_tmp, G, d_out);
   KDSB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -260,6 +260,9 @@ class MLCVPlan:
         self.nblk = Mpad // 256
         self.nb64 = int(L.kdsb200_mlcv_f64_blocks(M))
         self.d_scores = _lib.empty(len(self.grid), t.float64)
+        self.red_tmp = _lib.empty(L.kdsb200_mlcv_reduce_scratch(), t.float64)
+        self.fix_scratch = (_lib.empty(L.kdsb200_mlcv_fix_scratch_bytes(M), t.uint8)
+                            if dtype == "float32" else None)
         self.chunks = []
         for g0 in range(0, len(self.grid), 32):
             gsub = np.ascontiguousarray(self.grid[g0:g0 + 32])
@@ -272,8 +275,10 @@ class MLCVPlan:
             partial64 = _lib.empty(self.nb64 * gt64, t.float64)
             self.chunks.append((g0, gsub, gt, gt64, nk, sbuf, partial, partial64))
         #: kernel launches per launch() call
-        self.n_launches = len(self.chunks) * ((3 if self.nsplit == 1 else 4)
-                                              if dtype == "float32" else 2)
+        # pair kernel (+ finalize), slot assignment + two fp64 row launches + combine, or the
+        # fp64 row kernel alone; then the two-stage reduction
+        self.n_launches = len(self.chunks) * ((7 if self.nsplit == 1 else 8)
+                                              if dtype == "float32" else 3)
 
     def _row_folds(self):
         nf = np.diff(self._fb).astype(np.float64)
@@ -328,15 +333,15 @@ class MLCVPlan:
                 _lib.ptr(self.d_data), _lib.ptr(self.d_coef), self.N, self.D, r_lo, self.M,
                 _lib.ptr(self.d_lo), _lib.ptr(self.d_hi), _lib.ptr(self.d_cw), _lib.ptr(self.d_lw),
                 gsub.ctypes.data_as(_lib.c_double_p), G, self.log_shift,
-                _lib.ptr(self.flagmask), _lib.ptr(partial64), st))
+                _lib.ptr(self.flagmask), _lib.ptr(self.fix_scratch), _lib.ptr(partial64), st))
             out = self.d_scores[g0:g0 + G]
             if self.dtype == "float32":
                 _lib.check(L.kdsb200_mlcv_reduce(_lib.ptr(partial), self.nblk, gt,
                                                  _lib.ptr(partial64), self.nb64, gt64, G,
-                                                 _lib.ptr(out), st))
+                                                 _lib.ptr(self.red_tmp), _lib.ptr(out), st))
             else:
                 _lib.check(L.kdsb200_mlcv_reduce(_lib.ptr(partial64), self.nb64, gt64, None, 0, 0,
-                                                 G, _lib.ptr(out), st))
+                                                 G, _lib.ptr(self.red_tmp), _lib.ptr(out), st))
 
     def n_flagged(self):
         """Rows of the last launch() whose fp32 sums were recomputed in fp64 (synchronises)."""

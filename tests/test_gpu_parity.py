@@ -326,9 +326,10 @@ def test_mlcv_source_split_invariance(oracle, scaled):
         got[ns] = plan.collect()
         assert np.allclose(got[ns], ref, rtol=1e-5), ns
         assert np.allclose(got[ns], got[1], rtol=1e-12), ns
-    # pair kernel (+ finalize when the sources are split) + fp64 row check + reduction
-    assert kde.MLCVPlan(data, w, 0.4, grid, nsplit=1).n_launches == 3
-    assert kde.MLCVPlan(data, w, 0.4, grid, nsplit=3).n_launches == 4
+    # pair kernel (+ finalize when the sources are split) + 4 launches of the fp64
+    # recomputation + 2 of the reduction
+    assert kde.MLCVPlan(data, w, 0.4, grid, nsplit=1).n_launches == 7
+    assert kde.MLCVPlan(data, w, 0.4, grid, nsplit=3).n_launches == 8
 
 
 def test_mlcv_fp32_underflow_window_recomputed_in_fp64(oracle, scaled):
@@ -362,6 +363,16 @@ def test_mlcv_fp32_underflow_window_recomputed_in_fp64(oracle, scaled):
         got = plan.collect()
         assert plan.n_flagged() >= 5, plan.n_flagged()
         assert np.allclose(got, ref, rtol=1e-5), (ns, got, ref)
+    # most rows flagged (more row blocks than the sliced recomputation takes: the rest go
+    # through the whole-list launch)
+    d6 = np.random.default_rng(2).uniform(-2, 2, size=(4000, 6))
+    g6 = np.array([0.8, 1.0, 1.25])
+    ref6 = oracle.mlcv_scores_c(d6, None, 0.06, g6, 10)
+    plan = kde.MLCVPlan(d6, None, 0.06, g6, n_splits=10)
+    plan.launch()
+    got6 = plan.collect()
+    assert plan.n_flagged() > 256 * 8
+    assert np.all(np.isfinite(ref6)) and np.allclose(got6, ref6, rtol=1e-5), (got6, ref6)
     # per-sample bandwidths and the public entry point
     seed = rng.uniform(0.2, 0.3, N)
     ref = oracle.mlcv_scores_c(data, w, seed, grid, 7)
