@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(R64_THREADS)
       }
       const double u = r2 * sh[j], c = sc[j];
 #pragma unroll
-      for (int g = 0; g < GT; g++)
-        if (g < G) acc[g] += c * exp(-u * P.inv_g2[g]);
+      for (int g = 0; g < GT; g++)  // only the grid points this row needs (warp-uniform)
+        if ((mask >> g) & 1u) acc[g] += c * exp(-u * P.inv_g2[g]);
     }
   }
   const double cw = mask ? coefw[m] : 0.0, lw = mask ? lwtr[m] : 0.0;
