@@ -16,6 +16,7 @@
 // T = double reproduces numpy/sklearn bit for bit (sub, mul, add in coordinate
 // order, no FMA contraction); T = float is the fast mode (FMA chain).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kdsb200.h"
@@ -302,13 +303,12 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <typename T, int D, int KK>
+template <typename T, int D, int KK, int KS_CT>
 __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
     knn_small_kernel(const T* __restrict__ dataT, uint64_t Nstride,
                      const int64_t* __restrict__ batch_off, int chunks, int kk,
                      double* __restrict__ out_kth, double* __restrict__ out_dist,
                      int32_t* __restrict__ out_idx) {
-  constexpr int KS_CT = KsTile<T>::CT;
   constexpr int KS_PEND = KsPend<T>::N;
   extern __shared__ __align__(16) unsigned char ks_smem[];
   T(*tile)[D][KS_CT] = reinterpret_cast<T(*)[D][KS_CT]>(ks_smem);
@@ -431,19 +431,23 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
           any |= d2[v] < bd[KK - 1];
         }
       }
-      if (any) {
-        // park the survivors in this thread's pending list (shared memory); the
-        // expensive sorted insert runs later for the whole warp at once
+      // One warp-uniform branch guards everything that is not distance arithmetic: the
+      // survivors are parked in this thread's pending list (shared memory, predicated
+      // stores, no divergence), and the expensive sorted insert runs later for the whole
+      // warp at once.  Most steps of a long candidate stream skip all of it.
+      if (__any_sync(0xffffffffu, any)) {
+        const T thr = bd[KK - 1];
 #pragma unroll
         for (int v = 0; v < V; v++) {
-          if (c + v < cnt && d2[v] < bd[KK - 1]) {
+          const bool keep = (c + v < cnt) && (d2[v] < thr);
+          if (keep) {
             pend_d[npend][tid] = d2[v];
             pend_i[npend][tid] = cbase + c + v;
-            npend++;
           }
+          npend += keep ? 1 : 0;
         }
+        if (__any_sync(0xffffffffu, npend > KS_PEND - V)) flush_pending();
       }
-      if (__any_sync(0xffffffffu, npend > KS_PEND - V)) flush_pending();
     }
   }
   flush_pending();
@@ -499,18 +503,38 @@ static int launch_knn(const double* d_data, uint64_t N, const int64_t* d_batch_o
       return 1;
     }
     const unsigned g = (unsigned)(ch * nb);
-    const size_t ksm = sizeof(T) * 2 * D * KsTile<T>::CT +
+    // candidates per shared-memory tile: 256 in fp32 keeps four CTAs per SM resident next
+    // to the pending lists (KDSB200_KNN_TILE overrides, for tuning)
+    static int tile_sel = -1;
+    if (tile_sel < 0) {
+      const char* e = getenv("KDSB200_KNN_TILE");
+      tile_sel = e ? atoi(e) : 0;
+    }
+    const int ct = sizeof(T) == 4 ? (tile_sel == 512 ? 512 : 256) : (tile_sel == 256 ? 256 : 128);
+    const size_t ksm = sizeof(T) * 2 * D * ct +
                        (sizeof(T) + sizeof(int)) * KsPend<T>::N * KS_THREADS;
-#define KDSB_KS(KKV)                                                                        \
-  do {                                                                                      \
-    KDSB_CUDA(cudaFuncSetAttribute(knn_small_kernel<T, D, KKV>,                             \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm)); \
-    knn_small_kernel<T, D, KKV><<<g, KS_THREADS, ksm, st>>>(dataT, N, d_batch_off, (int)ch, \
-                                                            kk, out_kth, out_dist, out_idx); \
+#define KDSB_KS2(KKV, CTV)                                                                     \
+  do {                                                                                         \
+    KDSB_CUDA(cudaFuncSetAttribute(knn_small_kernel<T, D, KKV, CTV>,                           \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));    \
+    knn_small_kernel<T, D, KKV, CTV><<<g, KS_THREADS, ksm, st>>>(dataT, N, d_batch_off,        \
+                                                                 (int)ch, kk, out_kth,         \
+                                                                 out_dist, out_idx);           \
+  } while (0)
+#define KDSB_KS(KKV)                                             \
+  do {                                                           \
+    if (sizeof(T) == 4) {                                        \
+      if (ct == 512) KDSB_KS2(KKV, 512);                         \
+      else KDSB_KS2(KKV, 256);                                   \
+    } else {                                                     \
+      if (ct == 256) KDSB_KS2(KKV, 256);                         \
+      else KDSB_KS2(KKV, 128);                                   \
+    }                                                            \
   } while (0)
     if (kk <= 4) KDSB_KS(4);
     else if (kk <= 12) KDSB_KS(12);
     else KDSB_KS(24);
+#undef KDSB_KS2
 #undef KDSB_KS
     KDSB_CUDA(cudaGetLastError());
     return 0;
