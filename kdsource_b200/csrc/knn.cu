@@ -465,6 +465,143 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
   }
 }
 
+// ---------------------------------------------------------------------------
+// fp32 distances-only variant, TWO query rows per thread.  With one row per thread every
+// candidate coordinate is a broadcast LDS.128 that feeds only 4 pairs per lane: 6 LDS.128
+// (512 B each) per 128 pairs keep the 128 B/clk shared-memory port busy for 24 cycles,
+// twice what the FP32 pipe needs for the arithmetic -- the kernel was LSU-bound at ~50 %
+// of the FP32 roofline.  Two rows per thread halve the bytes per pair.  The neighbour
+// indices are dropped (bw_knn only needs the k-th distance), which pays for the second
+// row's sorted list in registers; when indices are requested the one-row kernel runs.
+// ---------------------------------------------------------------------------
+constexpr int K2_PEND = 12;
+
+template <int D, int KK, int CT>
+__global__ void __launch_bounds__(KS_THREADS, 2)
+    knn_kth2_kernel(const float* __restrict__ dataT, uint64_t Nstride,
+                    const int64_t* __restrict__ batch_off, int chunks, int kk,
+                    double* __restrict__ out_kth, double* __restrict__ out_dist) {
+  extern __shared__ __align__(16) unsigned char ks_smem[];
+  float(*tile)[D][CT] = reinterpret_cast<float(*)[D][CT]>(ks_smem);
+  float(*pend)[K2_PEND][KS_THREADS] = reinterpret_cast<float(*)[K2_PEND][KS_THREADS]>(
+      ks_smem + sizeof(float) * 2 * D * CT);
+  const int tid = threadIdx.x;
+  const int bidx = blockIdx.x / chunks;
+  const int64_t b0 = batch_off[bidx], b1 = batch_off[bidx + 1];
+  const int bn = (int)(b1 - b0);
+  const int r0 = (blockIdx.x % chunks) * (2 * KS_THREADS);
+  if (r0 >= bn) return;
+  const int row[2] = {r0 + tid, r0 + KS_THREADS + tid};
+
+  f2_t nq[2][D];  // -q, duplicated into both halves of a packed operand
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      const float v = row[r] < bn ? dataT[(uint64_t)k * Nstride + b0 + row[r]] : 0.f;
+      nq[r][k] = f2_pack(-v, -v);
+    }
+  float bd[2][KK];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int s = 0; s < KK; s++) bd[r][s] = INFINITY;
+  int npend[2] = {0, 0};
+
+  auto flush_pending = [&](int r) {
+    for (int e = 0; e < K2_PEND; e++) {
+      if (!__any_sync(0xffffffffu, e < npend[r])) break;
+      if (e < npend[r]) {
+        float nd = pend[r][e][tid];
+        if (nd < bd[r][KK - 1]) {
+          bool shifting = false;
+#pragma unroll
+          for (int s = 0; s < KK; s++) {
+            shifting = shifting || (nd < bd[r][s]);
+            if (shifting) {
+              const float td = bd[r][s];
+              bd[r][s] = nd;
+              nd = td;
+            }
+          }
+        }
+      }
+    }
+    npend[r] = 0;
+  };
+
+  auto load_tile = [&](int buf, int cbase) {
+    for (int e = tid; e < D * CT; e += KS_THREADS) {
+      const int k = e / CT, c = e % CT;
+      if (cbase + c < bn)
+        cp_async4(&tile[buf][k][c], dataT + (uint64_t)k * Nstride + b0 + cbase + c);
+      else
+        tile[buf][k][c] = 0.f;
+    }
+    cp_async_commit();
+  };
+
+  const int ntile = (bn + CT - 1) / CT;
+  load_tile(0, 0);
+  for (int t = 0; t < ntile; t++) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (t + 1 < ntile) load_tile((t + 1) & 1, (t + 1) * CT);
+    const int buf = t & 1;
+    const int cbase = t * CT;
+    const int cnt = min(CT, bn - cbase);
+    for (int c = 0; c < cnt; c += 4) {
+      float4 x[D];
+#pragma unroll
+      for (int k = 0; k < D; k++) x[k] = *reinterpret_cast<const float4*>(&tile[buf][k][c]);
+      float d2[2][4];
+      bool any[2];
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        f2_t acc01 = 0ull, acc23 = 0ull;
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+          const f2_t e01 = f2_add(f2_pack(x[k].x, x[k].y), nq[r][k]);
+          const f2_t e23 = f2_add(f2_pack(x[k].z, x[k].w), nq[r][k]);
+          acc01 = k == 0 ? f2_mul(e01, e01) : f2_fma(e01, e01, acc01);
+          acc23 = k == 0 ? f2_mul(e23, e23) : f2_fma(e23, e23, acc23);
+        }
+        f2_unpack(acc01, d2[r][0], d2[r][1]);
+        f2_unpack(acc23, d2[r][2], d2[r][3]);
+        any[r] = fminf(fminf(d2[r][0], d2[r][1]), fminf(d2[r][2], d2[r][3])) < bd[r][KK - 1];
+      }
+      if (__any_sync(0xffffffffu, any[0] || any[1])) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const float thr = bd[r][KK - 1];
+#pragma unroll
+          for (int v = 0; v < 4; v++) {
+            const bool keep = (c + v < cnt) && (d2[r][v] < thr);
+            if (keep) pend[r][npend[r]][tid] = d2[r][v];
+            npend[r] += keep ? 1 : 0;
+          }
+          if (__any_sync(0xffffffffu, npend[r] > K2_PEND - 4)) flush_pending(r);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    flush_pending(r);
+    if (row[r] < bn) {
+      const uint64_t grow = (uint64_t)(b0 + row[r]);
+#pragma unroll
+      for (int s = 0; s < KK; s++) {
+        if (s < kk) {
+          const double dd = sqrt((double)bd[r][s]);
+          if (out_dist) out_dist[grow * kk + s] = dd;
+          if (s == kk - 1 && out_kth) out_kth[grow] = dd;
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void knn_transpose_kernel(const double* __restrict__ data, uint64_t N, int D,
                                      uint64_t Nstride, T* __restrict__ dataT) {
@@ -496,6 +633,29 @@ static int launch_knn(const double* d_data, uint64_t N, const int64_t* d_batch_o
   T* dataT = reinterpret_cast<T*>(d_scratch);
   knn_transpose_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(d_data, N, D, N, dataT);
   KDSB_CUDA(cudaGetLastError());
+  if (sizeof(T) == 4 && kk <= 12 && !out_idx && !getenv("KDSB200_KNN_ONE_ROW")) {
+    // fp32, distances only: two rows per thread (see knn_kth2_kernel)
+    constexpr int CT2 = 256;
+    const int64_t ch = (max_batch + 2 * KS_THREADS - 1) / (2 * KS_THREADS);
+    if (ch * nb >= (1ll << 31)) {
+      set_error("knn: grid too large (%lld CTAs)", (long long)(ch * nb));
+      return 1;
+    }
+    const size_t ksm = sizeof(float) * 2 * D * CT2 + sizeof(float) * 2 * K2_PEND * KS_THREADS;
+    const float* dT = reinterpret_cast<const float*>(dataT);
+#define KDSB_K2(KKV)                                                                            \
+  do {                                                                                          \
+    KDSB_CUDA(cudaFuncSetAttribute(knn_kth2_kernel<D, KKV, CT2>,                                \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));     \
+    knn_kth2_kernel<D, KKV, CT2><<<(unsigned)(ch * nb), KS_THREADS, ksm, st>>>(                 \
+        dT, N, d_batch_off, (int)ch, kk, out_kth, out_dist);                                    \
+  } while (0)
+    if (kk <= 4) KDSB_K2(4);
+    else KDSB_K2(12);
+#undef KDSB_K2
+    KDSB_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (kk <= 24) {
     const int64_t ch = (max_batch + KS_THREADS - 1) / KS_THREADS;
     if (ch * nb >= (1ll << 31)) {
