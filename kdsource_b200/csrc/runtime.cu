@@ -82,6 +82,29 @@ __global__ void __launch_bounds__(256) calib_kernel(float* out, int iters, float
     float x, y;
     f2_unpack(f2_add(f2_add(p0, p1), f2_add(p2, p3)), x, y);
     a0 = x + y + s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7;
+  } else if (MODE == 5 || MODE == 6 || MODE == 7) {
+    // packed FADD2 (5), FMUL2 (6), and the kNN distance mix FADD2 -> FFMA2 (7)
+    f2_t p0 = f2_pack(a0, a1), p1 = f2_pack(a2, a3), p2 = f2_pack(a4, a5), p3 = f2_pack(a6, a7);
+    f2_t p4 = f2_pack(a1, a0), p5 = f2_pack(a3, a2), p6 = f2_pack(a5, a4), p7 = f2_pack(a7, a6);
+    const f2_t mm = f2_pack(m, m), cc = f2_pack(c, c);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (MODE == 5) {
+          p0 = f2_add(p0, cc); p1 = f2_add(p1, cc); p2 = f2_add(p2, cc); p3 = f2_add(p3, cc);
+          p4 = f2_add(p4, cc); p5 = f2_add(p5, cc); p6 = f2_add(p6, cc); p7 = f2_add(p7, cc);
+        } else if (MODE == 6) {
+          p0 = f2_mul(p0, mm); p1 = f2_mul(p1, mm); p2 = f2_mul(p2, mm); p3 = f2_mul(p3, mm);
+          p4 = f2_mul(p4, mm); p5 = f2_mul(p5, mm); p6 = f2_mul(p6, mm); p7 = f2_mul(p7, mm);
+        } else {
+          p0 = f2_add(p0, cc); p4 = f2_fma(p0, p0, p4); p1 = f2_add(p1, cc); p5 = f2_fma(p1, p1, p5);
+          p2 = f2_add(p2, cc); p6 = f2_fma(p2, p2, p6); p3 = f2_add(p3, cc); p7 = f2_fma(p3, p3, p7);
+        }
+      }
+    }
+    float x, y;
+    f2_unpack(f2_add(f2_add(p0, p1), f2_add(p2, p3)), x, y); a0 = x + y;
+    f2_unpack(f2_add(f2_add(p4, p5), f2_add(p6, p7)), x, y); a1 = x + y;
   } else if (MODE == 4) {  // fp64 pipe: DFMA
     double d0 = a0, d1 = a1, d2 = a2, d3 = a3, d4 = a4, d5 = a5, d6 = a6, d7 = a7;
     const double dm = 0.999, dc = 1e-3;
@@ -127,7 +150,8 @@ int kdsb200_device_info(int* sm, int* cc_major, int* cc_minor, int* clock_khz) {
   return 0;
 }
 
-// mode 0: FFMA, 1: FFMA2, 2: MUFU.EX2, 3: FFMA2+FFMA interleaved, 4: DFMA.  Returns lane-operations per second
+// mode 0: FFMA, 1: FFMA2, 2: MUFU.EX2, 3: FFMA2+FFMA interleaved, 4: DFMA, 5: FADD2, 6: FMUL2,
+// 7: FADD2+FFMA2 (the kNN distance mix).  Returns lane-operations per second
 // (FFMA2 counts two per lane-instruction) measured with CUDA events.
 int kdsb200_calibrate_pipe(int mode, float* d_scratch /* >= sm*8*256 floats */, int iters,
                            double* ops_per_s, void* stream) {
@@ -142,6 +166,9 @@ int kdsb200_calibrate_pipe(int mode, float* d_scratch /* >= sm*8*256 floats */, 
     else if (mode == 1) calib_kernel<1><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     else if (mode == 3) calib_kernel<3><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     else if (mode == 4) calib_kernel<4><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
+    else if (mode == 5) calib_kernel<5><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
+    else if (mode == 6) calib_kernel<6><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
+    else if (mode == 7) calib_kernel<7><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     else calib_kernel<2><<<blocks, 256, 0, st>>>(d_scratch, iters, 1.0f);
     KDSB_CUDA(cudaEventRecord(e1, st));
     KDSB_CUDA(cudaEventSynchronize(e1));

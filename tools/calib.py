@@ -17,7 +17,7 @@ def calibrate(iters=4096):
     scratch = _lib.empty(sm.value * 8 * 256, t.float32)
     out = {"sm": sm.value, "cc": "{}.{}".format(ma.value, mi.value), "clock_khz": clk.value}
     for mode, name in ((0, "ffma"), (1, "ffma2"), (2, "mufu_ex2"), (3, "ffma2_plus_ffma"),
-                       (4, "dfma")):
+                       (4, "dfma"), (5, "fadd2"), (6, "fmul2"), (7, "fadd2_ffma2_mix")):
         r = ctypes.c_double()
         _lib.check(L.kdsb200_calibrate_pipe(mode, _lib.ptr(scratch), iters, ctypes.byref(r),
                                             _lib.stream()))
