@@ -301,6 +301,16 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+// stores through 32-bit shared-window addresses (one STS, no 64-bit pointer arithmetic)
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_s32(uint32_t addr, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <typename T, int D, int KK, int KS_CT>
@@ -337,9 +347,13 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
   }
 
   // per-thread pending candidates; entries are in candidate (index) order, and the
-  // insert below is strict, so equal distances keep the smaller index first
-  int npend = 0;
+  // insert below is strict, so equal distances keep the smaller index first.  pd / pi
+  // point at the next free slot of this thread's column.
+  const uint32_t pd0 = smem_u32(&pend_d[0][tid]), pi0 = smem_u32(&pend_i[0][tid]);
+  uint32_t pd = pd0, pi = pi0;
+  constexpr uint32_t PDSTEP = KS_THREADS * sizeof(T), PISTEP = KS_THREADS * sizeof(int);
   auto flush_pending = [&]() {
+    const int npend = (int)((pd - pd0) / PDSTEP);
     for (int e = 0; e < KS_PEND; e++) {
       if (!__any_sync(0xffffffffu, e < npend)) break;
       if (e < npend) {
@@ -362,9 +376,11 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
         }
       }
     }
-    npend = 0;
+    pd = pd0;
+    pi = pi0;
   };
 
+  // padding candidates sit at infinity: their distance is +inf and never survives
   auto load_tile = [&](int buf, int cbase) {
     for (int e = tid; e < D * KS_CT; e += KS_THREADS) {
       const int k = e / KS_CT, c = e % KS_CT;
@@ -373,7 +389,7 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
         if (sizeof(T) == 4) cp_async4(&tile[buf][k][c], src);
         else cp_async8(&tile[buf][k][c], src);
       } else {
-        tile[buf][k][c] = (T)0;
+        tile[buf][k][c] = (T)INFINITY;
       }
     }
     cp_async_commit();
@@ -439,14 +455,15 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
         const T thr = bd[KK - 1];
 #pragma unroll
         for (int v = 0; v < V; v++) {
-          const bool keep = (c + v < cnt) && (d2[v] < thr);
-          if (keep) {
-            pend_d[npend][tid] = d2[v];
-            pend_i[npend][tid] = cbase + c + v;
+          if (d2[v] < thr) {  // two predicated stores and two offset bumps
+            if constexpr (sizeof(T) == 4) sts_f32(pd, d2[v]);
+            else sts_f64(pd, d2[v]);
+            sts_s32(pi, cbase + c + v);
+            pd += PDSTEP;
+            pi += PISTEP;
           }
-          npend += keep ? 1 : 0;
         }
-        if (__any_sync(0xffffffffu, npend > KS_PEND - V)) flush_pending();
+        if (__any_sync(0xffffffffu, pd > pd0 + (KS_PEND - V) * PDSTEP)) flush_pending();
       }
     }
   }
@@ -506,12 +523,16 @@ __global__ void __launch_bounds__(KS_THREADS, 2)
   for (int r = 0; r < 2; r++)
 #pragma unroll
     for (int s = 0; s < KK; s++) bd[r][s] = INFINITY;
-  int npend[2] = {0, 0};
+  // pending survivors: pp[r] points at the next free slot of this thread's column
+  const uint32_t pbase[2] = {smem_u32(&pend[0][0][tid]), smem_u32(&pend[1][0][tid])};
+  uint32_t pp[2] = {pbase[0], pbase[1]};
+  constexpr uint32_t PSTEP = KS_THREADS * sizeof(float);
 
   auto flush_pending = [&](int r) {
+    const int np = (int)((pp[r] - pbase[r]) / PSTEP);
     for (int e = 0; e < K2_PEND; e++) {
-      if (!__any_sync(0xffffffffu, e < npend[r])) break;
-      if (e < npend[r]) {
+      if (!__any_sync(0xffffffffu, e < np)) break;
+      if (e < np) {
         float nd = pend[r][e][tid];
         if (nd < bd[r][KK - 1]) {
           bool shifting = false;
@@ -527,16 +548,18 @@ __global__ void __launch_bounds__(KS_THREADS, 2)
         }
       }
     }
-    npend[r] = 0;
+    pp[r] = pbase[r];
   };
 
+  // padding candidates sit at infinity: their distance is +inf and never survives, so the
+  // hot loop needs no bounds test
   auto load_tile = [&](int buf, int cbase) {
     for (int e = tid; e < D * CT; e += KS_THREADS) {
       const int k = e / CT, c = e % CT;
       if (cbase + c < bn)
         cp_async4(&tile[buf][k][c], dataT + (uint64_t)k * Nstride + b0 + cbase + c);
       else
-        tile[buf][k][c] = 0.f;
+        tile[buf][k][c] = INFINITY;
     }
     cp_async_commit();
   };
@@ -571,16 +594,23 @@ __global__ void __launch_bounds__(KS_THREADS, 2)
         any[r] = fminf(fminf(d2[r][0], d2[r][1]), fminf(d2[r][2], d2[r][3])) < bd[r][KK - 1];
       }
       if (__any_sync(0xffffffffu, any[0] || any[1])) {
+        // warp-uniform slow path: predicated appends (a store and a pointer bump each)
 #pragma unroll
         for (int r = 0; r < 2; r++) {
           const float thr = bd[r][KK - 1];
 #pragma unroll
           for (int v = 0; v < 4; v++) {
-            const bool keep = (c + v < cnt) && (d2[r][v] < thr);
-            if (keep) pend[r][npend[r]][tid] = d2[r][v];
-            npend[r] += keep ? 1 : 0;
+            if (d2[r][v] < thr) {
+              sts_f32(pp[r], d2[r][v]);
+              pp[r] += PSTEP;
+            }
           }
-          if (__any_sync(0xffffffffu, npend[r] > K2_PEND - 4)) flush_pending(r);
+        }
+        const bool full0 = pp[0] > pbase[0] + (K2_PEND - 4) * PSTEP;
+        const bool full1 = pp[1] > pbase[1] + (K2_PEND - 4) * PSTEP;
+        if (__any_sync(0xffffffffu, full0 || full1)) {
+          flush_pending(0);
+          flush_pending(1);
         }
       }
     }
