@@ -491,10 +491,8 @@ __global__ void __launch_bounds__(KS_THREADS, sizeof(T) == 4 ? 4 : 2)
 // indices are dropped (bw_knn only needs the k-th distance), which pays for the second
 // row's sorted list in registers; when indices are requested the one-row kernel runs.
 // ---------------------------------------------------------------------------
-constexpr int K2_PEND = 12;
-
-template <int D, int KK, int CT>
-__global__ void __launch_bounds__(KS_THREADS, 2)
+template <int D, int KK, int CT, int K2_PEND>
+__global__ void __launch_bounds__(KS_THREADS, 3)
     knn_kth2_kernel(const float* __restrict__ dataT, uint64_t Nstride,
                     const int64_t* __restrict__ batch_off, int chunks, int kk,
                     double* __restrict__ out_kth, double* __restrict__ out_dist) {
@@ -510,14 +508,12 @@ __global__ void __launch_bounds__(KS_THREADS, 2)
   if (r0 >= bn) return;
   const int row[2] = {r0 + tid, r0 + KS_THREADS + tid};
 
-  f2_t nq[2][D];  // -q, duplicated into both halves of a packed operand
+  float q[2][D];
 #pragma unroll
   for (int r = 0; r < 2; r++)
 #pragma unroll
-    for (int k = 0; k < D; k++) {
-      const float v = row[r] < bn ? dataT[(uint64_t)k * Nstride + b0 + row[r]] : 0.f;
-      nq[r][k] = f2_pack(-v, -v);
-    }
+    for (int k = 0; k < D; k++)
+      q[r][k] = row[r] < bn ? dataT[(uint64_t)k * Nstride + b0 + row[r]] : 0.f;
   float bd[2][KK];
 #pragma unroll
   for (int r = 0; r < 2; r++)
@@ -584,8 +580,9 @@ __global__ void __launch_bounds__(KS_THREADS, 2)
         f2_t acc01 = 0ull, acc23 = 0ull;
 #pragma unroll
         for (int k = 0; k < D; k++) {
-          const f2_t e01 = f2_add(f2_pack(x[k].x, x[k].y), nq[r][k]);
-          const f2_t e23 = f2_add(f2_pack(x[k].z, x[k].w), nq[r][k]);
+          const f2_t nq = f2_pack(-q[r][k], -q[r][k]);  // scalar broadcast operand of FADD2
+          const f2_t e01 = f2_add(f2_pack(x[k].x, x[k].y), nq);
+          const f2_t e23 = f2_add(f2_pack(x[k].z, x[k].w), nq);
           acc01 = k == 0 ? f2_mul(e01, e01) : f2_fma(e01, e01, acc01);
           acc23 = k == 0 ? f2_mul(e23, e23) : f2_fma(e23, e23, acc23);
         }
@@ -671,17 +668,30 @@ static int launch_knn(const double* d_data, uint64_t N, const int64_t* d_batch_o
       set_error("knn: grid too large (%lld CTAs)", (long long)(ch * nb));
       return 1;
     }
-    const size_t ksm = sizeof(float) * 2 * D * CT2 + sizeof(float) * 2 * K2_PEND * KS_THREADS;
+    static int pend_sel = -1;  // pending slots per row (KDSB200_KNN_PEND: 12 | 16 | 24, tuning)
+    if (pend_sel < 0) {
+      const char* e = getenv("KDSB200_KNN_PEND");
+      pend_sel = e ? atoi(e) : 16;
+    }
+    const int pn = pend_sel == 12 ? 12 : pend_sel == 24 ? 24 : 16;
+    const size_t ksm = sizeof(float) * 2 * D * CT2 + sizeof(float) * 2 * pn * KS_THREADS;
     const float* dT = reinterpret_cast<const float*>(dataT);
-#define KDSB_K2(KKV)                                                                            \
+#define KDSB_K2P(KKV, PN)                                                                       \
   do {                                                                                          \
-    KDSB_CUDA(cudaFuncSetAttribute(knn_kth2_kernel<D, KKV, CT2>,                                \
+    KDSB_CUDA(cudaFuncSetAttribute(knn_kth2_kernel<D, KKV, CT2, PN>,                            \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksm));     \
-    knn_kth2_kernel<D, KKV, CT2><<<(unsigned)(ch * nb), KS_THREADS, ksm, st>>>(                 \
+    knn_kth2_kernel<D, KKV, CT2, PN><<<(unsigned)(ch * nb), KS_THREADS, ksm, st>>>(             \
         dT, N, d_batch_off, (int)ch, kk, out_kth, out_dist);                                    \
+  } while (0)
+#define KDSB_K2(KKV)                   \
+  do {                                 \
+    if (pn == 12) KDSB_K2P(KKV, 12);   \
+    else if (pn == 24) KDSB_K2P(KKV, 24); \
+    else KDSB_K2P(KKV, 16);            \
   } while (0)
     if (kk <= 4) KDSB_K2(4);
     else KDSB_K2(12);
+#undef KDSB_K2P
 #undef KDSB_K2
     KDSB_CUDA(cudaGetLastError());
     return 0;
