@@ -264,3 +264,30 @@ def hostvec(a):
     """numpy float64 vector -> (keepalive, POINTER(double))."""
     v = np.ascontiguousarray(a, dtype=np.float64)
     return v, v.ctypes.data_as(c_double_p)
+
+
+# ---------------------------------------------------------------------------
+# small device statistics (synchronising): thin wrappers over the reduction kernels
+# ---------------------------------------------------------------------------
+def dev_minmax(d_data, N, D):
+    """Column minima and maxima of a (N,D) fp64 device tensor -> two numpy vectors."""
+    L = load()
+    t = torch()
+    scr = empty(L.kdsb200_minmax_scratch(), t.float64)
+    mm = empty(2 * D, t.float64)
+    check(L.kdsb200_column_minmax(ptr(d_data), N, D, ptr(scr), ptr(mm), stream()))
+    h = mm.cpu().numpy()
+    return h[:D].copy(), h[D:].copy()
+
+
+def dev_moments(d_vecs, d_w, N, D, center=None, power=1):
+    """(sums (D,), sum_w, sum_w2) with sums[k] = sum_i w_i (v_ik - c_k)^power on the device."""
+    L = load()
+    t = torch()
+    scr = empty(L.kdsb200_moments_scratch(), t.float64)
+    out = empty(D + 2, t.float64)
+    keep, cp = (None, None) if center is None else hostvec(center)
+    check(L.kdsb200_weighted_moments(ptr(d_vecs), ptr(d_w), N, D, cp, int(power), ptr(scr),
+                                     ptr(out), stream()))
+    h = out.cpu().numpy()
+    return h[:D].copy(), float(h[D]), float(h[D + 1])

@@ -88,6 +88,12 @@ class Metric:
         centre = self.mean_sharded(vecs, weights, allsum)
         return np.sqrt(self._wavg_sharded((vecs - centre) ** 2, weights, allsum))
 
+    # -- the same statistics from column moments computed elsewhere (on the device):
+    # `avg(centre, power)` returns the weighted averages of (v - centre)^power over this
+    # metric's columns (centre None = 0), e.g. from kdsb200_weighted_moments.
+    def std_from_moments(self, avg):
+        return np.sqrt(avg(avg(None, 1), 2))
+
     # -- serialisation --------------------------------------------------------
     def params(self):
         return [getattr(self, n) for n in self._param_names]
@@ -193,6 +199,24 @@ class Geometry(Metric):
         out, col = [], 0
         for m in self.ms:
             out.append(m.std_sharded(vecs[:, col:col + m.dim], weights, allsum))
+            col += m.dim
+        return np.concatenate(out)
+
+    def std_from_moments(self, avg):
+        """:meth:`std` from a column-moment callback over all KDE variables:
+        `avg(centre (dim,) or None, power)` -> (dim,) weighted averages."""
+        out, col = [], 0
+        for m in self.ms:
+            lo, hi = col, col + m.dim
+
+            def sub(centre, power, lo=lo, hi=hi):
+                full = None
+                if centre is not None:
+                    full = np.zeros(self.dim)
+                    full[lo:hi] = centre
+                return avg(full, power)[lo:hi]
+
+            out.append(m.std_from_moments(sub))
             col += m.dim
         return np.concatenate(out)
 
@@ -529,6 +553,12 @@ class Isotrop(Metric):
         mn = self._wavg_sharded(vecs, weights, allsum)
         norm = np.linalg.norm(mn)
         return mn / (norm if norm != 0 else 1)
+
+    def std_from_moments(self, avg):
+        mn = avg(None, 1)
+        norm = np.linalg.norm(mn)
+        mn = mn / (norm if norm != 0 else 1)
+        return np.array(3 * [np.sqrt(np.mean(avg(mn, 2)))])
 
     def std_sharded(self, vecs, weights, allsum):
         mn = self.mean_sharded(vecs, weights, allsum)

@@ -23,6 +23,11 @@ from .treekde import TreeKDE
 _LOG2E = 1.4426950408889634
 
 
+def _lib_is_tensor(x):
+    """True for a torch tensor (without importing torch for plain numpy input)."""
+    return type(x).__module__.startswith("torch")
+
+
 def bw_silv(dim, N_eff):
     """Silverman's Rule (reference kde.py:18-38)."""
     return (4 / (2 + dim)) ** (1 / (4 + dim)) * N_eff ** (-1 / (4 + dim))
@@ -46,11 +51,16 @@ def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_
     ``dist`` (N,kk) ascending, ``idx`` (N,kk) int32 indices inside the batch
     ordered by (distance, index).  Batches are sharded over ranks.  In a batch
     with fewer than kk rows the missing neighbours are (+inf, -1); ``bw_knn``
-    refuses that case like scikit-learn does.
+    refuses that case like scikit-learn does.  `data` may be a (N,D) float64 CUDA
+    tensor (device-resident fit); ``kth`` is then returned as a CUDA tensor.
     """
     L = _lib.load()
     t = _lib.torch()
-    data = np.ascontiguousarray(data, dtype=np.float64)
+    on_device = t.is_tensor(data)  # (N,D) float64 CUDA tensor: stays where it is
+    if on_device:
+        data = data.to(dtype=t.float64).contiguous()
+    else:
+        data = np.ascontiguousarray(data, dtype=np.float64)
     N, D = data.shape
     batch_off = np.ascontiguousarray(batch_off, dtype=np.int64)
     nb = len(batch_off) - 1
@@ -65,7 +75,7 @@ def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_
     t_idx = _lib.empty(n_loc * kk, t.int32) if want_idx else None
     if n_loc > 0:
         loc_off = batch_off[b_lo:b_hi + 1] - r_lo
-        d_data = _lib.to_dev(data[r_lo:r_hi])
+        d_data = data[r_lo:r_hi] if on_device else _lib.to_dev(data[r_lo:r_hi])
         d_off = _lib.to_dev(loc_off, np.int64)
         use_f64 = precision == "float64"
         scratch = _lib.empty(n_loc * D, t.float64 if use_f64 else t.float32)
@@ -75,7 +85,9 @@ def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_
             _lib.ptr(t_kth), _lib.ptr(t_dist), _lib.ptr(t_idx), _lib.stream()))
     # the ranks' disjoint slices are all-gathered on the device (batches are contiguous,
     # so rank order is row order), then downloaded once
-    kth = _dist.allgather_concat_tensor(t_kth).cpu().numpy()
+    kth = _dist.allgather_concat_tensor(t_kth)
+    if not on_device:  # device input: the k-th distances stay on the device too
+        kth = kth.cpu().numpy()
     dist = idx = None
     if want_dist:
         dist = _dist.allgather_concat_tensor(t_dist.view(n_loc, kk)).cpu().numpy()
@@ -92,7 +104,8 @@ def bw_knn(data, weights=None, K_eff=100, k=None, batch_size=10000, precision="f
     ``f_k ** (1/dim)``.  ``precision="float64"`` reproduces the reference's
     distances bit for bit; ``"float32"`` is the fast mode.
     """
-    data = np.asarray(data)
+    if not _lib_is_tensor(data):
+        data = np.asarray(data)
     N, dim = data.shape
     batches = int(max(1, np.round(N / batch_size)))
     # The reference's branches are inverted (kde.py:70-74): with weights
@@ -462,7 +475,9 @@ def bw_auto(data, weights, grid=None, Nmlcv=1e4, Nbatch=1e4, Nknn=10, show=True,
     3. the MLCV factor is applied to the whole kNN bandwidth and corrected by
        the Silverman ratio between N and Nmlcv samples.
     """
-    data = np.asarray(data)
+    on_device = _lib_is_tensor(data)
+    if not on_device:
+        data = np.asarray(data)
     n_all, dim = data.shape
     print("Fitting first with kNN method:")
     if Nbatch == -1:
@@ -476,11 +491,21 @@ def bw_auto(data, weights, grid=None, Nmlcv=1e4, Nbatch=1e4, Nknn=10, show=True,
         Nmlcv = n_all
     n_cv = int(Nmlcv)
     print("If fitting takes too long, consider reducing Nmlcv.")
-    cv_bw = bw_mlcv(data[:n_cv], weights=weights, seed=knn_bw[:n_cv], grid=grid,
-                    show=show, n_splits=n_splits)
+    if on_device:
+        # the cross-validation subset (Nmlcv rows) goes through the host-array entry point;
+        # the full-length kNN bandwidths stay on the device
+        w_cv = weights[:n_cv].cpu().numpy() if _lib_is_tensor(weights) else weights
+        cv_bw = bw_mlcv(data[:n_cv].cpu().numpy(), weights=w_cv,
+                        seed=knn_bw[:n_cv].cpu().numpy(), grid=grid, show=show,
+                        n_splits=n_splits)
+        first = float(knn_bw[0].item())
+    else:
+        cv_bw = bw_mlcv(data[:n_cv], weights=weights, seed=knn_bw[:n_cv], grid=grid,
+                        show=show, n_splits=n_splits)
+        first = knn_bw[0]
     print("")
     print("Extending the MLCV optimization to full kNN bandwidth:")
-    factor = cv_bw[0] / knn_bw[0]
+    factor = cv_bw[0] / first
     factor *= bw_silv(dim, len(knn_bw)) / bw_silv(dim, len(cv_bw))
     print("Done.")
     return knn_bw * factor

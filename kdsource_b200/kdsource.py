@@ -82,8 +82,114 @@ class KDSource:
         self.R = R[self.kernel[0]]
         self.fitted = False
 
+    #: lists of at least this many records are fitted on the device by default
+    DEVICE_FIT_MIN = 1 << 20
+
+    def _fit_on_device(self, N, skip, device, kwargs):
+        """Device-resident fit: explicit request, or a large list on a CUDA machine; the
+        host-callable sample filters of optimize_bw (weightfun / maskfun) need the host path."""
+        if device is False or "weightfun" in kwargs or "maskfun" in kwargs:
+            return False
+        if device is True:
+            return True
+        return self.plist._use_device_decoder(N, skip) and (
+            N < 0 or N >= self.DEVICE_FIT_MIN)
+
+    def _fit_device(self, N, skip, scaling, importance, bw_method, sharded, kwargs):
+        """:meth:`fit` without host round trips of the sample arrays: records decoded on the
+        GPU (PList.get_device), Geometry.transform by kdsb200_geom_transform, weighted
+        moments (N_eff, scaling) by the reduction kernels, kNN / packing from device
+        tensors.  Only O(dim) statistics, the MLCV subset and the bandwidth vector (for
+        `kde.bw` and `save`) reach the host."""
+        from . import _lib
+        from . import dist as _dist
+        from .sampler import make_geom_struct
+
+        L = _lib.load()
+        t = _lib.torch()
+        rank, world = _dist.rank_world()
+        D = self.geom.dim
+        if sharded:
+            from . import mcpl as _mcpl
+
+            with _mcpl.MCPLFile(self.plist.filename) as f:
+                avail = max(0, f.nparticles - skip)
+            n_req = avail if N < 0 else min(N, avail)
+            lo, hi = _dist.shard_range(n_req, rank, world)
+            parts, ws = self.plist.get_device(hi - lo, skip + lo)
+        else:
+            parts, ws = self.plist.get_device(N, skip)
+        n_loc = int(parts.shape[0])
+        n_tot = n_loc
+        if sharded:
+            n_tot = int(round(_dist.allreduce_sum_numpy(np.array([float(n_loc)]))[0]))
+        if n_tot == 0:
+            raise Exception("No particles for fitting.")
+        print("Using {} particles for fit.".format(n_tot))
+        gs = make_geom_struct(self.geom, np.ones(D), "g")
+        rot_keep, rot_p = (None, None)
+        if self.geom.rot is not None:
+            rot_keep, rot_p = _lib.hostvec(self.geom.rot.inv().as_matrix().reshape(-1))
+        vecs = _lib.empty(max(n_loc, 1) * D, t.float64)[:n_loc * D].reshape(n_loc, D)
+        if n_loc:
+            _lib.check(L.kdsb200_geom_transform(_lib.ptr(parts), n_loc, ctypes.byref(gs), rot_p,
+                                                None, _lib.ptr(vecs), None, _lib.stream()))
+        del parts
+
+        def moments(center, power):
+            if n_loc:
+                sums, sw, sw2 = _lib.dev_moments(vecs, ws, n_loc, D, center, power)
+            else:
+                sums, sw, sw2 = np.zeros(D), 0.0, 0.0
+            tot = np.concatenate((sums, [sw, sw2]))
+            if sharded:
+                tot = _dist.allreduce_sum_numpy(tot)
+            return tot
+
+        tot = moments(None, 1)
+        self.N_eff = tot[D] ** 2 / tot[D + 1]
+        if scaling is None:
+            def avg(center, power):
+                m = moments(center, power)
+                return m[:D] / m[D]
+
+            scaling = self.geom.std_from_moments(avg)
+            if importance is None:
+                importance = [1] * D
+            elif len(importance) != D:
+                raise Exception("importance must have len = {}.".format(D))
+            scaling /= importance
+        else:
+            scaling = np.array(scaling, dtype=np.float64)
+        scaling[scaling == 0] = STD_DEFAULT
+        self.scaling = scaling
+        vecs /= t.as_tensor(scaling, dtype=t.float64, device="cuda")  # in place: KDE variables
+        if sharded:  # from here on every rank holds the whole sample, on its device
+            vecs = _dist.allgather_concat_tensor(vecs)
+            ws = _dist.allgather_concat_tensor(ws)
+        if bw_method is not None:
+            if bw_method not in bw_methods:
+                raise Exception("Invalid bw_method. Available: {}".format(list(bw_methods)))
+            self.bw_method = bw_method
+        d_bw = None
+        if self.bw_method is not None:
+            print("Calculating bw ... ")
+            if self.bw_method == "silv":
+                bw = bw_silv(D, self.N_eff)
+            elif self.bw_method == "mlcv":
+                bw = bw_methods["mlcv"](vecs.cpu().numpy(), weights=ws.cpu().numpy(), **kwargs)
+            else:  # "knn", "auto": kNN over device tensors
+                bw = bw_methods[self.bw_method](vecs, weights=ws, **kwargs)
+            if t.is_tensor(bw):
+                d_bw, bw = bw, bw.cpu().numpy()
+            bw_opt = np.reshape(bw, (-1, 1)) * self.scaling
+            print("Done\nOptimal bw ({}) = {}".format(self.bw_method, bw_opt))
+            self.kde = TreeKDE(kernel=self.kernel, bw=bw)
+        self.kde.fit_device(vecs, ws, d_bw=d_bw)
+        self.fitted = True
+
     def fit(self, N=-1, skip=0, scaling=None, importance=None, bw_method=None, sharded=False,
-            **kwargs):
+            device=None, **kwargs):
         """Load up to N particles (after `skip`) and fit the KDE model
         (reference kdsource.py:132-213): scaling = weighted std of each KDE
         variable / importance (or the given scaling; zeros -> 1), then the
@@ -93,11 +199,17 @@ class KDSource:
         transforms only its contiguous share of the N particles; N_eff and the scaling
         come from all-reduced weighted moments, and the transformed samples are
         all-gathered so that every rank ends with the same fitted model as an
-        unsharded fit."""
+        unsharded fit.
+
+        device=None (default) fits lists of 2^20 records or more on the GPU without
+        host round trips of the sample arrays (see :meth:`_fit_device`); True / False
+        force either path.  Both give the same scaling, N_eff and bandwidths to 1e-13."""
         from . import dist as _dist
 
         rank, world = _dist.rank_world()
         sharded = bool(sharded) and world > 1
+        if self._fit_on_device(N, skip, device, kwargs):
+            return self._fit_device(N, skip, scaling, importance, bw_method, sharded, kwargs)
         if sharded:
             from . import mcpl as _mcpl
 

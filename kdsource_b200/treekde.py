@@ -77,9 +77,65 @@ class TreeKDE:
             raise ValueError("dtype must be 'auto', 'float32', 'float32x2', 'float32_dense' "
                              "or 'float64'")
         self.dtype = dtype
-        self.data = None
-        self.weights = None
+        self._data = None      # host copies (numpy) ...
+        self._weights = None
+        self._d_data = None    # ... and / or device tensors (fit_device)
+        self._d_w = None
+        self._d_bw = None      # device copy of a per-sample bandwidth array, with the
+        self._d_bw_for = None  # host array it mirrors
+        self._has_w = False
+        self._gen = 0          # bumped whenever the samples change
         self._dev = None
+
+    # `.data` / `.weights` are what the reference reads from KDEpy (kdsource.py:457-479);
+    # after fit_device they are downloaded on first access
+    @property
+    def data(self):
+        if self._data is None and self._d_data is not None:
+            self._data = self._d_data.cpu().numpy()
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+        self._d_data = None
+        self._gen += 1
+
+    @property
+    def weights(self):
+        if self._weights is None and self._d_w is not None:
+            self._weights = self._d_w.cpu().numpy()
+        return self._weights
+
+    @weights.setter
+    def weights(self, value):
+        self._weights = value
+        self._d_w = None
+        self._has_w = value is not None
+        self._gen += 1
+
+    def fit_device(self, d_data, d_weights=None, d_bw=None):
+        """:meth:`fit` from (N,D) / (N,) float64 CUDA tensors that stay on the device
+        (the device-resident fit of KDSource); `d_bw` is an optional device copy of a
+        per-sample ``bw`` array."""
+        t = _lib.torch()
+        if d_data.dim() != 2 or d_data.shape[0] == 0 or d_data.shape[1] > 8:
+            raise ValueError("data must have shape (obs, dims) with obs > 0 and dims <= 8")
+        self._data = None
+        self._weights = None
+        self._d_data = d_data.to(dtype=t.float64).contiguous()
+        self._d_w = None if d_weights is None else d_weights.to(dtype=t.float64).contiguous()
+        self._has_w = d_weights is not None
+        if d_bw is not None:
+            self._d_bw, self._d_bw_for = d_bw, self.bw
+        self._gen += 1
+        self._dev = None
+        return self
+
+    def n_samples(self):
+        if self._d_data is not None:
+            return int(self._d_data.shape[0]), int(self._d_data.shape[1])
+        return self._data.shape
 
     # -- KDEpy interface ----------------------------------------------------
     def fit(self, data, weights=None):
@@ -108,13 +164,14 @@ class TreeKDE:
         """Densities at `points` ((obs, dims)).  With torch.distributed initialised
         and ``shard=True`` the query points are split contiguously over the ranks
         (sources replicated) and the result is assembled on every rank."""
-        if self.data is None:
+        if self._data is None and self._d_data is None:
             raise ValueError("Must call fit before evaluating.")
+        D = self.n_samples()[1]
         pts = np.ascontiguousarray(points, dtype=np.float64)
         if pts.ndim == 1:
-            pts = pts.reshape(-1, self.data.shape[1])
-        if pts.shape[1] != self.data.shape[1]:
-            raise ValueError("points must have shape (obs, {})".format(self.data.shape[1]))
+            pts = pts.reshape(-1, D)
+        if pts.shape[1] != D:
+            raise ValueError("points must have shape (obs, {})".format(D))
         from . import dist as _dist
 
         rank, world = _dist.rank_world()
@@ -132,13 +189,28 @@ class TreeKDE:
 
     # -- device side ----------------------------------------------------------
     def _bw_array(self):
-        N = len(self.data)
+        N = self.n_samples()[0]
         if np.ndim(self.bw) == 0:
             return None, float(self.bw)
         bw = np.ascontiguousarray(self.bw, dtype=np.float64).reshape(-1)
         if len(bw) < N:
             raise ValueError("If bw is array, must have same len as data")
         return bw[:N], 0.0
+
+    # Has the per-sample bandwidth array changed since the sources were packed (users and
+    # KDSource.save rescale it in place)?  Small arrays are compared in full; beyond 2^20
+    # entries a strided sample of 4096 values stands in for the array.
+    @staticmethod
+    def _bw_snapshot(bw):
+        if len(bw) <= (1 << 20):
+            return bw.copy()
+        return (len(bw), bw[::max(1, len(bw) // 4096)].copy())
+
+    @staticmethod
+    def _bw_same(bw, snap):
+        if isinstance(snap, tuple):
+            return len(bw) == snap[0] and np.array_equal(bw[::max(1, len(bw) // 4096)], snap[1])
+        return len(bw) == len(snap) and np.array_equal(bw, snap)
 
     def _cutoff_radius(self, bw_max):
         if self.cutoff is None:
@@ -153,37 +225,52 @@ class TreeKDE:
         """Upload and pack the fitted sources (cached until data/bw change)."""
         bw_arr, bw_scalar = self._bw_array()
         d = self._dev
-        if (d is not None and d["data_ref"] is self.data and d["weights_ref"] is self.weights
+        if (d is not None and d["gen"] == self._gen
                 and d["dtype_spec"] == self.dtype and d["cutoff_spec"] == self.cutoff
                 and d["kernel"] == self.kernel
                 and d["bw_scalar_snap"] == bw_scalar
                 and ((bw_arr is None) == (d["bw_snap"] is None))
-                and (bw_arr is None or np.array_equal(bw_arr, d["bw_snap"]))):
+                and (bw_arr is None or self._bw_same(bw_arr, d["bw_snap"]))):
             return d
         L = _lib.load()
         t = _lib.torch()
-        N, D = self.data.shape
-        w = self.weights
-        sumw = float(np.sum(w)) if w is not None else float(N)
-        wmax = float(np.max(w)) if w is not None else 1.0
+        N, D = self.n_samples()
         hmin = float(np.min(bw_arr)) if bw_arr is not None else bw_scalar
         hmax = float(np.max(bw_arr)) if bw_arr is not None else bw_scalar
         if not hmin > 0:
             raise ValueError("bandwidths must be positive")
-        if w is not None:
-            center = np.average(self.data, axis=0, weights=w)
+        if self._d_data is not None:
+            # device-resident samples: statistics from the reduction kernels
+            d_data, d_w = self._d_data, self._d_w
+            if d_w is not None:
+                sums, sumw, _ = _lib.dev_moments(d_data, d_w, N, D)
+                wmax = float(_lib.dev_minmax(d_w, N, 1)[1][0])
+            else:
+                sums, sumw, _ = _lib.dev_moments(d_data, None, N, D)
+                wmax = 1.0
+            center = sums / sumw
+            if (bw_arr is not None and self._d_bw is not None and self._d_bw_for is self.bw
+                    and len(self._d_bw) >= N):
+                d_bw = self._d_bw[:N]
+            else:
+                d_bw = _lib.to_dev(bw_arr) if bw_arr is not None else None
         else:
-            center = self.data.mean(axis=0)
+            w = self._weights
+            sumw = float(np.sum(w)) if w is not None else float(N)
+            wmax = float(np.max(w)) if w is not None else 1.0
+            if w is not None:
+                center = np.average(self._data, axis=0, weights=w)
+            else:
+                center = self._data.mean(axis=0)
+            d_data = _lib.to_dev(self._data)
+            d_w = _lib.to_dev(w) if w is not None else None
+            d_bw = _lib.to_dev(bw_arr) if bw_arr is not None else None
         gauss = self.kernel == "gaussian"
         dtype = self.dtype
         dev = {"N": N, "D": D, "center": center, "kernel": self.kernel, "dtype_spec": self.dtype,
-               "cutoff": self._cutoff_radius(hmax) if gauss else 0.0,
-               "data_ref": self.data, "weights_ref": self.weights,
+               "cutoff": self._cutoff_radius(hmax) if gauss else 0.0, "gen": self._gen,
                "cutoff_spec": self.cutoff, "bw_scalar_snap": bw_scalar,
-               "bw_snap": None if bw_arr is None else bw_arr.copy()}
-        d_data = _lib.to_dev(self.data)
-        d_w = _lib.to_dev(w) if w is not None else None
-        d_bw = _lib.to_dev(bw_arr) if bw_arr is not None else None
+               "bw_snap": None if bw_arr is None else self._bw_snapshot(bw_arr)}
         w_scale = 1.0 / sumw
         st = _lib.stream()
         if dtype in ("auto", "float32"):
@@ -241,7 +328,8 @@ class TreeKDE:
                 raise ValueError("dtype='float32x2' has no cutoff mode")
             # hi parts live on the grid 2^-S, chosen so that |x - c| 2^S < 2^20 (two spare
             # bits for query points outside the sources' bounding box)
-            maxabs = float(np.max(np.abs(self.data - center))) if N else 1.0
+            mlo, mhi = _lib.dev_minmax(d_data, N, D)
+            maxabs = float(max(np.max(np.abs(mlo - center)), np.max(np.abs(mhi - center))))
             S = 20 - int(np.ceil(np.log2(max(maxabs, 1e-300))))
             dev["grid"] = float(2.0 ** S)
             lc_ref = np.log2(wmax * w_scale) - D * np.log2(hmin)

@@ -1037,6 +1037,68 @@ def test_plist_get_device_equals_host_decoder(oracle, tmp_path):
     assert np.array_equal(dev[0], host[0]) and np.array_equal(dev[1], host[1])
 
 
+@pytest.mark.parametrize("geo", ["flat", "rot_time"])
+def test_kdsource_device_resident_fit_equals_host_fit(oracle, tmp_path, monkeypatch, geo):
+    """KDSource.fit(device=True): records decoded, transformed and reduced on the GPU, kNN
+    from device tensors -- same N_eff / scaling (1e-13), bandwidths and densities as the
+    host fit (reference kdsource.py:132-213)."""
+    import kdsource_b200.api as kds
+    from kdsource_b200 import mcpl
+
+    monkeypatch.chdir(tmp_path)
+    parts, w = oracle.synthetic_particles(30000, seed=61, wseed=62, z_spread=2.0)
+    parts[:, 7] = np.random.default_rng(3).uniform(0.5, 5, len(parts))
+    w[::19] = 0.0
+    mcpl.write_mcpl_file("l.mcpl.gz", ekin=parts[:, 0], x=parts[:, 1], y=parts[:, 2],
+                         z=parts[:, 3], ux=parts[:, 4], uy=parts[:, 5], uz=parts[:, 6],
+                         time=parts[:, 7], weight=w, pdgcode=2112, srcname="t")
+    if geo == "flat":
+        mk = lambda: kds.geom.Geometry([kds.geom.Lethargy(10), kds.geom.SurfXY(),
+                                        kds.geom.Isotrop(keep_zdir=True)])
+        plkw = {}
+    else:
+        mk = lambda: kds.geom.Geometry([kds.geom.Energy(), kds.geom.Vol(), kds.geom.Polar(),
+                                        kds.geom.Decade()], trasl=[0.5, -1.0, 0.2],
+                                       rot=[0.05, -0.1, 0.2])
+        plkw = dict(trasl=[1.0, 2.0, -0.5], rot=[0.1, 0.0, -0.2], switch_x2z=True)
+    q = parts[:700].copy()
+    for method, kw in (("silv", {}), ("knn", dict(k=8, batch_size=5000)),
+                       ("auto", dict(Nmlcv=3000, Nbatch=5000, Nknn=8, show=False,
+                                     grid=np.logspace(-0.3, 0.5, 12)))):
+        if geo != "flat" and method == "auto":
+            continue
+        host = kds.KDSource(kds.PList("l.mcpl.gz", **plkw), mk(), bw=method)
+        host.fit(device=False, importance=None, **kw)
+        dev = kds.KDSource(kds.PList("l.mcpl.gz", **plkw), mk(), bw=method)
+        dev.fit(device=True, **kw)
+        assert dev.kde._d_data is not None and dev.kde._data is None  # nothing downloaded
+        assert dev.N_eff == pytest.approx(host.N_eff, rel=1e-13)
+        assert np.allclose(dev.scaling, host.scaling, rtol=1e-13, atol=0)
+        assert np.allclose(dev.kde.bw, host.kde.bw, rtol=1e-11, atol=0), method
+        eh, sh = host.evaluate(q.copy())
+        ed, sd = dev.evaluate(q.copy())
+        ok = eh > 1e-12 * eh.max()
+        assert np.allclose(ed[ok], eh[ok], rtol=2e-5) and np.allclose(sd[ok], sh[ok], rtol=2e-5)
+        assert np.allclose(dev.kde.data, host.kde.data, rtol=1e-12, atol=1e-12)  # lazy download
+        assert np.array_equal(dev.kde.weights, host.kde.weights)
+    # importance, given scaling, N / skip and the save file of a device fit
+    host = kds.KDSource(kds.PList("l.mcpl.gz", **plkw), mk(), bw="knn")
+    host.fit(N=12000, skip=500, device=False, importance=np.arange(1, host.geom.dim + 1),
+             k=5, batch_size=4000)
+    dev = kds.KDSource(kds.PList("l.mcpl.gz", **plkw), mk(), bw="knn")
+    dev.fit(N=12000, skip=500, device=True, importance=np.arange(1, host.geom.dim + 1),
+            k=5, batch_size=4000)
+    assert np.allclose(dev.scaling, host.scaling, rtol=1e-13)
+    assert np.allclose(dev.kde.bw, host.kde.bw, rtol=1e-11)
+    dev.save("dev.xml")
+    host.save("host.xml")
+    assert np.allclose(np.fromfile("dev_bws", dtype="float32"),
+                       np.fromfile("host_bws", dtype="float32"), rtol=1e-6)
+    fixed = kds.KDSource(kds.PList("l.mcpl.gz", **plkw), mk(), bw=0.4)
+    fixed.fit(device=True, scaling=host.scaling)
+    assert np.array_equal(fixed.scaling, host.scaling) and fixed.kde.bw == 0.4
+
+
 # ------------------------------------------------------------------ edge cases
 def test_edge_cases_small_ragged_and_degenerate(oracle):
     """Tile boundaries, single samples, empty inputs and the errors the reference
