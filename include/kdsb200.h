@@ -97,12 +97,13 @@ int kdsb200_hilbert_order(const double* d_data, uint64_t N, int D, const double*
                           const double* h_hi, void* d_scratch, uint32_t* d_perm, void* stream);
 /* Sources in d_perm order, tiles as kdsb200_pack_sources_f32 (same `mode`) but with
  * coordinates relative to the tile centre d_tilecen[t][D] (multiples of 1/grid, grid a
- * power of two); d_tilebox[t] = {lo[D], hi[D]} of x - h_center over the tile. */
+ * power of two); d_tilebox[t] = {lo[D], hi[D]} of x - h_center over the tile;
+ * d_tilehmax[t] = the tile's largest bandwidth (as passed in d_bw / bw_scalar). */
 int kdsb200_pack_sources_sorted_f32(const double* d_data, const double* d_w, const double* d_bw,
                                     double bw_scalar, uint64_t N, int D, const uint32_t* d_perm,
                                     const double* h_center, double grid, double w_scale,
                                     double lc_ref, int mode, float* d_packed, float* d_tilebox,
-                                    float* d_tilecen, void* stream);
+                                    float* d_tilecen, float* d_tilehmax, void* stream);
 uint64_t kdsb200_sorted_qpad(uint64_t M); /* query count padded to the CTA tile (1024) */
 /* queries in d_perm order as hi + lo floats, hi on the grid: d_qT [2D][Mpad] */
 int kdsb200_pack_queries_sorted_f32(const double* d_pts, uint64_t M, uint64_t Mpad, int D,
@@ -112,16 +113,19 @@ int kdsb200_sorted_ctas(void);
 int kdsb200_sorted_nsplit(uint64_t N, uint64_t M);
 uint64_t kdsb200_sorted_scratch_bytes(uint64_t N, uint64_t Mpad, int nsplit);
 /* d_out[d_perm_q[m]] = out_scale * sum over sources, as kdsb200_kde_eval_kernel_f32.
- * kernel 0 with cutoff > 0: hard radius, tiles beyond it skipped (exact: pairs inside
- * visited tiles are still masked one by one); kernel 1/2: `cutoff` = the largest support
- * radius (0: no culling); kernel 0 with cutoff <= 0: the exact sum over every tile.
- * *d_tiles_visited (device, may be NULL) = tiles loaded, summed over (1024-query block,
- * source split) work items: executed pairs = that * 512 * 1024. */
+ * kernel 0: cutoff > 0 = one hard radius for every source (KDEpy's TreeKDE derives it from
+ * the largest bandwidth); cutoff_rel > 0 = a hard radius cutoff_rel * h_i per source, tiles
+ * culled at cutoff_rel times their largest bandwidth; both <= 0 = the exact sum over every
+ * tile.  kernel 1/2: culled at the tile's largest support radius.  Culling is exact: a
+ * skipped tile holds no pair inside the radius and pairs inside visited tiles are still
+ * masked one by one.  *d_tiles_visited (device, may be NULL) = tiles loaded, summed over
+ * (1024-query block, source split) work items: executed pairs = that * 512 * 1024. */
 int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
-                                const float* d_tilecen, uint64_t N, int D, const float* d_qT,
-                                const uint32_t* d_perm_q, uint64_t M, uint64_t Mpad, int kernel,
-                                double cutoff, double out_scale, int nsplit, void* d_scratch,
-                                double* d_out, uint64_t* d_tiles_visited, void* stream);
+                                const float* d_tilecen, const float* d_tilehmax, uint64_t N,
+                                int D, const float* d_qT, const uint32_t* d_perm_q, uint64_t M,
+                                uint64_t Mpad, int kernel, double cutoff, double cutoff_rel,
+                                double out_scale, int nsplit, void* d_scratch, double* d_out,
+                                uint64_t* d_tiles_visited, void* stream);
 /* fp64 mode (1e-12 parity).  d_scratch: 2N + nsplit*M doubles. */
 int kdsb200_kde_eval_kernel_f64(const double* d_data, const double* d_w, const double* d_bw,
                                 double bw_scalar, uint64_t N, int D, double w_scale,

@@ -129,16 +129,17 @@ _SIGNATURES = {
     "kdsb200_pack_sources_sorted_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_u64,
                                                 c_int, c_void_p, c_double_p, c_double, c_double,
                                                 c_double, c_int, c_void_p, c_void_p, c_void_p,
-                                                c_void_p]),
+                                                c_void_p, c_void_p]),
     "kdsb200_sorted_qpad": (c_u64, [c_u64]),
     "kdsb200_pack_queries_sorted_f32": (c_int, [c_void_p, c_u64, c_u64, c_int, c_void_p,
                                                 c_double_p, c_double, c_void_p, c_void_p]),
     "kdsb200_sorted_ctas": (c_int, []),
     "kdsb200_sorted_nsplit": (c_int, [c_u64, c_u64]),
     "kdsb200_sorted_scratch_bytes": (c_u64, [c_u64, c_u64, c_int]),
-    "kdsb200_kde_eval_sorted_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_int, c_void_p,
-                                            c_void_p, c_u64, c_u64, c_int, c_double, c_double,
-                                            c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kdsb200_kde_eval_sorted_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_u64, c_int,
+                                            c_void_p, c_void_p, c_u64, c_u64, c_int, c_double,
+                                            c_double, c_double, c_int, c_void_p, c_void_p,
+                                            c_void_p, c_void_p]),
     "kdsb200_mlcv_gtile": (c_int, [c_int]),
     "kdsb200_mlcv_mpad": (c_u64, [c_u64]),
     "kdsb200_mlcv_nsplit": (c_int, [c_u64, c_u64]),

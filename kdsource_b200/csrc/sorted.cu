@@ -310,8 +310,10 @@ __global__ void __launch_bounds__(TS)
                        const double* __restrict__ bw, double bw_scalar, uint64_t N,
                        const uint32_t* __restrict__ perm, Center8 cen, double grid, double w_scale,
                        double lc_ref, int mode, float* __restrict__ packed,
-                       float* __restrict__ tilebox, float* __restrict__ tilecen) {
+                       float* __restrict__ tilebox, float* __restrict__ tilecen,
+                       float* __restrict__ tilehmax) {
   __shared__ double smn[D][TS / 32], smx[D][TS / 32];
+  __shared__ double shm[TS / 32];
   __shared__ double tc[D];
   const uint64_t t = blockIdx.x;
   const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
@@ -321,6 +323,12 @@ __global__ void __launch_bounds__(TS)
   double v[D];
 #pragma unroll
   for (int k = 0; k < D; k++) v[k] = live ? data[i * D + k] - cen.c[k] : 0.0;
+  {
+    double hm = live ? (bw ? bw[i] : bw_scalar) : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) hm = fmax(hm, __shfl_down_sync(0xffffffffu, hm, off));
+    if (lane == 0) shm[warp] = hm;
+  }
 #pragma unroll
   for (int k = 0; k < D; k++) {
     double a = live ? v[k] : INFINITY, b = live ? v[k] : -INFINITY;
@@ -350,6 +358,13 @@ __global__ void __launch_bounds__(TS)
     const double mid = rint(0.5 * (a + b) * grid) / grid;
     tc[j] = mid;
     tilecen[t * D + j] = (float)mid;
+  }
+  if (j == TS - 1) {  // largest bandwidth of the tile, rounded up
+    double hm = 0.0;
+    for (int e = 0; e < TS / 32; e++) hm = fmax(hm, shm[e]);
+    float hf = (float)hm;
+    if ((double)hf < hm) hf = nextafterf(hf, INFINITY);
+    tilehmax[t] = hf;
   }
   __syncthreads();
   constexpr int ROWS = D + 2;
@@ -404,19 +419,23 @@ struct SortedCtl {
   unsigned long long tiles_visited;  // sum over work items of the tiles they loaded
 };
 
-// KERN 0 gaussian, 1 epa, 2 box (rows as in kde_eval.cu); CUT: hard radius (cut2 > 0).
-template <int D, bool CUT, int KERN>
+// KERN 0 gaussian, 1 epa, 2 box (rows as in kde_eval.cu).  CUT 1: one hard radius for all
+// sources (cut2 = r^2); CUT 2: a hard radius proportional to each source's bandwidth
+// (r_i = c h_i, i.e. u <= cut2 in the kernel's units).  Tiles are culled at cull_r, or at
+// tilehmax[t] * rad_scale when rad_scale > 0 (per-tile radius).
+template <int D, int CUT, int KERN>
 __global__ void __launch_bounds__(SV_THREADS, 2)
     kde_eval_sorted_kernel(const float* __restrict__ packed, const float* __restrict__ tilebox,
-                           const float* __restrict__ tilecen, uint32_t n_tiles,
+                           const float* __restrict__ tilecen,
+                           const float* __restrict__ tilehmax, uint32_t n_tiles,
                            uint32_t tiles_per_split, int nsplit, const float* __restrict__ qT,
-                           uint64_t Mpad, float cut2, float cull_r, double out_scale,
-                           uint32_t* __restrict__ lists, SortedCtl* __restrict__ ctl,
-                           double* __restrict__ out) {
+                           uint64_t Mpad, float cut2, float cull_r, float rad_scale,
+                           double out_scale, uint32_t* __restrict__ lists,
+                           SortedCtl* __restrict__ ctl, double* __restrict__ out) {
   constexpr int ROWS = D + 2;
   constexpr int TILE_FLOATS = ROWS * TS;
   constexpr uint32_t TILE_BYTES = TILE_FLOATS * sizeof(float);
-  constexpr bool CULL = CUT || KERN != 0;
+  constexpr bool CULL = CUT != 0 || KERN != 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tiles = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t full[SV_STAGES];
@@ -496,8 +515,8 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
         qlo[k] = s_box[k];
         qhi[k] = s_box[D + k];
       }
-      // ordered list of the tiles of [t0, t1) whose box is within cull_r of the query box
-      const float r2 = cull_r * cull_r;
+      // ordered list of the tiles of [t0, t1) whose box is within the (tile's) radius of
+      // the query box
       for (uint32_t c0 = t0; c0 < t1; c0 += SV_THREADS) {
         const uint32_t t = c0 + tid;
         bool keep = false;
@@ -509,7 +528,8 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
             const float g = fmaxf(fmaxf(__ldg(bx + k) - qhi[k], qlo[k] - __ldg(bx + D + k)), 0.f);
             d2 = fmaf(g, g, d2);
           }
-          keep = d2 <= r2;
+          const float rt = rad_scale > 0.f ? __ldg(tilehmax + t) * rad_scale : cull_r;
+          keep = d2 <= rt * rt;
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_wcnt[warp] = __popc(bal);
@@ -578,10 +598,12 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
         const f2_t a01 = f2_pack(r[D].x, r[D].y), a23 = f2_pack(r[D].z, r[D].w);
         const f2_t l01 = f2_pack(r[D + 1].x, r[D + 1].y), l23 = f2_pack(r[D + 1].z, r[D + 1].w);
         f2_t c01 = 0ull, c23 = 0ull;
-        if (CUT) {
+        if (CUT == 1) {
           const f2_t cc = f2_pack(cut2, cut2);
           c01 = f2_mul(f2_mul(a01, a01), cc);
           c23 = f2_mul(f2_mul(a23, a23), cc);
+        } else if (CUT == 2) {
+          c01 = c23 = f2_pack(cut2, cut2);
         }
 #pragma unroll
         for (int qi = 0; qi < SV_Q; qi++) {
@@ -660,8 +682,9 @@ __global__ void reduce_scatter_kernel(const double* __restrict__ partial, int ns
 
 template <int D>
 static int launch_sorted(const float* packed, const float* tilebox, const float* tilecen,
-                         uint32_t ntl, uint32_t tps, int nsplit, const float* qT, uint64_t Mpad,
-                         int kern, float cut2, float cull_r, double out_scale, uint32_t* lists,
+                         const float* tilehmax, uint32_t ntl, uint32_t tps, int nsplit,
+                         const float* qT, uint64_t Mpad, int kern, int cut, float cut2,
+                         float cull_r, float rad_scale, double out_scale, uint32_t* lists,
                          SortedCtl* ctl, double* out, int ctas, cudaStream_t st) {
   const size_t smem = (size_t)SV_STAGES * (D + 2) * TS * sizeof(float);
 #define KDSB_SV(CUTV, KV)                                                                      \
@@ -669,13 +692,14 @@ static int launch_sorted(const float* packed, const float* tilebox, const float*
     KDSB_CUDA(cudaFuncSetAttribute(kde_eval_sorted_kernel<D, CUTV, KV>,                        \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     kde_eval_sorted_kernel<D, CUTV, KV><<<ctas, SV_THREADS, smem, st>>>(                        \
-        packed, tilebox, tilecen, ntl, tps, nsplit, qT, Mpad, cut2, cull_r, out_scale, lists,  \
-        ctl, out);                                                                             \
+        packed, tilebox, tilecen, tilehmax, ntl, tps, nsplit, qT, Mpad, cut2, cull_r,          \
+        rad_scale, out_scale, lists, ctl, out);                                                \
   } while (0)
-  if (kern == 1) KDSB_SV(false, 1);
-  else if (kern == 2) KDSB_SV(false, 2);
-  else if (cut2 > 0.f) KDSB_SV(true, 0);
-  else KDSB_SV(false, 0);
+  if (kern == 1) KDSB_SV(0, 1);
+  else if (kern == 2) KDSB_SV(0, 2);
+  else if (cut == 1) KDSB_SV(1, 0);
+  else if (cut == 2) KDSB_SV(2, 0);
+  else KDSB_SV(0, 0);
 #undef KDSB_SV
   KDSB_CUDA(cudaGetLastError());
   return 0;
@@ -786,7 +810,7 @@ int kdsb200_pack_sources_sorted_f32(const double* d_data, const double* d_w, con
                                     double bw_scalar, uint64_t N, int D, const uint32_t* d_perm,
                                     const double* h_center, double grid, double w_scale,
                                     double lc_ref, int mode, float* d_packed, float* d_tilebox,
-                                    float* d_tilecen, void* stream) {
+                                    float* d_tilecen, float* d_tilehmax, void* stream) {
   if (D < 1 || D > 8 || !(grid > 0)) {
     set_error("pack_sources_sorted: D=%d out of range 1..8 or grid <= 0", D);
     return 1;
@@ -801,7 +825,8 @@ int kdsb200_pack_sources_sorted_f32(const double* d_data, const double* d_w, con
   case d:                                                                                    \
     pack_sorted_kernel<d><<<(unsigned)ntl, TS, 0, st>>>(d_data, d_w, d_bw, bw_scalar, N,     \
                                                         d_perm, cen, grid, w_scale, lc_ref,  \
-                                                        mode, d_packed, d_tilebox, d_tilecen); \
+                                                        mode, d_packed, d_tilebox, d_tilecen,  \
+                                                        d_tilehmax);                         \
     break;
     KDSB_CASE(1)
     KDSB_CASE(2)
@@ -857,10 +882,11 @@ int kdsb200_sorted_nsplit(uint64_t N, uint64_t M) {
 }
 
 int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
-                                const float* d_tilecen, uint64_t N, int D, const float* d_qT,
-                                const uint32_t* d_perm_q, uint64_t M, uint64_t Mpad, int kernel,
-                                double cutoff, double out_scale, int nsplit, void* d_scratch,
-                                double* d_out, uint64_t* d_tiles_visited, void* stream) {
+                                const float* d_tilecen, const float* d_tilehmax, uint64_t N,
+                                int D, const float* d_qT, const uint32_t* d_perm_q, uint64_t M,
+                                uint64_t Mpad, int kernel, double cutoff, double cutoff_rel,
+                                double out_scale, int nsplit, void* d_scratch, double* d_out,
+                                uint64_t* d_tiles_visited, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (M == 0) return 0;
   if (kernel < 0 || kernel > 2) {
@@ -889,17 +915,36 @@ int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
   off = (off + 63) / 64 * 64;
   double* partial = (double*)(p + off);
   KDSB_CUDA(cudaMemsetAsync(ctl, 0, sizeof(SortedCtl), st));
-  const float cut2 = (kernel == 0 && cutoff > 0) ? (float)(cutoff * cutoff) : -1.f;
-  // culling radius: the cutoff (gaussian) or 1 in the support-radius units the finite
-  // kernels are packed in -- there the caller passes the largest support radius as `cutoff`;
-  // a relative margin keeps fp32 rounding of the boxes from dropping a boundary tile
-  const float cull_r = (float)(cutoff > 0 ? cutoff * (1.0 + 1e-5) : INFINITY);
+  // Gaussian kernel: cutoff > 0 is one hard radius for every source; cutoff_rel > 0 a hard
+  // radius c h_i per source (u = |q-x|^2 log2(e) / (2 h_i^2) <= c^2 log2(e) / 2 in the
+  // kernel's units), with tiles culled at c times the tile's largest bandwidth.  Finite
+  // kernels are packed with their support radius R_i in place of h_i and culled at the
+  // tile's largest R_i.  A relative margin keeps fp32 rounding of the boxes from dropping a
+  // boundary tile.
+  int cut = 0;
+  float cut2 = -1.f, cull_r = INFINITY, rad_scale = 0.f;
+  if (kernel == 0 && cutoff > 0) {
+    cut = 1;
+    cut2 = (float)(cutoff * cutoff);
+    cull_r = (float)(cutoff * (1.0 + 1e-5));
+  } else if (kernel == 0 && cutoff_rel > 0) {
+    cut = 2;
+    cut2 = (float)(cutoff_rel * cutoff_rel * 0.72134752044448170368);
+    rad_scale = (float)(cutoff_rel * (1.0 + 1e-5));
+  } else if (kernel != 0) {
+    rad_scale = (float)(1.0 + 1e-5);
+  }
+  if (rad_scale > 0.f && !d_tilehmax) {
+    set_error("kde_eval_sorted: per-tile radii requested without d_tilehmax");
+    return 1;
+  }
   int rc = 1;
   switch (D) {
 #define KDSB_CASE(d)                                                                          \
   case d:                                                                                     \
-    rc = launch_sorted<d>(d_packed, d_tilebox, d_tilecen, ntl, tps, nsplit, d_qT, Mpad,       \
-                          kernel, cut2, cull_r, out_scale, lists, ctl, partial, ctas, st);    \
+    rc = launch_sorted<d>(d_packed, d_tilebox, d_tilecen, d_tilehmax, ntl, tps, nsplit, d_qT, \
+                          Mpad, kernel, cut, cut2, cull_r, rad_scale, out_scale, lists, ctl,  \
+                          partial, ctas, st);                                                 \
     break;
     KDSB_CASE(1)
     KDSB_CASE(2)

@@ -42,6 +42,7 @@ __all__ = [
     "record_dtype",
     "build_header",
     "write_mcpl_file",
+    "pack_records",
     "patch_nparticles",
 ]
 
@@ -430,11 +431,31 @@ def write_mcpl_file(
     universal-pdgcode header options (flags bit2 / bit1 of
     ``clib/src/writemcpl.c:4-13``).
     """
-    import numbers
-
     filename = str(filename)
     if compress is None:
         compress = filename.endswith(".gz")
+    rec, hdr = pack_records(ekin=ekin, x=x, y=y, z=z, ux=ux, uy=uy, uz=uz, time=time,
+                            weight=weight, pdgcode=pdgcode, polx=polx, poly=poly, polz=polz,
+                            userflags=userflags, double_prec=double_prec, srcname=srcname)
+    opener = (
+        (lambda f: gzip.open(f, "wb", compresslevel=compresslevel))
+        if compress
+        else (lambda f: open(f, "wb"))
+    )
+    with opener(filename) as fh:
+        fh.write(hdr)
+        fh.write(rec.tobytes())
+    return os.path.abspath(filename)
+
+
+def pack_records(*, ekin, x, y, z, ux, uy, uz, time, weight, pdgcode, polx=None, poly=None,
+                 polz=None, userflags=None, double_prec=False, srcname="KDSource MCPL writer",
+                 nparticles=None):
+    """(structured record array, header bytes) of an MCPL-3 file holding these particles;
+    `nparticles` overrides the count written into the header (a file assembled from
+    several record arrays)."""
+    import numbers
+
     n = len(ekin)
     uni_pdg = int(pdgcode) if isinstance(pdgcode, numbers.Integral) else 0
     uni_w = float(weight) if isinstance(weight, numbers.Number) else 0.0
@@ -462,14 +483,7 @@ def write_mcpl_file(
     if userflags is not None:
         rec["userflags"] = userflags
     hdr = build_header(
-        n, srcname, not double_prec, has_pol, uni_pdg, uni_w, userflags is not None
+        n if nparticles is None else nparticles, srcname, not double_prec, has_pol, uni_pdg,
+        uni_w, userflags is not None
     )
-    opener = (
-        (lambda f: gzip.open(f, "wb", compresslevel=compresslevel))
-        if compress
-        else (lambda f: open(f, "wb"))
-    )
-    with opener(filename) as fh:
-        fh.write(hdr)
-        fh.write(rec.tobytes())
-    return os.path.abspath(filename)
+    return rec, hdr

@@ -10,7 +10,9 @@ ABI (``kdsb200_kde_eval_f32`` / ``_f64``).
 Semantics: ``out[m] = sum_i w_i/sum(w) (2 pi)^(-d/2) h_i^-d exp(-|q_m - x_i|^2 /
 (2 h_i^2))``.  ``cutoff=None`` is the exact sum (KDEpy NaiveKDE semantics);
 ``cutoff="treekde"`` applies the hard support radius KDEpy's TreeKDE derives
-from the largest bandwidth; a float is an explicit radius.
+from the largest bandwidth; a float is an explicit radius; ``cutoff="adaptive"``
+cuts every source at the radius that rule gives relative to its own bandwidth
+(r_i = c h_i), which is what keeps the truncation local for per-sample bandwidths.
 
 ``dtype``: ``"float32"`` -- sources ordered along a Hilbert curve and stored in tiles of
 512 with coordinates relative to the tile centre, so the fp32 rounding error scales with
@@ -213,13 +215,22 @@ class TreeKDE:
         return len(bw) == len(snap) and np.array_equal(bw, snap)
 
     def _cutoff_radius(self, bw_max):
-        if self.cutoff is None:
+        if self.cutoff is None or self.cutoff == "adaptive":
             return 0.0
         if isinstance(self.cutoff, str):
             if self.cutoff != "treekde":
-                raise ValueError("cutoff must be None, 'treekde' or a radius")
+                raise ValueError("cutoff must be None, 'treekde', 'adaptive' or a radius")
             return treekde_radius(bw_max)
         return float(self.cutoff)
+
+    def _cutoff_rel(self, bw_min):
+        """cutoff="adaptive": every source is cut at r_i = c h_i, with c the ratio KDEpy's
+        rule gives for the smallest bandwidth (so no source is cut closer than TreeKDE would
+        cut it).  The same as "treekde" for one bandwidth; with per-sample bandwidths the
+        radius follows the local bandwidth instead of the largest one of the whole list."""
+        if self.cutoff != "adaptive":
+            return 0.0
+        return treekde_radius(bw_min) / bw_min
 
     def _device_state(self):
         """Upload and pack the fitted sources (cached until data/bw change)."""
@@ -299,11 +310,12 @@ class TreeKDE:
             packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
             tilebox = _lib.empty(ntl * 2 * D, t.float32)
             tilecen = _lib.empty(ntl * D, t.float32)
+            tilehmax = _lib.empty(ntl, t.float32)
             cen_keep, cen_p = _lib.hostvec(center)
             _lib.check(L.kdsb200_pack_sources_sorted_f32(
                 _lib.ptr(d_data), _lib.ptr(d_w), _lib.ptr(d_h), bw_scalar * sc, N, D,
                 _lib.ptr(perm), cen_p, grid, w_scale, lc_ref, 0 if gauss else 1,
-                _lib.ptr(packed), _lib.ptr(tilebox), _lib.ptr(tilecen), st))
+                _lib.ptr(packed), _lib.ptr(tilebox), _lib.ptr(tilecen), _lib.ptr(tilehmax), st))
             box = tilebox.cpu().numpy().reshape(ntl, 2, D)
             extent = float(np.max(box[:, 1] - box[:, 0])) / 2 if N > 1 else 0.0
             if (dtype == "auto" and gauss and self.cutoff is None
@@ -315,7 +327,8 @@ class TreeKDE:
                     norm = (2 * np.pi) ** (-D / 2)
                 else:
                     norm = (0.5 * (D + 2) if self.kernel == "epa" else 1.0) / unit_ball_volume(D)
-                dev.update(packed=packed, tilebox=tilebox, tilecen=tilecen, grid=grid,
+                dev.update(packed=packed, tilebox=tilebox, tilecen=tilecen, tilehmax=tilehmax,
+                           cull_rel=self._cutoff_rel(hmin) if gauss else 0.0, grid=grid,
                            lo=mmh[:D].copy(), hi=mmh[D:].copy(), tile_extent=extent,
                            out_scale=float(2.0 ** lc_ref * norm),
                            cull=dev["cutoff"] if gauss else hmax * sc)
@@ -411,10 +424,10 @@ class TreeKDE:
             scratch = _lib.empty(L.kdsb200_sorted_scratch_bytes(N, Mpad, nsplit), t.uint8)
             visited = _lib.empty(1, t.int64)
             _lib.check(L.kdsb200_kde_eval_sorted_f32(
-                _lib.ptr(dev["packed"]), _lib.ptr(dev["tilebox"]), _lib.ptr(dev["tilecen"]), N, D,
-                _lib.ptr(qT), _lib.ptr(perm_q), M, Mpad, _KERNEL_ID[dev["kernel"]], dev["cull"],
-                dev["out_scale"], nsplit, _lib.ptr(scratch), _lib.ptr(d_out), _lib.ptr(visited),
-                st))
+                _lib.ptr(dev["packed"]), _lib.ptr(dev["tilebox"]), _lib.ptr(dev["tilecen"]),
+                _lib.ptr(dev["tilehmax"]), N, D, _lib.ptr(qT), _lib.ptr(perm_q), M, Mpad,
+                _KERNEL_ID[dev["kernel"]], dev["cull"], dev["cull_rel"], dev["out_scale"], nsplit,
+                _lib.ptr(scratch), _lib.ptr(d_out), _lib.ptr(visited), st))
             #: device counter of the last call: tiles loaded, summed over the (1024-query
             #: block, source split) work items; executed pairs = that * 512 * 1024
             self.last_tiles_visited = visited

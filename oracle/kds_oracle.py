@@ -119,13 +119,15 @@ def normalise_weights(weights, N):
     return w / w.sum()
 
 
-def kde_sum(data, weights, bw, points, cutoff=None, chunk=256, kernel="gaussian"):
+def kde_sum(data, weights, bw, points, cutoff=None, chunk=256, kernel="gaussian",
+            cutoff_rel=None):
     """Kernel sum (KDEpy Naive/TreeKDE.evaluate with norm=2), the arithmetic behind
     python/kdsource/kdsource.py:239 and kde.py:146-151:
 
         out[m] = sum_i w_i/sum(w) (2 pi)^(-d/2) h_i^-d exp(-|q_m-x_i|^2/(2 h_i^2))
 
-    ``cutoff``: hard support radius (None = exact sum).  ``kernel`` "epa"/"box"
+    ``cutoff``: hard support radius (None = exact sum); ``cutoff_rel``: a hard radius
+    ``cutoff_rel * h_i`` per source instead.  ``kernel`` "epa"/"box"
     (kdsource.py:60-65): KDEpy's radial finite-support kernels, published form
     (KDEpy is not in the tree -- restated from its documentation, pinned against
     scikit-learn's KernelDensity in tests/test_oracle.py): bandwidth = standard
@@ -172,6 +174,8 @@ def kde_sum(data, weights, bw, points, cutoff=None, chunk=256, kernel="gaussian"
         K = coef * np.exp(-r2 * ih2)
         if cutoff is not None:
             K = np.where(r2 <= cutoff * cutoff, K, 0.0)
+        if cutoff_rel is not None:  # per-source hard radius r_i = cutoff_rel * h_i
+            K = np.where(r2 <= (cutoff_rel * h) ** 2, K, 0.0)
         out[s:s + chunk] = K.sum(axis=1)
     return out
 

@@ -263,6 +263,25 @@ def test_evaluate_tile_culling_is_exact(oracle, bwkind, D):
     ref_x = oracle.kde_sum_c(data, w, bw, q[20:600])
     assert np.max(np.abs(exact[20:600] / ref_x - 1)) < 1e-5
     if bwkind == "adaptive":
+        # cutoff="adaptive": every source cut at c h_i, tiles culled at c * (their largest
+        # bandwidth); with bandwidths spread over a decade the single-radius rule would
+        # keep almost every tile, the per-source rule does not
+        bwa = bw.copy()
+        bwa[::97] *= 10.0
+        ka = TreeKDE(bw=bwa, cutoff="adaptive").fit(data, w)
+        ga = ka.evaluate(q)
+        va = int(ka.last_tiles_visited.item())
+        c = treekde_radius(float(bwa.min())) / float(bwa.min())
+        sel = rng.choice(np.arange(20, M), 300, replace=False)
+        ra = oracle.kde_sum(data, w, bwa, q[sel], cutoff_rel=c)
+        rr = np.array([np.min(np.abs(np.sqrt(((data - q[m]) ** 2).sum(axis=1)) / (c * bwa) - 1))
+                       for m in sel])
+        good = (rr > 1e-5) & (ra > 0)
+        assert good.sum() > 200
+        assert np.max(np.abs(ga[sel][good] / ra[good] - 1)) < 1e-5
+        kt = TreeKDE(bw=bwa, cutoff="treekde").fit(data, w)
+        kt.evaluate(q)
+        assert va < 0.6 * int(kt.last_tiles_visited.item())
         return
     # finite-support kernels are culled at their support radius
     for kern in ("epa", "box"):
@@ -1064,7 +1083,7 @@ def test_kdsource_device_resident_fit_equals_host_fit(oracle, tmp_path, monkeypa
     q = parts[:700].copy()
     for method, kw in (("silv", {}), ("knn", dict(k=8, batch_size=5000)),
                        ("auto", dict(Nmlcv=3000, Nbatch=5000, Nknn=8, show=False,
-                                     grid=np.logspace(-0.3, 0.5, 12)))):
+                                     grid=np.logspace(-1.0, 1.0, 25)))):
         if geo != "flat" and method == "auto":
             continue
         host = kds.KDSource(kds.PList("l.mcpl.gz", **plkw), mk(), bw=method)

@@ -241,57 +241,138 @@ def config4(args):
 
 
 def config5(args):
-    """Full pipeline on a 1e8-particle list: kNN + MLCV bandwidth (bw_auto), density map,
-    1e10 resamples.  The density map (1e9 queries = 1e17 pairs) is bounded to
-    1e5*scale queries per rank and its rate reported; resampled records stay in HBM."""
+    """Full pipeline on a 1e8-particle list, as a user would run it: an MCPL file on disk ->
+    KDSource.fit with the kNN + MLCV bandwidth (bw="auto"), device-resident and sharded over
+    the ranks -> a density map of 1e9*scale query points (hard support radius proportional to
+    each source's bandwidth, tiles beyond it culled exactly) -> 1e10 resamples.  Query points
+    are jittered copies of list entries drawn on the device (they follow the data, where the
+    work is); every rank evaluates its share in blocks of 2^25."""
+    import kdsource_b200.api as kds
+    from kdsource_b200 import mcpl
+
     rank, world = dist.rank_world()
     N = int(args.n5)
-    need = 30.0 * N / 1e8 * min(world, 8)
-    if mem_available_gb() < need:
-        return {"config": 5, "skipped": "needs ~{:.0f} GB of host memory, {:.0f} available".format(
-            need, mem_available_gb())}
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    tmp = os.path.join(base, "kdsb_c5")
+    fn = os.path.join(tmp, "list.mcpl")
+    # the list: every rank draws its share and writes its records into place
     t0 = time.perf_counter()
-    ps, w, g, sc, data = synthetic_scaled(N, seed=5)
-    t_gen = time.perf_counter() - t0
-    grid = np.logspace(-0.7, 0.5, 32)  # wide: the optimum factor on the kNN seed is not known
+    lo, hi = dist.shard_range(N, rank, world)
+    ps, w, g, _, _ = synthetic_scaled(hi - lo, seed=5 + 1000 * rank, wseed=777 + rank)
+    rec, hdr = mcpl.pack_records(ekin=ps[:, 0], x=ps[:, 1], y=ps[:, 2], z=ps[:, 3], ux=ps[:, 4],
+                                 uy=ps[:, 5], uz=ps[:, 6], time=ps[:, 7], weight=w, pdgcode=2112,
+                                 srcname="synthetic", nparticles=N)
+    if rank == 0:
+        shutil.rmtree(tmp, ignore_errors=True)
+        os.makedirs(tmp)
+        with open(fn, "wb") as fh:
+            fh.write(hdr)
+            fh.truncate(len(hdr) + N * rec.dtype.itemsize)
+    dist.barrier()
+    with open(fn, "r+b") as fh:
+        fh.seek(len(hdr) + lo * rec.dtype.itemsize)
+        fh.write(rec.tobytes())
+    del rec, ps, w
+    dist.barrier()
+    t_list = time.perf_counter() - t0
+    note = None
+    try:
+        s = kds.KDSource(kds.PList(fn, set_params=False), g, bw="auto")
+        grid = np.logspace(-0.7, 0.5, 32)  # wide: the optimum factor on the kNN seed is not known
 
-    def auto():
-        try:
-            return kde.bw_auto(data, w, grid=grid, Nmlcv=1e6, Nbatch=1e4, Nknn=10, show=False)
-        except Exception as e:  # maximum at a grid edge: keep the kNN seed, report it
-            print("bw_auto:", e)
+        def fit():
+            try:
+                s.fit(device=True, sharded=world > 1, Nmlcv=1e6, Nbatch=1e4, Nknn=10, show=False,
+                      grid=grid)
+            except Exception as e:  # maximum at a grid edge: keep the kNN seed, report it
+                if "Maximum not found" not in str(e):
+                    raise
+                print("bw_auto:", e)
+                s.fit(device=True, sharded=world > 1, bw_method="knn", k=10, batch_size=10000)
+                return str(e)
             return None
 
-    bw, t_bw = timed(auto)
-    note = None
-    if bw is None:
-        note = "MLCV maximum at a grid edge for this list: kNN bandwidth used"
-        bw = kde.bw_knn(data, w, k=10, batch_size=10000)
-    Mq = int(1e5 * args.scale)
-    q = synthetic_scaled(Mq, seed=999 + rank, wseed=1)[4]
-    k = TreeKDE(bw=bw).fit(data, w)
-    _, t_pack = timed(lambda: k._device_state())
-    k.evaluate(q[:1024], shard=False)
-    dens, t_eval = timed(lambda: k.evaluate(q, shard=False))
-    smp, t_setup = timed(lambda: DeviceSampler(ps, w, bw.astype(np.float32),
-                                               make_geom_struct(g, sc, "g")))
-    n_res = 10_000_000_000
-    lo, hi = dist.shard_range(n_res, rank, world)
-    per = 125_000_000
-    out = _lib.empty(per * 36, torch.uint8)
+        note, t_fit = timed(fit)
+        k = s.kde
+        k.cutoff = "adaptive"
+        _, t_pack = timed(lambda: k._device_state())
+        dev = k._device_state()
+        # density map: jittered copies of list entries, generated on the device
+        M_tot = int(1e9 * args.scale)
+        qlo, qhi = dist.shard_range(M_tot, rank, world)
+        blk = 1 << 25
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(4242 + rank)
+        d_data = k._d_data
+        bw_typ = float(np.median(k.bw[::1000]))
 
-    def gen():
-        for s in range(lo, hi, per):
-            smp.sample_device(min(per, hi - s), seed=13, first=s, out=out)
+        def density_map():
+            visited, checksum, nz = 0, 0.0, 0
+            for q0 in range(qlo, qhi, blk):
+                m = min(blk, qhi - q0)
+                idx = torch.randint(0, N, (m,), device="cuda", generator=gen)
+                d_q = d_data[idx] + bw_typ * torch.randn((m, d_data.shape[1]), device="cuda",
+                                                         dtype=torch.float64, generator=gen)
+                out = k.evaluate_device(d_q, m, dev)
+                visited += int(k.last_tiles_visited.item())
+                checksum += float(out.sum().item())
+                nz += int((out > 0).sum().item())
+            return visited, checksum, nz
 
-    _, t_res = timed(gen)
-    return {"config": 5, "N": N, "host_list_generation_s": t_gen, "bw_auto_s": t_bw, "note": note,
-            "source_pack_upload_s": t_pack, "density_queries": Mq * world,
-            "density_s": t_eval, "pairs_per_s_e2e": float(N) * Mq * world / t_eval,
-            "density_map_1e9_queries_projected_s": 1e9 * N / (float(N) * Mq * world / t_eval),
-            "density_checksum": sum_ranks(float(np.sum(dens))),
-            "sampler_setup_s": t_setup, "resamples": n_res, "resample_s": t_res,
-            "resampled_particles_per_s": n_res / t_res}
+        (visited, checksum, nz), t_map = timed(density_map)
+        executed = sum_ranks(visited * 512.0 * 1024.0)
+        dense = float(N) * M_tot
+        # spot check against the oracle's per-source hard radius on a few queries (rank 0)
+        spot = None
+        if rank == 0:
+            from oracle import kds_oracle as O
+
+            m = 64
+            idx = torch.randint(0, N, (m,), device="cuda", generator=gen)
+            d_q = d_data[idx] + bw_typ * torch.randn((m, 6), device="cuda", dtype=torch.float64,
+                                                     generator=gen)
+            got = k.evaluate_device(d_q, m, dev).cpu().numpy()
+            nsub = min(N, 20_000_000)  # the oracle on a bounded prefix of the sources
+            ksub = TreeKDE(bw=k.bw[:nsub], cutoff="adaptive").fit(k.data[:nsub], k.weights[:nsub])
+            gsub = ksub.evaluate(d_q.cpu().numpy(), shard=False)
+            c = dev["cull_rel"]
+            ref = O.kde_sum(k.data[:nsub], k.weights[:nsub], k.bw[:nsub], d_q.cpu().numpy(),
+                            cutoff_rel=c, chunk=4)
+            ok = ref > 1e-9 * ref.max()
+            spot = {"queries": m, "sources": nsub,
+                    "max_rel_err_vs_oracle": float(np.max(np.abs(gsub[ok] / ref[ok] - 1)))}
+            del ksub
+        # resampling: records stay in HBM
+        parts_d, ws_d = s.plist.get_device(-1)
+        smp, t_setup = timed(lambda: DeviceSampler(parts_d, ws_d, k.bw.astype(np.float32),
+                                                   make_geom_struct(g, s.scaling, "g")))
+        del parts_d, ws_d
+        n_res = 10_000_000_000
+        rlo, rhi = dist.shard_range(n_res, rank, world)
+        per = 125_000_000
+        out = _lib.empty(per * 36, torch.uint8)
+
+        def gen_res():
+            for s0 in range(rlo, rhi, per):
+                smp.sample_device(min(per, rhi - s0), seed=13, first=s0, out=out)
+
+        _, t_res = timed(gen_res)
+    finally:
+        dist.barrier()
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return {"config": 5, "N": N, "list_generation_and_write_s": t_list,
+            "list_file": "uncompressed MCPL-3 on " + base, "fit_bw_auto_s": t_fit, "note": note,
+            "N_eff": float(s.N_eff), "bw_min_med_max": [float(np.min(k.bw)), bw_typ,
+                                                        float(np.max(k.bw))],
+            "source_order_pack_s": t_pack, "tile_extent": dev["tile_extent"],
+            "cutoff": "adaptive: r_i = {:.3f} h_i".format(dev["cull_rel"]),
+            "density_queries": M_tot, "density_map_s": t_map,
+            "dense_equivalent_pairs_per_s": dense / t_map,
+            "executed_pairs_per_s": executed / t_map, "visited_fraction": executed / dense,
+            "density_checksum": sum_ranks(checksum), "nonzero_queries": sum_ranks(nz),
+            "spot_check": spot, "sampler_setup_s": t_setup, "resamples": n_res,
+            "resample_s": t_res, "resampled_particles_per_s": n_res / t_res}
 
 
 def main():
