@@ -327,12 +327,12 @@ def config5(args):
         if rank == 0:
             from oracle import kds_oracle as O
 
-            m = 64
+            m = 32
             idx = torch.randint(0, N, (m,), device="cuda", generator=gen)
             d_q = d_data[idx] + bw_typ * torch.randn((m, 6), device="cuda", dtype=torch.float64,
                                                      generator=gen)
             got = k.evaluate_device(d_q, m, dev).cpu().numpy()
-            nsub = min(N, 20_000_000)  # the oracle on a bounded prefix of the sources
+            nsub = min(N, 5_000_000)  # the oracle on a bounded prefix of the sources
             ksub = TreeKDE(bw=k.bw[:nsub], cutoff="adaptive").fit(k.data[:nsub], k.weights[:nsub])
             gsub = ksub.evaluate(d_q.cpu().numpy(), shard=False)
             c = dev["cull_rel"]
