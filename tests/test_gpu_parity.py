@@ -264,10 +264,10 @@ def test_evaluate_tile_culling_is_exact(oracle, bwkind, D):
     assert np.max(np.abs(exact[20:600] / ref_x - 1)) < 1e-5
     if bwkind == "adaptive":
         # cutoff="adaptive": every source cut at c h_i, tiles culled at c * (their largest
-        # bandwidth); with bandwidths spread over a decade the single-radius rule would
-        # keep almost every tile, the per-source rule does not
-        bwa = bw.copy()
-        bwa[::97] *= 10.0
+        # bandwidth); with bandwidths that grow towards the tails the single-radius rule
+        # (from the largest bandwidth of the list) keeps almost every tile, the per-source
+        # rule does not
+        bwa = h * (0.7 + 0.3 * (data ** 2).sum(axis=1))  # wide in the tails, as kNN gives
         ka = TreeKDE(bw=bwa, cutoff="adaptive").fit(data, w)
         ga = ka.evaluate(q)
         va = int(ka.last_tiles_visited.item())
