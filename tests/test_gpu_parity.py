@@ -1109,8 +1109,8 @@ def test_kdsource_device_resident_fit_equals_host_fit(oracle, tmp_path, monkeypa
             k=5, batch_size=4000)
     assert np.allclose(dev.scaling, host.scaling, rtol=1e-13)
     assert np.allclose(dev.kde.bw, host.kde.bw, rtol=1e-11)
-    dev.save("dev.xml")
-    host.save("host.xml")
+    dev.save("dev.xml", bwfile="dev_bws")
+    host.save("host.xml", bwfile="host_bws")
     assert np.allclose(np.fromfile("dev_bws", dtype="float32"),
                        np.fromfile("host_bws", dtype="float32"), rtol=1e-6)
     fixed = kds.KDSource(kds.PList("l.mcpl.gz", **plkw), mk(), bw=0.4)
