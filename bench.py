@@ -264,41 +264,57 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
     parts, w, g, scaling, data = synthetic_scaled(N)
     _, _, _, _, q = synthetic_scaled(M, seed=54321, wseed=1)
     bw = kde.bw_silv(D_MLCV, np.sum(w) ** 2 / np.sum(w ** 2))
-    k = TreeKDE(bw=bw, dtype="float32").fit(data, w)
-    dev = k._device_state()
+
+    def eval_leg(kd, d_qq, Mq, lane_ops, reps=5):
+        """Device rate of one TreeKDE configuration: dense-equivalent and executed pairs/s
+        (they differ when tiles are culled), roofline on the executed pairs."""
+        dv = kd._device_state()
+        for _ in range(3):
+            kd.evaluate_device(d_qq, Mq, dv)
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            ts += time_events(t, lambda: kd.evaluate_device(d_qq, Mq, dv), 1)
+        ms_ = float(np.median(ts))
+        dense = float(dv["N"]) * Mq
+        executed = dense
+        if dv["dtype"] == "float32":
+            executed = float(kd.last_tiles_visited.item()) * 512.0 * 1024.0
+        return {"kernel": dv["dtype"], "cutoff": kd.cutoff, "ms": ms_,
+                "pairs_per_s": dense / (ms_ * 1e-3),
+                "executed_pairs_per_s": executed / (ms_ * 1e-3),
+                "visited_fraction": executed / dense,
+                "roofline": {"bound": "fp32", "achieved": executed * lane_ops / (ms_ * 1e-3) / 1e9,
+                             "peak": peaks["ffma2"] / 1e9, "unit": "Glane-op/s",
+                             "frac": executed * lane_ops / (ms_ * 1e-3) / peaks["ffma2"],
+                             "per_unit": "{} FP32 lane-ops + 1 MUFU per executed pair (d=6); "
+                                         "includes ordering and packing the queries".format(lane_ops),
+                             "traffic": None}}
+
     d_q = _lib.to_dev(q)
-
-    def ev():
-        return k.evaluate_device(d_q, M, dev)
-
-    for _ in range(3):
-        ev()
-    ts = []
-    for _ in range(5):
-        flush.zero_()
-        ts += time_events(t, ev, 1)
-    ms = float(np.median(ts))
-    pairs = float(N) * M
+    # the default path of the public API (dtype="auto"): ordered tiles, tile-local coordinates
+    k = TreeKDE(bw=bw).fit(data, w)
+    leg = eval_leg(k, d_q, M, 13)
     sub["evaluate"] = {
-        "workload": "N=1e5 sources x M={:g} queries, d=6, Silverman bw".format(M),
-        "pairs_per_s": pairs / (ms * 1e-3), "ms": ms,
-        "roofline": {"bound": "fp32", "achieved": pairs * 13 / (ms * 1e-3) / 1e9,
-                     "peak": peaks["ffma2"] / 1e9, "unit": "Glane-op/s",
-                     "frac": pairs * 13 / (ms * 1e-3) / peaks["ffma2"],
-                     "per_unit": "13 FP32 lane-ops + 1 MUFU per pair (d=6)", "traffic": None}}
-    # split-coordinate kernel (dtype="float32x2", what dtype="auto" selects for small bandwidths)
-    k2 = TreeKDE(bw=bw, dtype="float32x2").fit(data, w)
-    dev2 = k2._device_state()
-    for _ in range(2):
-        k2.evaluate_device(d_q, M, dev2)
-    ms2 = float(np.median(time_events(t, lambda: k2.evaluate_device(d_q, M, dev2), 3)))
-    sub["evaluate"]["float32x2"] = {
-        "pairs_per_s": pairs / (ms2 * 1e-3), "ms": ms2,
-        "roofline": {"bound": "fp32", "achieved": pairs * 25 / (ms2 * 1e-3) / 1e9,
-                     "peak": peaks["ffma2"] / 1e9, "unit": "Glane-op/s",
-                     "frac": pairs * 25 / (ms2 * 1e-3) / peaks["ffma2"],
-                     "per_unit": "25 FP32 lane-ops + 1 MUFU per pair (d=6)", "traffic": None}}
-    del k2, dev2
+        "workload": "N=1e5 sources x M={:g} queries, d=6, Silverman bw, dtype='auto' (the "
+                    "default)".format(M), **leg}
+    ms = leg["ms"]
+    # the other kernels on the same shape
+    for name, lane in (("float32x2", 25), ("float32_dense", 13)):
+        kk = TreeKDE(bw=bw, dtype=name).fit(data, w)
+        sub["evaluate"][name] = eval_leg(kk, d_q, M, lane, reps=3)
+        del kk
+    if not quick:
+        # a list of 1e6 (Silverman 0.23 of the spread, where the unordered fp32 kernel is past
+        # its 1e-5 domain): the default path, exact and with KDEpy's hard support radius
+        N2 = 1_000_000
+        _, w2, _, _, data2 = synthetic_scaled(N2)
+        bw2 = kde.bw_silv(D_MLCV, np.sum(w2) ** 2 / np.sum(w2 ** 2))
+        for name, cut in (("auto_N1e6", None), ("auto_N1e6_cutoff_treekde", "treekde")):
+            kk = TreeKDE(bw=bw2, cutoff=cut).fit(data2, w2)
+            sub["evaluate"][name] = eval_leg(kk, d_q, M, 13, reps=3)
+            del kk
+        del data2, w2
     if cpu:
         from oracle import kds_oracle as O
 

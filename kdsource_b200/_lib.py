@@ -292,3 +292,19 @@ def dev_moments(d_vecs, d_w, N, D, center=None, power=1):
                                      ptr(out), stream()))
     h = out.cpu().numpy()
     return h[:D].copy(), float(h[D]), float(h[D + 1])
+
+
+# ---------------------------------------------------------------------------
+# pinned staging buffers (grow-only cache: cudaHostAlloc is slow, reuse matters)
+# ---------------------------------------------------------------------------
+_pinned = {}
+
+
+def pinned(tag, nelem, dtype):
+    """A pinned host tensor of at least `nelem` elements, cached under `tag`."""
+    t = torch()
+    buf = _pinned.get((tag, dtype))
+    if buf is None or buf.numel() < nelem:
+        buf = t.empty(int(nelem), dtype=dtype, pin_memory=True)
+        _pinned[(tag, dtype)] = buf
+    return buf

@@ -162,10 +162,13 @@ class TreeKDE:
     def __call__(self, points):
         return self.evaluate(points)
 
-    def evaluate(self, points, chunk=1 << 22, shard=True):
+    def evaluate(self, points, chunk=None, shard=True):
         """Densities at `points` ((obs, dims)).  With torch.distributed initialised
         and ``shard=True`` the query points are split contiguously over the ranks
-        (sources replicated) and the result is assembled on every rank."""
+        (sources replicated) and the result is assembled on every rank.
+
+        The points travel in pieces through two pinned staging buffers: the upload of piece
+        i+1 and the download of piece i-1 overlap the kernels of piece i."""
         if self._data is None and self._d_data is None:
             raise ValueError("Must call fit before evaluating.")
         D = self.n_samples()[1]
@@ -178,13 +181,53 @@ class TreeKDE:
 
         rank, world = _dist.rank_world()
         lo, hi = _dist.shard_range(len(pts), rank, world) if shard else (0, len(pts))
-        out = np.zeros(hi - lo, dtype=np.float64)
+        n = hi - lo
+        out = np.zeros(n, dtype=np.float64)
         dev = self._device_state()
-        for s in range(lo, hi, chunk):
-            e = min(s + chunk, hi)
-            d_pts = _lib.to_dev(pts[s:e])
-            d_out = self.evaluate_device(d_pts, e - s, dev)
-            out[s - lo:e - lo] = d_out.cpu().numpy()
+        if chunk is None:  # at least four pieces once the input is large enough to overlap
+            chunk = int(min(1 << 22, max(1 << 16, -(-n // 4))))
+        if n <= chunk:
+            if n:
+                d_out = self.evaluate_device(_lib.to_dev(pts[lo:hi]), n, dev)
+                out[:] = d_out.cpu().numpy()
+        else:
+            t = _lib.torch()
+            main, side = t.cuda.current_stream(), t.cuda.Stream()
+            pin_in = [_lib.pinned(("eval_in", b), chunk * D, t.float64) for b in range(2)]
+            pin_out = [_lib.pinned(("eval_out", b), chunk, t.float64) for b in range(2)]
+            pending = [None, None]
+            visited = [0]
+
+            def finish(b):
+                if pending[b] is not None:
+                    done, s0, m0, keep = pending[b]
+                    done.synchronize()
+                    out[s0 - lo:s0 - lo + m0] = pin_out[b][:m0].numpy()
+                    if keep[2] is not None:
+                        visited[0] += int(keep[2].item())
+                    pending[b] = None
+
+            for i, s0 in enumerate(range(lo, hi, chunk)):
+                b, m = i % 2, min(chunk, hi - s0)
+                finish(b)  # piece i-2: its staging buffers are free again
+                stage = pin_in[b][:m * D].view(m, D)
+                stage.numpy()[...] = pts[s0:s0 + m]
+                with t.cuda.stream(side):
+                    d_pts = stage.to("cuda", non_blocking=True)
+                    up = t.cuda.Event()
+                    up.record(side)
+                d_pts.record_stream(main)
+                main.wait_event(up)
+                d_out = self.evaluate_device(d_pts, m, dev)
+                pin_out[b][:m].copy_(d_out, non_blocking=True)
+                done = t.cuda.Event()
+                done.record(main)
+                pending[b] = (done, s0, m, (d_pts, d_out, getattr(self, "last_tiles_visited", None)
+                                            if dev["dtype"] == "float32" else None))
+            finish(0)
+            finish(1)
+            if dev["dtype"] == "float32":  # over all pieces of this call
+                self.last_tiles_visited = t.tensor(visited[0], dtype=t.int64)
         if shard and world > 1:  # the ranks' disjoint slices, in rank (= query) order
             out = _dist.allgather_rows(out)
         return out
