@@ -687,6 +687,127 @@ def run_ours(args):
         td.destroy_process_group()
 
 
+def run_mode(args):
+    """`--mode evaluate|knn|resample`: the other three sub-paths as N-GPU benchmarks of their
+    own (strong scaling of a fixed configuration, one JSON line, same timing rules as the
+    headline: warm-up, CUDA events, barrier + synchronize on both sides, max over ranks)."""
+    import contextlib
+
+    import torch
+    import torch.distributed as td
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from kdsource_b200 import _lib, dist, kde
+    from kdsource_b200.sampler import DeviceSampler, make_geom_struct
+    from kdsource_b200.treekde import TreeKDE
+
+    t = torch
+    L = _lib.load()
+    hbm, _ = measured_peaks()
+    flush = t.empty(256 << 20, dtype=t.uint8, device="cuda")
+
+    def timed_steps(fn):
+        for _ in range(args.warmup):
+            fn()
+        dist.barrier()
+        t.cuda.synchronize()
+        ms = []
+        for _ in range(args.steps):
+            flush.zero_()
+            ms += time_events(t, fn, 1)
+        dist.barrier()
+        t.cuda.synchronize()
+        tot = t.tensor([float(np.sum(ms))], device="cuda", dtype=t.float64)
+        if world > 1:
+            td.all_reduce(tot, op=td.ReduceOp.MAX)
+        return float(tot.item()) / args.steps
+
+    def timed_e2e(fn):
+        dist.barrier()
+        t.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        t.cuda.synchronize()
+        dt = t.tensor([time.perf_counter() - t0], device="cuda", dtype=t.float64)
+        if world > 1:
+            td.all_reduce(dt, op=td.ReduceOp.MAX)
+        return float(dt.item())
+
+    with contextlib.redirect_stdout(sys.stderr):
+        if args.mode == "evaluate":
+            N, M = 1_000_000, 8_000_000
+            _, w, _, _, data = synthetic_scaled(N)
+            q = synthetic_scaled(M, seed=54321, wseed=1)[4]
+            bw = kde.bw_silv(D_MLCV, np.sum(w) ** 2 / np.sum(w ** 2))
+            k = TreeKDE(bw=bw).fit(data, w)
+            dev = k._device_state()
+            lo, hi = dist.shard_range(M, rank, world)
+            d_q = _lib.to_dev(q[lo:hi])
+            ms = timed_steps(lambda: k.evaluate_device(d_q, hi - lo, dev))
+            units, unit, metric = float(N) * M, "pairs/s", METRIC
+            e2e_s = timed_e2e(lambda: k.evaluate(q))
+            h2d, d2h = (hi - lo) * 48, (hi - lo) * 8
+            work = "evaluate_1e6x8e6_silverman_auto"
+            roof = {"bound": "fp32", "achieved": units * 13 / world / (ms * 1e-3) / 1e9,
+                    "peak": None, "unit": "Glane-op/s", "frac": None,
+                    "per_unit": "13 FP32 lane-ops + 1 MUFU per pair (d=6), rank 0", "traffic": None}
+            launches = 40  # ordering + packing of the queries + the pair kernel + scatter
+        elif args.mode == "knn":
+            N = 10_000_000
+            _, w, _, _, data = synthetic_scaled(N, seed=99)
+            off = kde.array_split_bounds(N, 1000)
+            b_lo, b_hi = dist.shard_range(1000, rank, world)
+            d_rows = _lib.to_dev(data[off[b_lo]:off[b_hi]])
+            ms = timed_steps(lambda: kde.knn_batched(d_rows, 11, off[b_lo:b_hi + 1] - off[b_lo]))
+            units = float(np.sum(np.diff(off).astype(np.float64) ** 2))
+            unit, metric = "pairs/s", "knn_distance_pairs_per_s"
+            e2e_s = timed_e2e(lambda: kde.bw_knn(data, w, k=10, batch_size=10000))
+            h2d, d2h = int(off[b_hi] - off[b_lo]) * 48, N * 8
+            work = "knn_1e7_k10_batch1e4_f64"
+            roof = {"bound": "fp64", "achieved": units * 17 / world / (ms * 1e-3) / 1e9,
+                    "peak": None, "unit": "Gfp64 lane-op/s", "frac": None,
+                    "per_unit": "17 fp64 ops per pair (no FMA contraction), rank 0",
+                    "traffic": None}
+            launches = 2
+        else:
+            Ns, nout = 10_000_000, 400_000_000
+            ps, ws_, gs_, sc_, _ = synthetic_scaled(Ns, seed=7)
+            bws = np.random.default_rng(3).uniform(0.2, 0.5, Ns).astype(np.float32)
+            smp = DeviceSampler(ps, ws_, bws, make_geom_struct(gs_, sc_, "g"))
+            lo, hi = dist.shard_range(nout, rank, world)
+            out = _lib.empty((hi - lo) * 36, t.uint8)
+            ms = timed_steps(lambda: smp.sample_device(hi - lo, seed=1, first=lo, out=out))
+            del out
+            units, unit, metric = float(nout), "particles/s", "resampled_particles_per_s"
+            res = resample_e2e(ps, ws_, bws, gs_, sc_, False) if world == 1 else None
+            e2e_s = (res["gpu_gzip"]["s"] * nout / res["gpu_gzip"]["particles"]) if res else None
+            h2d, d2h = 76_000_000, int(22.5 * nout / world)
+            work = "resample_1e7src_4e8out_adaptive_bw"
+            roof = {"bound": "hbm", "achieved": 76.0 * nout / world / (ms * 1e-3) / 1e9,
+                    "peak": hbm, "unit": "GB/s",
+                    "frac": 76.0 * nout / world / (ms * 1e-3) / 1e9 / hbm,
+                    "per_unit": "76 B per particle (40 read + 36 written), rank 0", "traffic": None}
+            launches = 1
+    if rank == 0:
+        line = {"metric": metric, "value": units / (ms * 1e-3), "unit": unit, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64" if args.mode == "knn" else "f32", "data": "synthetic",
+                "config": {"workload": work, "mode": args.mode,
+                           "l2": "flushed between timed steps (256 MiB write, untimed)"},
+                "e2e": {"value": units / e2e_s if e2e_s else None, "unit": unit,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches * args.steps, "roofline": roof}
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -696,9 +817,13 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the MLCV list size (debug)")
     ap.add_argument("--quick", action="store_true", help="smaller secondary benchmarks")
     ap.add_argument("--no-sub", action="store_true", help="skip secondary benchmarks")
+    ap.add_argument("--mode", default="mlcv", choices=["mlcv", "evaluate", "knn", "resample"],
+                    help="mlcv (headline, BASELINE configs[1]) or one of the other sub-paths")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode != "mlcv":
+        run_mode(args)
     else:
         run_ours(args)
 

@@ -308,3 +308,59 @@ def pinned(tag, nelem, dtype):
         buf = t.empty(int(nelem), dtype=dtype, pin_memory=True)
         _pinned[(tag, dtype)] = buf
     return buf
+
+
+def stream_pieces(src, lo, hi, chunk, work, n_out=1, tag="pieces"):
+    """Run `work(d_piece (m,C) float64 CUDA tensor, m)` -> tuple of `n_out` (m,) float64
+    device tensors over rows [lo, hi) of the host array `src`, in pieces of `chunk` rows
+    that travel through two pinned staging buffers: the upload of piece i+1 and the
+    download of piece i-1 overlap the kernels of piece i.  `work` may return one extra
+    trailing object per piece, handed to the caller as ``extras``.  Returns
+    (list of n_out host arrays of length hi-lo, extras)."""
+    t = torch()
+    n, C = hi - lo, src.shape[1]
+    outs = [np.zeros(n, dtype=np.float64) for _ in range(n_out)]
+    extras = []
+    if n <= 0:
+        return outs, extras
+    if n <= chunk:
+        res = work(to_dev(src[lo:hi]), n)
+        for k in range(n_out):
+            outs[k][:] = res[k].cpu().numpy()
+        extras.extend(res[n_out:])
+        return outs, extras
+    main, side = t.cuda.current_stream(), t.cuda.Stream()
+    pin_in = [pinned((tag, "in", b), chunk * C, t.float64) for b in range(2)]
+    pin_out = [[pinned((tag, "out", b, k), chunk, t.float64) for k in range(n_out)]
+               for b in range(2)]
+    pending = [None, None]
+
+    def finish(b):
+        if pending[b] is not None:
+            done, s0, m0, keep = pending[b]
+            done.synchronize()
+            for k in range(n_out):
+                outs[k][s0 - lo:s0 - lo + m0] = pin_out[b][k][:m0].numpy()
+            extras.extend(keep[1][n_out:])
+            pending[b] = None
+
+    for i, s0 in enumerate(range(lo, hi, chunk)):
+        b, m = i % 2, min(chunk, hi - s0)
+        finish(b)  # piece i-2: its staging buffers are free again
+        stage = pin_in[b][:m * C].view(m, C)
+        stage.numpy()[...] = src[s0:s0 + m]
+        with t.cuda.stream(side):
+            d_piece = stage.to("cuda", non_blocking=True)
+            up = t.cuda.Event()
+            up.record(side)
+        d_piece.record_stream(main)
+        main.wait_event(up)
+        res = work(d_piece, m)
+        for k in range(n_out):
+            pin_out[b][k][:m].copy_(res[k], non_blocking=True)
+        done = t.cuda.Event()
+        done.record(main)
+        pending[b] = (done, s0, m, (d_piece, res))
+    finish(0)
+    finish(1)
+    return outs, extras

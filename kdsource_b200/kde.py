@@ -73,16 +73,50 @@ def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_
     t_kth = _lib.empty(n_loc, t.float64)
     t_dist = _lib.empty(n_loc * kk, t.float64) if want_dist else None
     t_idx = _lib.empty(n_loc * kk, t.int32) if want_idx else None
-    if n_loc > 0:
-        loc_off = batch_off[b_lo:b_hi + 1] - r_lo
-        d_data = data[r_lo:r_hi] if on_device else _lib.to_dev(data[r_lo:r_hi])
-        d_off = _lib.to_dev(loc_off, np.int64)
-        use_f64 = precision == "float64"
-        scratch = _lib.empty(n_loc * D, t.float64 if use_f64 else t.float32)
+    use_f64 = precision == "float64"
+
+    def run(d_rows, g_lo, g_hi, row0):
+        """batches [g_lo, g_hi) of this rank; their rows start at local row `row0`"""
+        offs = batch_off[g_lo:g_hi + 1] - batch_off[g_lo]
+        n = int(offs[-1])
+        d_off = _lib.to_dev(offs, np.int64)
+        scratch = _lib.empty(n * D, t.float64 if use_f64 else t.float32)
         _lib.check(L.kdsb200_knn(
-            _lib.ptr(d_data), n_loc, D, _lib.ptr(d_off), b_hi - b_lo,
-            int(np.max(np.diff(loc_off))), kk, int(use_f64), _lib.ptr(scratch),
-            _lib.ptr(t_kth), _lib.ptr(t_dist), _lib.ptr(t_idx), _lib.stream()))
+            _lib.ptr(d_rows), n, D, _lib.ptr(d_off), g_hi - g_lo, int(np.max(np.diff(offs))),
+            kk, int(use_f64), _lib.ptr(scratch), _lib.ptr(t_kth[row0:]),
+            _lib.ptr(t_dist[row0 * kk:]) if want_dist else None,
+            _lib.ptr(t_idx[row0 * kk:]) if want_idx else None, _lib.stream()))
+
+    if n_loc > 0 and (on_device or n_loc * D * 8 < (32 << 20)):
+        run(data[r_lo:r_hi] if on_device else _lib.to_dev(data[r_lo:r_hi]), b_lo, b_hi, 0)
+    elif n_loc > 0:
+        # host input: groups of whole batches (~16 MB) go through two pinned staging
+        # buffers, so the upload of the next group overlaps the kernel of this one
+        main, side = t.cuda.current_stream(), t.cuda.Stream()
+        groups, g0 = [], b_lo
+        while g0 < b_hi:
+            g1 = g0 + 1
+            while g1 < b_hi and (batch_off[g1 + 1] - batch_off[g0]) * D * 8 <= (16 << 20):
+                g1 += 1
+            groups.append((g0, g1))
+            g0 = g1
+        cap = max(int(batch_off[b] - batch_off[a]) for a, b in groups)
+        pins = [_lib.pinned(("knn_in", i), cap * D, t.float64) for i in range(2)]
+        busy = [None, None]
+        for i, (ga, gb) in enumerate(groups):
+            s0, s1 = int(batch_off[ga]), int(batch_off[gb])
+            if busy[i % 2] is not None:
+                busy[i % 2][0].synchronize()  # the copy out of this staging buffer is done
+            stage = pins[i % 2][:(s1 - s0) * D].view(s1 - s0, D)
+            stage.numpy()[...] = data[s0:s1]
+            with t.cuda.stream(side):
+                d_rows = stage.to("cuda", non_blocking=True)
+                up = t.cuda.Event()
+                up.record(side)
+            d_rows.record_stream(main)
+            main.wait_event(up)
+            run(d_rows, ga, gb, s0 - r_lo)
+            busy[i % 2] = (up, d_rows)
     # the ranks' disjoint slices are all-gathered on the device (batches are contiguous,
     # so rank order is row order), then downloaded once
     kth = _dist.allgather_concat_tensor(t_kth)

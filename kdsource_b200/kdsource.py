@@ -303,19 +303,17 @@ class KDSource:
         # query points are split contiguously over the ranks (sources replicated)
         rank, world = _dist.rank_world()
         lo, hi = _dist.shard_range(M, rank, world)
-        dens = np.zeros(hi - lo)
-        jacs = np.zeros(hi - lo)
-        for s in range(lo, hi, chunk):
-            n = min(chunk, hi - s)
-            d_parts = _lib.to_dev(parts[s:s + n])
+        def work(d_parts, n):
             d_vecs = _lib.empty(n * D, t.float64)
             d_jac = _lib.empty(n, t.float64)
             _lib.check(L.kdsb200_geom_transform(_lib.ptr(d_parts), n, ctypes.byref(gs), rot_p,
                                                 inv_p, _lib.ptr(d_vecs), _lib.ptr(d_jac),
                                                 _lib.stream()))
-            d_out = self.kde.evaluate_device(d_vecs, n, dev)
-            dens[s - lo:s - lo + n] = d_out.cpu().numpy()
-            jacs[s - lo:s - lo + n] = d_jac.cpu().numpy()
+            return self.kde.evaluate_device(d_vecs, n, dev), d_jac
+
+        n_loc = hi - lo
+        chunk = int(min(chunk, max(1 << 16, -(-n_loc // 4))))
+        (dens, jacs), _ = _lib.stream_pieces(parts, lo, hi, chunk, work, n_out=2, tag="kds_eval")
         if world > 1:  # the ranks' disjoint slices, gathered in rank (= query) order
             dens = _dist.allgather_rows(dens)
             jacs = _dist.allgather_rows(jacs)

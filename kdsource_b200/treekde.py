@@ -182,52 +182,20 @@ class TreeKDE:
         rank, world = _dist.rank_world()
         lo, hi = _dist.shard_range(len(pts), rank, world) if shard else (0, len(pts))
         n = hi - lo
-        out = np.zeros(n, dtype=np.float64)
         dev = self._device_state()
         if chunk is None:  # at least four pieces once the input is large enough to overlap
             chunk = int(min(1 << 22, max(1 << 16, -(-n // 4))))
-        if n <= chunk:
-            if n:
-                d_out = self.evaluate_device(_lib.to_dev(pts[lo:hi]), n, dev)
-                out[:] = d_out.cpu().numpy()
-        else:
+        culled = dev["dtype"] == "float32"
+
+        def work(d_pts, m):
+            d_out = self.evaluate_device(d_pts, m, dev)
+            return (d_out, self.last_tiles_visited) if culled else (d_out,)
+
+        (out,), visited = _lib.stream_pieces(pts, lo, hi, chunk, work, tag="eval")
+        if culled and n:  # tiles loaded over all pieces of this call
             t = _lib.torch()
-            main, side = t.cuda.current_stream(), t.cuda.Stream()
-            pin_in = [_lib.pinned(("eval_in", b), chunk * D, t.float64) for b in range(2)]
-            pin_out = [_lib.pinned(("eval_out", b), chunk, t.float64) for b in range(2)]
-            pending = [None, None]
-            visited = [0]
-
-            def finish(b):
-                if pending[b] is not None:
-                    done, s0, m0, keep = pending[b]
-                    done.synchronize()
-                    out[s0 - lo:s0 - lo + m0] = pin_out[b][:m0].numpy()
-                    if keep[2] is not None:
-                        visited[0] += int(keep[2].item())
-                    pending[b] = None
-
-            for i, s0 in enumerate(range(lo, hi, chunk)):
-                b, m = i % 2, min(chunk, hi - s0)
-                finish(b)  # piece i-2: its staging buffers are free again
-                stage = pin_in[b][:m * D].view(m, D)
-                stage.numpy()[...] = pts[s0:s0 + m]
-                with t.cuda.stream(side):
-                    d_pts = stage.to("cuda", non_blocking=True)
-                    up = t.cuda.Event()
-                    up.record(side)
-                d_pts.record_stream(main)
-                main.wait_event(up)
-                d_out = self.evaluate_device(d_pts, m, dev)
-                pin_out[b][:m].copy_(d_out, non_blocking=True)
-                done = t.cuda.Event()
-                done.record(main)
-                pending[b] = (done, s0, m, (d_pts, d_out, getattr(self, "last_tiles_visited", None)
-                                            if dev["dtype"] == "float32" else None))
-            finish(0)
-            finish(1)
-            if dev["dtype"] == "float32":  # over all pieces of this call
-                self.last_tiles_visited = t.tensor(visited[0], dtype=t.int64)
+            self.last_tiles_visited = t.tensor(sum(int(v.item()) for v in visited),
+                                               dtype=t.int64)
         if shard and world > 1:  # the ranks' disjoint slices, in rank (= query) order
             out = _dist.allgather_rows(out)
         return out
