@@ -259,6 +259,11 @@ int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void
  * seq_start >= 0 replaces the pick by the list walk i = (seq_start + first + n) % N
  * (the w_crit <= 0 mode of KDS_rand_sample2); pass -1 for weighted sampling.
  * d_ext_uniforms (count x slots doubles) replaces Philox (test mode).
+ * contract: how the Philox words turn into Gaussian deviates.  1 = the reference's own
+ * map (Marsaglia polar method, second value discarded, utils.c:9-29; ~12 words per
+ * particle, rejection loops); 2 = Box-Muller with both values of a pair used (8 words
+ * per particle of the usual geometries, no rejection).  External uniforms always follow
+ * the reference's map.  Same distribution, different particles for a given seed.
  * Outputs (each may be NULL): 36-byte MCPL-3 single-precision records, picked
  * source index, full-precision particle (8 doubles). */
 /* 1 if the geometry has a specialised fp32 kernel (Lethargy+SurfXY+Isotrop or
@@ -269,8 +274,8 @@ int kdsb200_resample_fp32_ok(const kdsb200_geom* h_geom);
 int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
                      const uint32_t* d_guide, int guide_bits, const float* d_bw, double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
                      uint64_t seed, uint64_t first, uint64_t count, int64_t seq_start,
-                     const double* d_ext_uniforms, int slots, int perturb, void* d_out36,
-                     int64_t* d_out_idx, double* d_out_parts, void* stream);
+                     const double* d_ext_uniforms, int slots, int perturb, int contract,
+                     void* d_out36, int64_t* d_out_idx, double* d_out_parts, void* stream);
 
 /* ---- MCPL-3 records -> particles on the device: the decode step of PList_get /
  * mcpl_read (clib/src/plist.c:69-89, python/kdsource/plist.py:349-395) ----------- */

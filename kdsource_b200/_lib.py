@@ -176,7 +176,7 @@ _SIGNATURES = {
     "kdsb200_resample": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_double,
                                  c_i64,
                                  ctypes.POINTER(Geom), c_i32, c_u64, c_u64, c_u64, c_i64, c_void_p,
-                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kdsb200_mcpl_unpack": (c_int, [c_void_p, c_u64, ctypes.POINTER(McplLayout), c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
     "kdsb200_gz_histogram": (c_int, [c_void_p, c_u64, ctypes.c_uint32, ctypes.c_uint32,

@@ -396,6 +396,7 @@ struct Impl {
   uint64_t have = 0, used = 0;           // particles in the host batch / handed out
   int batch_perturb = -1, batch_seq = -1;
   uint64_t seed = 0, counter = 0;        // Philox key and global output index
+  int contract = 2;                      // uniform-consumption contract (KDSB200_RESAMPLE_CONTRACT)
   uint64_t cursor = 0;                   // list cursor (sequential mode, w_mean)
   cudaStream_t stream = nullptr;
   // WeightFun bias (kdsource.c:294-325): the pick follows w_i * bias(part_i); the CDF of
@@ -490,6 +491,8 @@ Impl* ensure_impl(KDSource* kds) {
   I->h_idx.resize(BATCH);
   const char* e = getenv("KDSB200_SEED");
   I->seed = e ? strtoull(e, nullptr, 10) : 0;
+  const char* ec = getenv("KDSB200_RESAMPLE_CONTRACT");
+  I->contract = (ec && atoi(ec) == 1) ? 1 : 2;
   cu(cudaStreamSynchronize(I->stream));
   cudaFree(d_tmp);
   kds->impl = I;
@@ -589,7 +592,8 @@ void fill_batch(KDSource* kds, Impl* I, kds_rng_fct_t rng, void* st, int perturb
   cuda_or_die(kdsb200_resample(
       I->d_src, I->src_f32, biased ? I->d_cdf_bias : I->d_cdf, biased ? I->d_guide_bias : I->d_guide,
       I->guide_bits, I->d_bw, kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed, first,
-      BATCH, seq_start, nullptr, 0, perturb, nullptr, I->d_idx, I->d_parts, (void*)I->stream));
+      BATCH, seq_start, nullptr, 0, perturb, I->contract, nullptr, I->d_idx, I->d_parts,
+      (void*)I->stream));
   cu(cudaMemcpyAsync(I->h_parts.data(), I->d_parts, BATCH * 8 * sizeof(double),
                      cudaMemcpyDeviceToHost, I->stream));
   cu(cudaMemcpyAsync(I->h_idx.data(), I->d_idx, BATCH * sizeof(int64_t), cudaMemcpyDeviceToHost,
@@ -606,6 +610,7 @@ void fill_batch(KDSource* kds, Impl* I, kds_rng_fct_t rng, void* st, int perturb
 // uniforms from the caller's generator, for the single-particle host entry points
 struct HostStream {
   static constexpr bool EXT = true;
+  static constexpr bool V2 = false;
   kds_rng_fct_t rng;
   void* st;
   // __host__ __device__ only so that the shared templates compile without warnings;
@@ -1233,7 +1238,8 @@ void kdsource_resample_to_mcpl(double (*rng_stateless)(void), const char* kds_so
     const uint64_t n = nout - first < B ? nout - first : B;
     cuda_or_die(kdsb200_resample(I->d_src, I->src_f32, I->d_cdf, I->d_guide, I->guide_bits, I->d_bw,
                                  kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed, first,
-                                 n, -1, nullptr, 0, 1, d_rec, nullptr, nullptr, (void*)I->stream));
+                                 n, -1, nullptr, 0, 1, I->contract, d_rec, nullptr, nullptr,
+                                 (void*)I->stream));
     cuda_or_die(kdsb200_gz_writer_put_device(w, d_rec, n * 36));
   }
   cuda_or_die(kdsb200_gz_writer_close(w, nullptr));

@@ -127,8 +127,47 @@ __host__ __device__ __forceinline__ R uniform(S& s) {
 // kds_rand_norm: Marsaglia polar method, second value discarded (utils.c:9-29).
 // Accept/reject is decided exactly (integers for Philox, fp64 for external
 // uniforms) so fp32 and fp64 modes consume the same number of uniforms.
+//
+// Contract 2 (S::V2, counter-based streams only): Box-Muller, z0 = r cos(2 pi u2), z1 =
+// r sin(2 pi u2) with r = sqrt(-2 ln u1); z1 is kept and returned by the next call, so a
+// pair of deviates costs exactly two uniforms and nothing is rejected.  The usual
+// geometries then need 8 Philox words per particle (pick 2, two pairs 4, direction 2).
 template <typename R, typename S, bool FAST>
 __host__ __device__ R rand_norm(S& s) {
+  if constexpr (S::V2) {
+    if (s.have_spare) {
+      s.have_spare = false;
+      return s.spare;
+    }
+    const int k1 = s.kint(), k2 = s.kint();
+    if constexpr (sizeof(R) == 8) {
+      const double u1 = ((double)k1 + 0.5) * (1.0 / 8388608.0);
+      const double u2 = ((double)k2 + 0.5) * (1.0 / 8388608.0);
+      const double r = sqrt(-2.0 * log(u1));
+      const double a = (2.0 * KDS_PI) * u2;
+      s.spare = (R)(r * sin(a));
+      s.have_spare = true;
+      return (R)(r * cos(a));
+    } else {
+      const float u1 = ((float)k1 + 0.5f) * (1.0f / 8388608.0f);
+      const float u2 = ((float)k2 + 0.5f) * (1.0f / 8388608.0f);
+      // 1 - u1 = (2^24 - (2 k1 + 1)) 2^-24, exact: -ln u1 keeps its relative accuracy
+      // where u1 -> 1 and the deviate is small
+      const float m = (float)((1 << 24) - (2 * k1 + 1)) * (1.0f / 16777216.0f);
+      float L, sn, cs;
+      if (FAST) {
+        L = fast_neglog(u1, m);
+        fast_sincos(6.2831853072f * (u2 - (u2 >= 0.5f ? 1.0f : 0.0f)), &sn, &cs);
+      } else {
+        L = m < 0.5f ? -log1pf(-m) : -logf(u1);
+        sincos2pi(u2, &sn, &cs);
+      }
+      const float r = Mf<float, FAST>::sqrt_(2.0f * L);
+      s.spare = (R)(r * sn);
+      s.have_spare = true;
+      return (R)(r * cs);
+    }
+  }
   if (S::EXT) {
     double t, g1, g2;
     do {

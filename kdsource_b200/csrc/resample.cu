@@ -144,33 +144,44 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // words 0,1 form the 64-bit pick, later words give u = ((w >> 9) + 0.5) 2^-23;
 // external mode reads U[p*slots + (n % slots)] instead (slot 0 is the pick)
 constexpr int RS_THREADS = 256;
-constexpr int RS_RING = 16;  // Philox words kept per thread in shared memory (4 blocks)
+// Philox words generated up front per thread and kept in shared memory: 4 blocks under
+// contract 1 (the polar method with rejection needs ~12 words per particle of the usual
+// geometries), 2 blocks under contract 2 (Box-Muller: exactly 8)
+__host__ __device__ constexpr int rs_ring(bool v2) { return v2 ? 8 : 16; }
 
 // rare path of Stream::word(): a lane ran past the words generated up front.  Out
 // of line (by value, so the stream state stays in registers) to keep the
 // ~60-instruction generator from being replicated at every call site.
 __device__ __noinline__ void philox_refill(uint32_t p0, uint32_t p1, uint32_t blk, uint32_t k0,
-                                           uint32_t k1, uint32_t* ring) {
+                                           uint32_t k1, uint32_t* ring, int ring_words) {
   uint32_t o[4];
   philox4x32_10(p0, p1, blk, 0u, k0, k1, o);
-  const int s0 = (blk * 4) % RS_RING;
+  const int s0 = (blk * 4) % ring_words;
 #pragma unroll
   for (int k = 0; k < 4; k++) ring[(s0 + k) * RS_THREADS] = o[k];
 }
 
-template <bool EXT_>
+// V2_: uniform-consumption contract 2 (see rand_norm in perturb.cuh): Gaussian deviates by
+// Box-Muller, both values of a pair used (`spare`), no rejection.
+template <bool EXT_, bool V2_, typename R>
 struct Stream {
   static constexpr bool EXT = EXT_;
+  static constexpr bool V2 = V2_ && !EXT_;
+  static constexpr int RS_RING = rs_ring(V2);
   uint32_t k0, k1, p0, p1;
   uint32_t* ring;  // shared memory, word w of this thread at ring[(w % RS_RING) * RS_THREADS]
   const double* ext;
   int slots, next;
+  R spare;            // second value of the last Box-Muller pair (contract 2)
+  bool have_spare;
 
   // The first RS_RING words (Philox blocks 0..3) are generated up front by all
   // lanes in lock-step; only a lane that runs past them generates further blocks.
   __device__ __forceinline__ void init(uint64_t seed, uint64_t p, const double* e, int nslots,
                                        uint32_t* ring_base) {
     next = 0;
+    have_spare = false;
+    spare = (R)0;
     if (EXT) {
       ext = e + p * (uint64_t)nslots;
       slots = nslots;
@@ -193,7 +204,7 @@ struct Stream {
   // ~60-instruction generator is not replicated at every call site of word()
   __device__ __forceinline__ uint32_t word() {
     if (next >= RS_RING && (next & 3) == 0)
-      philox_refill(p0, p1, (uint32_t)next >> 2, k0, k1, ring);
+      philox_refill(p0, p1, (uint32_t)next >> 2, k0, k1, ring, RS_RING);
     const uint32_t w = ring[(next % RS_RING) * RS_THREADS];
     next++;
     return w;
@@ -217,7 +228,7 @@ struct Stream {
 
 enum { SIG_GENERIC = 0, SIG_FLAT = 1, SIG_ACTIV = 2 };
 
-template <typename R, bool EXT, int SIG, bool FAST>
+template <typename R, bool EXT, int SIG, bool FAST, bool V2>
 __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
     resample_kernel(const R* __restrict__ src8, const uint64_t* __restrict__ cdf,
                     const uint32_t* __restrict__ guide, int guide_bits,
@@ -227,13 +238,14 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
                     unsigned char* __restrict__ out36, int64_t* __restrict__ out_idx,
                     double* __restrict__ out_parts) {
   __shared__ __align__(16) uint32_t stage[RS_THREADS * 9];
-  __shared__ uint32_t ring[EXT ? 1 : RS_RING * RS_THREADS];
+  using St = Stream<EXT, V2, R>;
+  __shared__ uint32_t ring[EXT ? 1 : St::RS_RING * RS_THREADS];
   const uint64_t n0 = (uint64_t)blockIdx.x * RS_THREADS;
   const uint64_t n = n0 + threadIdx.x;
   const bool live = n < count;
   uint32_t rec[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (live) {
-  Stream<EXT> s;
+  St s;
   s.init(seed, EXT ? n : first + n, ext, slots, ring);
   const uint64_t total = __ldg(cdf + (N - 1));
   const uint64_t T = s.pick_target(total);
@@ -279,15 +291,15 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
       rotv<R>(p.dir, g.rot, 1);
     }
     if (SIG == SIG_FLAT) {          // Lethargy + SurfXY + Isotrop (GeomFlat)
-      metric_perturb<R, Stream<EXT>, M_LETHARGY, FAST>(s, g.ms[0], p, h, 'g');
-      metric_perturb<R, Stream<EXT>, M_SURFXY, FAST>(s, g.ms[1], p, h, 'g');
-      metric_perturb<R, Stream<EXT>, M_ISOTROP, FAST>(s, g.ms[2], p, h, 'g');
+      metric_perturb<R, St, M_LETHARGY, FAST>(s, g.ms[0], p, h, 'g');
+      metric_perturb<R, St, M_SURFXY, FAST>(s, g.ms[1], p, h, 'g');
+      metric_perturb<R, St, M_ISOTROP, FAST>(s, g.ms[2], p, h, 'g');
     } else if (SIG == SIG_ACTIV) {  // Energy + Vol + Isotrop (GeomActiv)
-      metric_perturb<R, Stream<EXT>, M_ENERGY, FAST>(s, g.ms[0], p, h, 'g');
-      metric_perturb<R, Stream<EXT>, M_VOL, FAST>(s, g.ms[1], p, h, 'g');
-      metric_perturb<R, Stream<EXT>, M_ISOTROP, FAST>(s, g.ms[2], p, h, 'g');
+      metric_perturb<R, St, M_ENERGY, FAST>(s, g.ms[0], p, h, 'g');
+      metric_perturb<R, St, M_VOL, FAST>(s, g.ms[1], p, h, 'g');
+      metric_perturb<R, St, M_ISOTROP, FAST>(s, g.ms[2], p, h, 'g');
     } else {
-      for (int k = 0; k < g.order; k++) metric_perturb<R, Stream<EXT>, -1, FAST>(s, g.ms[k], p, h, g.kernel);
+      for (int k = 0; k < g.order; k++) metric_perturb<R, St, -1, FAST>(s, g.ms[k], p, h, g.kernel);
     }
     if (SIG == SIG_GENERIC && g.has_rot) {
       rotv<R>(p.pos, g.rot, 0);
@@ -425,10 +437,15 @@ int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void
 int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
                      const uint32_t* d_guide, int guide_bits, const float* d_bw, double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
                      uint64_t seed, uint64_t first, uint64_t count, int64_t seq_start,
-                     const double* d_ext_uniforms, int slots, int perturb, void* d_out36,
-                     int64_t* d_out_idx, double* d_out_parts, void* stream) {
+                     const double* d_ext_uniforms, int slots, int perturb, int contract,
+                     void* d_out36, int64_t* d_out_idx, double* d_out_parts, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (count == 0) return 0;
+  if (contract != 1 && contract != 2) {
+    set_error("resample: uniform-consumption contract %d (1 or 2)", contract);
+    return 1;
+  }
+  const bool v2 = contract == 2;
   if (N <= 0) {
     set_error("resample: empty source list");
     return 1;
@@ -454,17 +471,20 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
   static int precise = -1;
   if (precise < 0) precise = getenv("KDSB200_RESAMPLE_PRECISE") ? 1 : 0;
   const bool fast = !precise && src_is_f32 && !d_ext_uniforms && sig != SIG_GENERIC;
-#define KDSB_LAUNCH1(R, EXT, SIG)                                                                \
-  if (fast && sizeof(R) == 4 && !EXT && SIG != SIG_GENERIC)                                      \
-    resample_kernel<float, false, SIG == SIG_GENERIC ? SIG_FLAT : SIG, true>                     \
-        <<<blocks, RS_THREADS, 0, st>>>(                                                         \
-            (const float*)d_src8, d_cdf, d_guide, guide_bits, d_bw, bw_scalar, N, *h_geom,       \
-            pdgcode, seed, first, count, seq_start, d_ext_uniforms, slots, perturb, o36,         \
-            d_out_idx, d_out_parts);                                                             \
-  else                                                                                           \
-    resample_kernel<R, EXT, SIG, false><<<blocks, RS_THREADS, 0, st>>>(                          \
-      (const R*)d_src8, d_cdf, d_guide, guide_bits, d_bw, bw_scalar, N, *h_geom, pdgcode, seed, \
-      first, count, seq_start, d_ext_uniforms, slots, perturb, o36, d_out_idx, d_out_parts)
+#define KDSB_ARGS(R)                                                                            \
+  (const R*)d_src8, d_cdf, d_guide, guide_bits, d_bw, bw_scalar, N, *h_geom, pdgcode, seed,     \
+      first, count, seq_start, d_ext_uniforms, slots, perturb, o36, d_out_idx, d_out_parts
+#define KDSB_LAUNCH2(R, EXT, SIG, V2)                                                           \
+  if (fast && sizeof(R) == 4 && !EXT && SIG != SIG_GENERIC)                                     \
+    resample_kernel<float, false, SIG == SIG_GENERIC ? SIG_FLAT : SIG, true, V2>                \
+        <<<blocks, RS_THREADS, 0, st>>>(KDSB_ARGS(float));                                      \
+  else                                                                                          \
+    resample_kernel<R, EXT, SIG, false, V2><<<blocks, RS_THREADS, 0, st>>>(KDSB_ARGS(R))
+#define KDSB_LAUNCH1(R, EXT, SIG)                   \
+  do {                                              \
+    if (v2 && !EXT) { KDSB_LAUNCH2(R, EXT, SIG, true); }  \
+    else { KDSB_LAUNCH2(R, EXT, SIG, false); }      \
+  } while (0)
 #define KDSB_LAUNCH(R, EXT)                                     \
   do {                                                          \
     if (sig == SIG_FLAT) KDSB_LAUNCH1(R, EXT, SIG_FLAT);        \
@@ -478,6 +498,8 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
     if (d_ext_uniforms) KDSB_LAUNCH(double, true);
     else KDSB_LAUNCH(double, false);
   }
+#undef KDSB_ARGS
+#undef KDSB_LAUNCH2
 #undef KDSB_LAUNCH1
 #undef KDSB_LAUNCH
   KDSB_CUDA(cudaGetLastError());

@@ -24,7 +24,7 @@ from .utils import pt2pdg
 from .writemcpl import _check_new_mcpl_filename, _normalised_mcpl_filename
 
 
-def open_source(kds_sourcefile, precision="float32"):
+def open_source(kds_sourcefile, precision="float32", contract=2):
     """Parse an XML source file and upload its particle list: returns a
     :class:`DeviceSampler` plus a dict of the parsed fields."""
     path = pathlib.Path(kds_sourcefile)
@@ -58,7 +58,8 @@ def open_source(kds_sourcefile, precision="float32"):
     else:
         bw = float(bwel.text)
     gs = make_geom_struct(geom, scaling, kernel)
-    sampler = DeviceSampler(parts, ws, bw, gs, pdgcode=pt2pdg(plist.pt), precision=precision)
+    sampler = DeviceSampler(parts, ws, bw, gs, pdgcode=pt2pdg(plist.pt), precision=precision,
+                            contract=contract)
     info = dict(J=float(root.find("J").text), kernel=kernel, plist=plist, geom=geom,
                 scaling=scaling, bw=bw, N=len(parts), cwd=cwd)
     return sampler, info
@@ -72,7 +73,8 @@ def _gzip_member(data, level):
 
 
 def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=False,
-                     batch=None, compresslevel=None, precision="float32", threads=None):
+                     batch=None, compresslevel=None, precision="float32", threads=None,
+                     contract=2, one_file=True):
     """Resample `nout` particles from an XML source file into a new MCPL file
     (always ``*.mcpl.gz``; refuses to overwrite unless `force`).
 
@@ -87,7 +89,13 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
     generated.  An int selects host zlib at that level instead (`threads` worker
     threads, default all cores; 0 = stored).  With torch.distributed initialised
     each rank produces a contiguous share of the particles and rank 0 assembles
-    the file; the particles do not depend on the number of ranks.
+    the file; the particles do not depend on the number of ranks.  ``one_file=False``
+    skips the assembly: rank r > 0 leaves its share as a complete MCPL file of its own,
+    ``<name>.rank<r>.mcpl.gz`` (all ranks write concurrently, nothing is copied).
+
+    contract: how Philox words become Gaussian deviates -- 2 (default) Box-Muller pairs,
+    1 the reference's polar method (``kdsb200_resample`` in include/kdsb200.h); the
+    distribution is the same, the particles of a given seed are not.
     """
     from . import dist as _dist
 
@@ -127,12 +135,18 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
 
     timing = os.environ.get("KDSB200_TIMING")
     t_start = time.perf_counter()
-    sampler, _ = open_source(ksrc.absolute(), precision=precision)
+    sampler, _ = open_source(ksrc.absolute(), precision=precision, contract=contract)
     if timing:
         print("[timing] open_source {:.3f} s".format(time.perf_counter() - t_start))
     lo, hi = _dist.shard_range(nout, rank, world)
     part_name = str(dst) + ".part{}".format(rank) if world > 1 else None
     header = mcpl.build_header(nout, "KDSource resample", singleprec=True) if rank == 0 else None
+    if world > 1 and not one_file:  # one complete file per rank
+        if rank > 0:
+            part_name = str(dst)[:-len(".mcpl.gz")] + ".rank{}.mcpl.gz".format(rank)
+        else:
+            part_name = str(dst)
+        header = mcpl.build_header(hi - lo, "KDSource resample", singleprec=True)
     if batch is None:
         # small batches keep the pinned staging buffers (and their allocation time) small;
         # long runs amortise larger ones better (measured: 1e8 particles 0.62 s with 2^20,
@@ -165,7 +179,9 @@ def resample_to_mcpl(kds_sourcefile, destination_mcpl, nout, rng=None, force=Fal
         _write_host_gzip(part_name or str(dst), header, batches(), compresslevel, threads)
     if timing:
         print("[timing] total {:.3f} s".format(time.perf_counter() - t_start))
-    if world > 1:
+    if world > 1 and not one_file:
+        _dist.barrier()
+    elif world > 1:
         _dist.barrier()
         if rank == 0:
             with open(dst, "wb") as out:

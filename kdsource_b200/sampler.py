@@ -70,7 +70,8 @@ class DeviceSampler:
     two geometries with specialised kernels (every coordinate within 1e-5 of its scale);
     any other geometry, and ``precision="float64"``, use the fp64 store (1e-12)."""
 
-    def __init__(self, parts, weights, bw, geom_struct, pdgcode=2112, precision="float32"):
+    def __init__(self, parts, weights, bw, geom_struct, pdgcode=2112, precision="float32",
+                 contract=2):
         L = _lib.load()
         t = _lib.torch()
         on_device = t.is_tensor(parts)  # (N,8) / (N,) float64 CUDA tensors (PList.get_device)
@@ -88,6 +89,11 @@ class DeviceSampler:
             raise ValueError("weights must be positive (filter w <= 0 first)")
         if precision not in ("float32", "float64"):
             raise ValueError("precision must be 'float32' or 'float64'")
+        if contract not in (1, 2):
+            raise ValueError("contract must be 1 (polar method, as the reference) or 2 "
+                             "(Box-Muller pairs)")
+        #: uniform-consumption contract of the Philox mode (kdsb200.h, kdsb200_resample)
+        self.contract = int(contract)
         self.N = len(parts)
         self.precision = precision
         self.geom = geom_struct
@@ -159,7 +165,8 @@ class DeviceSampler:
             self.guide_bits, _lib.ptr(self.bw), self.bw_scalar, self.N, ctypes.byref(self.geom), self.pdgcode,
             int(seed) & 0xFFFFFFFFFFFFFFFF, int(first), count, int(seq_start), _lib.ptr(d_ext),
             slots,
-            int(bool(perturb)), _lib.ptr(res.get("records")), _lib.ptr(res.get("idx")),
+            int(bool(perturb)), self.contract, _lib.ptr(res.get("records")),
+            _lib.ptr(res.get("idx")),
             _lib.ptr(res.get("parts")), _lib.stream()))
         return res
 

@@ -279,6 +279,11 @@ typedef struct {
   uint32_t ctr[4];
   uint32_t buf[4];
   int have; /* words left in buf */
+  /* uniform-consumption contract of the counter-based mode (include/kdsb200.h,
+   * kdsb200_resample): 1 = the reference's polar method, 2 = Box-Muller pairs */
+  int contract;
+  int have_spare;
+  double spare;
 } orc_stream;
 
 static void stream_init(orc_stream *s, uint64_t seed, uint64_t p,
@@ -340,6 +345,20 @@ static double stream_uniform(orc_stream *s) {
 /* kds_rand_norm (Marsaglia polar, second value discarded):
  * clib/src/utils.c:9-29 */
 static double rand_norm(orc_stream *s) {
+  if (!s->external && s->contract == 2) {
+    /* contract 2 (this library's own; no counterpart in the reference): Box-Muller, both
+     * values of a pair used, two uniforms per pair, no rejection */
+    if (s->have_spare) {
+      s->have_spare = 0;
+      return s->spare;
+    }
+    const double u1 = stream_uniform(s), u2 = stream_uniform(s);
+    const double r = sqrt(-2.0 * log(u1));
+    const double a = (2.0 * ORC_PI) * u2;
+    s->spare = r * sin(a);
+    s->have_spare = 1;
+    return r * cos(a);
+  }
   double t, g1, g2;
   do {
     g1 = 2.0 * stream_uniform(s) - 1.0;
@@ -907,7 +926,7 @@ static void pack36(const orc_part *p, double weight, int32_t pdg,
 void orc_resample(const double *src8, const uint64_t *cdf, const float *bw,
                   double bw_scalar, int64_t N, const orc_geom *g, int32_t pdg,
                   uint64_t seed, uint64_t first, uint64_t count,
-                  const double *ext_uniforms, int slots, int perturb,
+                  const double *ext_uniforms, int slots, int perturb, int contract,
                   unsigned char *out36, int64_t *out_idx, double *out_parts) {
   const uint64_t total = cdf[N - 1];
 #pragma omp parallel for schedule(static)
@@ -915,6 +934,7 @@ void orc_resample(const double *src8, const uint64_t *cdf, const float *bw,
     const uint64_t p = first + (uint64_t)n;
     orc_stream s;
     stream_init(&s, seed, ext_uniforms ? (uint64_t)n : p, ext_uniforms, slots);
+    s.contract = contract;
     const uint64_t T = stream_pick_target(&s, total);
     const int64_t i = upper_bound_u64(cdf, N, T);
     const double *r = src8 + i * 8;

@@ -463,7 +463,7 @@ def weights_cdf(w):
 
 
 def resample(src8, weights, bw, geom, nout, seed=0, first=0, pdg=2112,
-             ext_uniforms=None, perturb=True, want=("idx", "parts", "rec")):
+             ext_uniforms=None, perturb=True, want=("idx", "parts", "rec"), contract=2):
     """This project's resampling contract (prefix-sum + binary search pick,
     per-particle Philox stream, reference perturbation maps)."""
     src8 = np.ascontiguousarray(src8, dtype=np.float64)
@@ -487,7 +487,8 @@ def resample(src8, weights, bw, geom, nout, seed=0, first=0, pdg=2112,
         ctypes.c_double(bws), ctypes.c_int64(N), ctypes.byref(geom),
         ctypes.c_int32(pdg), ctypes.c_uint64(seed), ctypes.c_uint64(first),
         ctypes.c_uint64(nout), _p(ext_uniforms, c_double_p), ctypes.c_int(slots),
-        ctypes.c_int(int(perturb)), _p(rec, c_u8_p), _p(idx, c_i64_p),
+        ctypes.c_int(int(perturb)), ctypes.c_int(int(contract)), _p(rec, c_u8_p),
+        _p(idx, c_i64_p),
         _p(parts, c_double_p))
     return {"idx": idx, "parts": parts, "rec": rec, "cdf": cdf}
 

@@ -515,19 +515,20 @@ def _metrics(scaling):
             ("Isotrop", scaling[3:6], [0, 0, 1])]
 
 
-@pytest.mark.parametrize("precision", ["float32", "float64"])
-def test_resample_vs_oracle_philox(oracle, scaled, precision):
+@pytest.mark.parametrize("precision,contract", [("float32", 2), ("float64", 2), ("float32", 1),
+                                                ("float64", 1)])
+def test_resample_vs_oracle_philox(oracle, scaled, precision, contract):
     from kdsource_b200.sampler import DeviceSampler, make_geom_struct
 
     parts, w, scaling = scaled["parts"], scaled["w"], scaled["scaling"]
     bw = np.random.default_rng(7).uniform(0.2, 0.5, len(parts)).astype(np.float32)
     gs = make_geom_struct(scaled["geom"], scaling, "g")
-    smp = DeviceSampler(parts, w, bw, gs, precision=precision)
+    smp = DeviceSampler(parts, w, bw, gs, precision=precision, contract=contract)
     assert np.array_equal(smp.cdf_host(), oracle.weights_cdf(w))  # bit-exact CDF
     n = 50000 if precision == "float64" else 2_000_000
     out = smp.sample(n, seed=99, first=1234, want=("idx", "parts", "records"))
     ref = oracle.resample(parts, w, bw, oracle.make_geom(_metrics(scaling)), n, seed=99,
-                          first=1234)
+                          first=1234, contract=contract)
     assert np.array_equal(out["idx"], ref["idx"])  # bit-exact sampled indices
     scale = np.array([1.0, 30, 30, 1, 1, 1, 1, 1])
     tol = 1e-12 if precision == "float64" else 1e-5

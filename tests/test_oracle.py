@@ -330,3 +330,28 @@ def test_hilbert_keys_visit_neighbouring_cells(oracle):
         assert len(np.unique(k)) == len(k) and k.max() == len(k) - 1
         walk = cells[np.argsort(k)]
         assert np.all(np.abs(np.diff(walk, axis=0)).sum(axis=1) == 1)
+
+
+def test_resample_contracts_sample_the_same_distribution(oracle):
+    """Contract 1 (the reference's polar method) and contract 2 (Box-Muller pairs) consume
+    the Philox words differently but draw from the same density: same picks, KS-compatible
+    coordinates, standard-normal displacements."""
+    from scipy import stats
+
+    parts, w = oracle.synthetic_particles(3000, seed=41, wseed=42)
+    geom = oracle.make_geom([("Energy", [1.0], []), ("Vol", [1.0, 1.0, 1.0], [-1e9, 1e9] * 3),
+                             ("Isotrop", [0.3] * 3, [0, 0, 0])])
+    a = oracle.resample(parts, w, 0.5, geom, 60000, seed=7, contract=1)
+    b = oracle.resample(parts, w, 0.5, geom, 60000, seed=7, contract=2)
+    assert np.array_equal(a["idx"], b["idx"])  # the pick does not depend on the contract
+    assert not np.array_equal(a["parts"], b["parts"])
+    for r in (a, b):
+        for col in (1, 2, 3):  # displacement / bandwidth of the Vol coordinates ~ N(0, 1)
+            z = (r["parts"][:, col] - parts[r["idx"], col]) / 0.5
+            assert stats.kstest(z, "norm").pvalue > 1e-3
+        # the two values of a Box-Muller pair are uncorrelated
+        zx = (r["parts"][:, 1] - parts[r["idx"], 1]) / 0.5
+        zy = (r["parts"][:, 2] - parts[r["idx"], 2]) / 0.5
+        assert abs(np.corrcoef(zx, zy)[0, 1]) < 0.02
+    for col in (0, 1, 4, 6):
+        assert stats.ks_2samp(a["parts"][:, col], b["parts"][:, col]).pvalue > 1e-3
