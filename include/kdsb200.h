@@ -250,12 +250,24 @@ int kdsb200_weights_cdf(const double* d_w, uint64_t N, double sum_w, uint64_t* d
 /* Optional search accelerator: d_guide[b] (2^bits + 1 uint32) = first i with
  * cdf[i] > (b << (62-bits)); narrows the binary search window, same result. */
 int kdsb200_cdf_guide(const uint64_t* d_cdf, uint64_t N, int bits, uint32_t* d_guide, void* stream);
+/* Pick table (guide_kind 1 of kdsb200_resample): the window table with the answer inlined.
+ * 2^bits entries of 128 bytes (one HBM line, fetched by eight lanes as one request) --
+ * {cdf[i0], cdf[i0+1], i0, i1 - i0, the fp32 particles i0 and i0+1 and their bandwidths}
+ * -- so a pick whose target lies below the bucket's second CDF boundary costs one line
+ * in all; other targets continue in cdf[i0+2 .. i1].  Same index as the plain search.
+ * bits ~ log2(2 N) keeps the search to ~1 pick in 30.  d_src8_f32 is the fp32 store of
+ * kdsb200_convert_particles; d_bw may be NULL (bw_scalar is stored). */
+uint64_t kdsb200_pick_table_bytes(int bits);
+int kdsb200_pick_table(const uint64_t* d_cdf, uint64_t N, int bits, const float* d_src8_f32,
+                       const float* d_bw, double bw_scalar, void* d_table, void* stream);
 /* (N,8) fp64 particles [ekin,x,y,z,ux,uy,uz,t] -> fp32 or fp64 device store */
 int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void* d_out,
                               void* stream);
 /* Output particle n (global index first+n): Philox4x32-10 counter (index, block),
  * key = seed; pick = first i with cdf[i] > mulhi64(R64, total); then Geom_perturb.
- * d_guide/guide_bits: table from kdsb200_cdf_guide, or NULL for the plain search.
+ * d_guide/guide_bits/guide_kind: table from kdsb200_cdf_guide (kind 0) or
+ * kdsb200_pick_table (kind 1: fp32 store, Philox mode, specialised geometries), or NULL
+ * for the plain search.
  * seq_start >= 0 replaces the pick by the list walk i = (seq_start + first + n) % N
  * (the w_crit <= 0 mode of KDS_rand_sample2); pass -1 for weighted sampling.
  * d_ext_uniforms (count x slots doubles) replaces Philox (test mode).
@@ -272,7 +284,8 @@ int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void
  * maps that fp32-rounded sources cannot hold to 1e-5 and should use the fp64 store. */
 int kdsb200_resample_fp32_ok(const kdsb200_geom* h_geom);
 int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
-                     const uint32_t* d_guide, int guide_bits, const float* d_bw, double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
+                     const void* d_guide, int guide_bits, int guide_kind, const float* d_bw,
+                     double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
                      uint64_t seed, uint64_t first, uint64_t count, int64_t seq_start,
                      const double* d_ext_uniforms, int slots, int perturb, int contract,
                      void* d_out36, int64_t* d_out_idx, double* d_out_parts, void* stream);

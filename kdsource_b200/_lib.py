@@ -173,8 +173,11 @@ _SIGNATURES = {
                                        c_double_p, c_void_p, c_void_p, c_void_p]),
     "kdsb200_cdf_guide": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_void_p]),
     "kdsb200_resample_fp32_ok": (c_int, [ctypes.POINTER(Geom)]),
-    "kdsb200_resample": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_double,
-                                 c_i64,
+    "kdsb200_pick_table_bytes": (c_u64, [c_int]),
+    "kdsb200_pick_table": (c_int, [c_void_p, c_u64, c_int, c_void_p, c_void_p, c_double, c_void_p,
+                                   c_void_p]),
+    "kdsb200_resample": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                 c_double, c_i64,
                                  ctypes.POINTER(Geom), c_i32, c_u64, c_u64, c_u64, c_i64, c_void_p,
                                  c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kdsb200_mcpl_unpack": (c_int, [c_void_p, c_u64, ctypes.POINTER(McplLayout), c_void_p,
@@ -198,7 +201,8 @@ EXPORTS = sorted(_SIGNATURES)
 
 
 def libpath():
-    return os.path.join(_HERE, LIBNAME)
+    # KDSB200_LIB: another build of the same library (kernel-tuning runs, tools/)
+    return os.environ.get("KDSB200_LIB") or os.path.join(_HERE, LIBNAME)
 
 
 def load():

@@ -591,7 +591,7 @@ void fill_batch(KDSource* kds, Impl* I, kds_rng_fct_t rng, void* st, int perturb
   const bool biased = bias && !seq;
   cuda_or_die(kdsb200_resample(
       I->d_src, I->src_f32, biased ? I->d_cdf_bias : I->d_cdf, biased ? I->d_guide_bias : I->d_guide,
-      I->guide_bits, I->d_bw, kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed, first,
+      I->guide_bits, 0, I->d_bw, kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed, first,
       BATCH, seq_start, nullptr, 0, perturb, I->contract, nullptr, I->d_idx, I->d_parts,
       (void*)I->stream));
   cu(cudaMemcpyAsync(I->h_parts.data(), I->d_parts, BATCH * 8 * sizeof(double),
@@ -1236,7 +1236,7 @@ void kdsource_resample_to_mcpl(double (*rng_stateless)(void), const char* kds_so
   cu(cudaMalloc(&d_rec, B * 36));
   for (uint64_t first = 0; first < nout; first += B) {
     const uint64_t n = nout - first < B ? nout - first : B;
-    cuda_or_die(kdsb200_resample(I->d_src, I->src_f32, I->d_cdf, I->d_guide, I->guide_bits, I->d_bw,
+    cuda_or_die(kdsb200_resample(I->d_src, I->src_f32, I->d_cdf, I->d_guide, I->guide_bits, 0, I->d_bw,
                                  kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed, first,
                                  n, -1, nullptr, 0, 1, I->contract, d_rec, nullptr, nullptr,
                                  (void*)I->stream));

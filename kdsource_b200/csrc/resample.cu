@@ -125,6 +125,67 @@ __global__ void cdf_guide_kernel(const uint64_t* __restrict__ cdf, uint64_t N, i
   guide[b] = (uint32_t)(lo < N ? lo : N - 1);
 }
 
+// pick table: the guide table with the answer inlined.  A random access costs a whole
+// 128-byte line of HBM on this GPU whatever its width (tools/probes/gather_probe.cu:
+// 3.9 DRAM sectors per access for 16..128-byte reads, 4.6e10 lines/s), so the resampler's
+// chain guide -> CDF probes -> particle -> bandwidth (5 lines per pick on a list that
+// has outgrown the L2) is replaced by ONE line per bucket b of the pick range,
+// K = 2^bits >= 2 N buckets:
+//   words 0-1  thr0 = cdf[i0]       (~0 if no CDF boundary falls in the bucket)
+//   words 2-3  thr1 = cdf[i0 + 1]   (~0 if fewer than two do)
+//   word  4    i0   = first i with cdf[i] > (b << shift)
+//   word  5    span = i1 - i0, i1 = first i with cdf[i] > ((b+1) << shift), <= N-1
+//   words 6-7  bandwidths of particles i0 and i0 + 1
+//   words 8-15 fp32 particle i0, words 16-23 fp32 particle i0 + 1, words 24-31 unused
+// A pick target T of bucket b is particle i0 if T < thr0, i0 + 1 if T < thr1 -- both in
+// hand -- and otherwise (a few percent of the picks) found in cdf[i0+2 .. i0+span]: the
+// same index as the plain search in every case.
+constexpr int PICK_WORDS = 32;
+
+__device__ __forceinline__ uint64_t cdf_upper_bound(const uint64_t* __restrict__ cdf, uint64_t N,
+                                                    uint64_t T) {
+  uint64_t lo = 0, hi = N;
+  while (lo < hi) {
+    const uint64_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(cdf + mid) > T)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+    pick_table_kernel(const uint64_t* __restrict__ cdf, uint64_t N, int bits,
+                      const float* __restrict__ src8, const float* __restrict__ bw,
+                      float bw_scalar, uint32_t* __restrict__ table) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t K = 1ull << bits;
+  if (b >= K) return;
+  const int shift = 62 - bits;
+  uint64_t i0 = cdf_upper_bound(cdf, N, b << shift);
+  if (i0 > N - 1) i0 = N - 1;
+  uint64_t i1 = N - 1;
+  if (b + 1 < K) {
+    i1 = cdf_upper_bound(cdf, N, (b + 1) << shift);
+    if (i1 > N - 1) i1 = N - 1;
+  }
+  const uint64_t ia = i0 + 1 < N ? i0 + 1 : N - 1;
+  const uint64_t thr0 = i1 > i0 ? __ldg(cdf + i0) : ~0ull;
+  const uint64_t thr1 = i1 > i0 + 1 ? __ldg(cdf + i0 + 1) : ~0ull;
+  uint4* e = reinterpret_cast<uint4*>(table + b * PICK_WORDS);
+  e[0] = make_uint4((uint32_t)thr0, (uint32_t)(thr0 >> 32), (uint32_t)thr1, (uint32_t)(thr1 >> 32));
+  e[1] = make_uint4((uint32_t)i0, (uint32_t)(i1 - i0),
+                    __float_as_uint(bw ? __ldg(bw + i0) : bw_scalar),
+                    __float_as_uint(bw ? __ldg(bw + ia) : bw_scalar));
+  const uint4* s0 = reinterpret_cast<const uint4*>(src8 + i0 * 8);
+  const uint4* s1 = reinterpret_cast<const uint4*>(src8 + ia * 8);
+  e[2] = __ldg(s0); e[3] = __ldg(s0 + 1);
+  e[4] = __ldg(s1); e[5] = __ldg(s1 + 1);
+  e[6] = make_uint4(0u, 0u, 0u, 0u);
+  e[7] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ---- Philox4x32-10 --------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
@@ -226,10 +287,37 @@ struct Stream {
   __device__ __forceinline__ int kint() { return (int)(word() >> 9); }
 };
 
+// MCPL-3 single-precision record (36 bytes) with the adaptive projection packing of the
+// direction (libmcpl mcpl_unitvect_pack_adaptproj); weight = 1/bias = 1, kdsource.c:325
+template <typename R, bool FAST>
+__device__ __forceinline__ void pack_mcpl_record(const Part<R>& p, int32_t pdg, uint32_t (&rec)[9]) {
+  const R ax = fabs(p.dir[0]), ay = fabs(p.dir[1]), az = fabs(p.dir[2]);
+  R p0, p1, sg;
+  if (az < fmax(ax, ay)) {
+    const R invz = p.dir[2] != 0 ? Mf<R, FAST>::div_((R)1, p.dir[2]) : (R)INFINITY;
+    if (ax >= ay) { p0 = invz; p1 = p.dir[1]; sg = p.dir[0]; }
+    else { p0 = p.dir[0]; p1 = invz; sg = p.dir[1]; }
+  } else {
+    p0 = p.dir[0]; p1 = p.dir[1]; sg = p.dir[2];
+  }
+  rec[0] = __float_as_uint((float)p.pos[0]);
+  rec[1] = __float_as_uint((float)p.pos[1]);
+  rec[2] = __float_as_uint((float)p.pos[2]);
+  rec[3] = __float_as_uint((float)p0);
+  rec[4] = __float_as_uint((float)p1);
+  rec[5] = __float_as_uint((float)copysign(fabs(p.ekin), sg));
+  rec[6] = __float_as_uint((float)p.time);
+  rec[7] = __float_as_uint(1.0f);
+  rec[8] = (uint32_t)pdg;
+}
+
 enum { SIG_GENERIC = 0, SIG_FLAT = 1, SIG_ACTIV = 2 };
 
-template <typename R, bool EXT, int SIG, bool FAST, bool V2>
-__global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
+#ifndef KDSB_RS_MINB
+#define KDSB_RS_MINB 5
+#endif
+template <typename R, bool EXT, int SIG, bool FAST, bool V2, bool TAB = false>
+__global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? (FAST ? KDSB_RS_MINB : 4) : 2)
     resample_kernel(const R* __restrict__ src8, const uint64_t* __restrict__ cdf,
                     const uint32_t* __restrict__ guide, int guide_bits,
                     const float* __restrict__ bw, double bw_scalar, int64_t N, kdsb200_geom g,
@@ -237,21 +325,73 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
                     const double* __restrict__ ext, int slots, int perturb,
                     unsigned char* __restrict__ out36, int64_t* __restrict__ out_idx,
                     double* __restrict__ out_parts) {
-  __shared__ __align__(16) uint32_t stage[RS_THREADS * 9];
+  // TAB: one 128-byte table entry per lane, fetched by the warp (below); the records are
+  // staged over the entries once these are consumed
+  __shared__ __align__(128) uint32_t stage[RS_THREADS * (TAB ? PICK_WORDS : 9)];
   using St = Stream<EXT, V2, R>;
   __shared__ uint32_t ring[EXT ? 1 : St::RS_RING * RS_THREADS];
   const uint64_t n0 = (uint64_t)blockIdx.x * RS_THREADS;
   const uint64_t n = n0 + threadIdx.x;
   const bool live = n < count;
   uint32_t rec[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (live) {
+  // TAB: a lane past the end repeats the last particle (the table fetch is a warp
+  // operation) and writes nothing
+  const uint64_t ne = TAB && !live ? count - 1 : n;
+  if (live || TAB) {
   St s;
-  s.init(seed, EXT ? n : first + n, ext, slots, ring);
+  s.init(seed, EXT ? ne : first + ne, ext, slots, ring);
   const uint64_t total = __ldg(cdf + (N - 1));
   const uint64_t T = s.pick_target(total);
   // upper_bound: first i with cdf[i] > T (window from the guide table if present)
   int64_t lo = 0, hi = N - 1;
-  if (guide) {
+  bool inl = false;  // TAB: the picked particle came with the table entry
+  float4 ea, eb;
+  float eh;
+  if (TAB) {
+    // guide = pick table (pick_table_kernel).  On a list that has outgrown the L2 every
+    // request that leaves the L1 for a random line costs an address translation, and the
+    // translations bound the rate (tools/probes/gather_probe.cu: 4.6e10 sector requests/s
+    // however few bytes each carries).  So eight lanes fetch one entry as ONE 128-byte
+    // request (asynchronous copy into the warp's shared-memory area), four entries per
+    // instruction, and each lane then reads its header and the chosen particle there.
+    const uint64_t K = 1ull << guide_bits;
+    uint64_t b = T >> (62 - guide_bits);
+    if (b > K - 1) b = K - 1;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wbase = smem_u32(stage) + (threadIdx.x & ~31u) * (PICK_WORDS * 4);
+#pragma unroll
+    for (uint32_t m = 0; m < 8; m++) {
+      const uint32_t owner = (lane >> 3) + 4u * m, c = lane & 7u;
+      const uint64_t bo = __shfl_sync(0xffffffffu, b, owner);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                       wbase + owner * 128u + ((c ^ (owner & 7u)) << 4)),
+                   "l"(reinterpret_cast<const uint4*>(guide) + bo * (PICK_WORDS / 4) + c));
+    }
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const unsigned char* ent = reinterpret_cast<const unsigned char*>(stage) +
+                               (size_t)threadIdx.x * 128u;
+    const uint32_t sw = lane & 7u;
+    const uint4 h0 = *reinterpret_cast<const uint4*>(ent + ((0u ^ sw) << 4));
+    const uint4 h1 = *reinterpret_cast<const uint4*>(ent + ((1u ^ sw) << 4));
+    const uint64_t thr0 = (uint64_t)h0.x | ((uint64_t)h0.y << 32);
+    const uint64_t thr1 = (uint64_t)h0.z | ((uint64_t)h0.w << 32);
+    lo = h1.x;
+    hi = lo + h1.y;
+    if (T < thr1 && seq_start < 0) {
+      const uint32_t sel = T < thr0 ? 0u : 1u;
+      lo += sel;
+      hi = lo;
+      inl = true;
+      ea = *reinterpret_cast<const float4*>(ent + (((2u + 2u * sel) ^ sw) << 4));
+      eb = *reinterpret_cast<const float4*>(ent + (((3u + 2u * sel) ^ sw) << 4));
+      eh = __uint_as_float(sel ? h1.w : h1.z);
+    } else if (T >= thr1) {
+      lo += 2;
+    }
+    __syncwarp();  // entries consumed: the area is reused for the records
+  } else if (guide) {
     const uint64_t K = 1ull << guide_bits;
     uint64_t b = T >> (62 - guide_bits);
     if (b > K - 1) b = K - 1;
@@ -267,10 +407,13 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
   }
   // seq_start >= 0: walk the list in order instead (w_crit <= 0 mode of
   // KDS_rand_sample2, kdsource.c:286-292); the pick number is still consumed
-  const int64_t i = seq_start >= 0 ? (int64_t)(((uint64_t)seq_start + first + n) % (uint64_t)N) : lo;
+  const int64_t i = seq_start >= 0 ? (int64_t)(((uint64_t)seq_start + first + ne) % (uint64_t)N) : lo;
 
   Part<R> p;
-  {
+  if (TAB && inl) {
+    p.ekin = ea.x; p.pos[0] = ea.y; p.pos[1] = ea.z; p.pos[2] = ea.w;
+    p.dir[0] = eb.x; p.dir[1] = eb.y; p.dir[2] = eb.z; p.time = eb.w;
+  } else {
     const R* r = src8 + i * 8;
     if (sizeof(R) == 4) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(r));
@@ -282,7 +425,7 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
       p.dir[0] = r[4]; p.dir[1] = r[5]; p.dir[2] = r[6]; p.time = r[7];
     }
   }
-  const R h = bw ? (R)__ldg(bw + i) : (R)bw_scalar;
+  const R h = (TAB && inl) ? (R)eh : bw ? (R)__ldg(bw + i) : (R)bw_scalar;
   if (perturb) {  // Geom_perturb geom.c:139-158 (specialised signatures have no trasl/rot)
     if (SIG == SIG_GENERIC && g.has_trasl)
       for (int k = 0; k < 3; k++) p.pos[k] -= (R)g.trasl[k];
@@ -308,52 +451,40 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(R) == 4 ? 4 : 2)
     if (SIG == SIG_GENERIC && g.has_trasl)
       for (int k = 0; k < 3; k++) p.pos[k] += (R)g.trasl[k];
   }
-  if (out_idx) out_idx[n] = i;
-  if (out_parts) {
+  if (out_idx && live) out_idx[n] = i;
+  if (out_parts && live) {
     double* o = out_parts + n * 8;
     o[0] = p.ekin; o[1] = p.pos[0]; o[2] = p.pos[1]; o[3] = p.pos[2];
     o[4] = p.dir[0]; o[5] = p.dir[1]; o[6] = p.dir[2]; o[7] = p.time;
   }
-  if (out36) {
-    // MCPL adaptive projection packing (libmcpl mcpl_unitvect_pack_adaptproj)
-    const R ax = fabs(p.dir[0]), ay = fabs(p.dir[1]), az = fabs(p.dir[2]);
-    R p0, p1, sg;
-    if (az < fmax(ax, ay)) {
-      const R invz = p.dir[2] != 0 ? Mf<R, FAST>::div_((R)1, p.dir[2]) : (R)INFINITY;
-      if (ax >= ay) { p0 = invz; p1 = p.dir[1]; sg = p.dir[0]; }
-      else { p0 = p.dir[0]; p1 = invz; sg = p.dir[1]; }
-    } else {
-      p0 = p.dir[0]; p1 = p.dir[1]; sg = p.dir[2];
-    }
-    rec[0] = __float_as_uint((float)p.pos[0]);
-    rec[1] = __float_as_uint((float)p.pos[1]);
-    rec[2] = __float_as_uint((float)p.pos[2]);
-    rec[3] = __float_as_uint((float)p0);
-    rec[4] = __float_as_uint((float)p1);
-    rec[5] = __float_as_uint((float)copysign(fabs(p.ekin), sg));
-    rec[6] = __float_as_uint((float)p.time);
-    rec[7] = __float_as_uint(1.0f);  // weight = 1/bias, kdsource.c:325
-    rec[8] = (uint32_t)pdg;
+  if (out36 && live) {
+    pack_mcpl_record<R, FAST>(p, pdg, rec);
   }
   }  // live
   if (out36) {
-    // stage the CTA's records in shared memory (stride 9 words: conflict-free) and
-    // write them out as one contiguous, 16-byte-vectorised block
+    // stage each warp's 32 records in shared memory (stride 9 words: conflict-free) and
+    // write them out as one contiguous block of 1152 bytes, 16 bytes per lane and store;
+    // warps never wait for each other
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t* wst = stage + (threadIdx.x & ~31u) * (TAB ? PICK_WORDS : 9);
 #pragma unroll
-    for (int k = 0; k < 9; k++) stage[threadIdx.x * 9 + k] = rec[k];
-    __syncthreads();
-    const uint64_t nblk = count - n0 < RS_THREADS ? count - n0 : RS_THREADS;
-    const uint32_t words = (uint32_t)nblk * 9;
-    unsigned char* base = out36 + n0 * 36;  // n0*36 is a multiple of 16
-    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
-      uint4* dst = reinterpret_cast<uint4*>(base);
-      const uint4* srcv = reinterpret_cast<const uint4*>(stage);
-      for (uint32_t v = threadIdx.x; v < words / 4; v += RS_THREADS) dst[v] = srcv[v];
-      for (uint32_t wd = (words / 4) * 4 + threadIdx.x; wd < words; wd += RS_THREADS)
-        reinterpret_cast<uint32_t*>(base)[wd] = stage[wd];
-    } else {
-      for (uint32_t wd = threadIdx.x; wd < words; wd += RS_THREADS)
-        reinterpret_cast<uint32_t*>(base)[wd] = stage[wd];
+    for (int k = 0; k < 9; k++) wst[lane * 9 + k] = rec[k];
+    __syncwarp();
+    const uint64_t nw0 = n0 + (threadIdx.x & ~31u);
+    if (nw0 < count) {
+      const uint64_t nblk = count - nw0 < 32 ? count - nw0 : 32;
+      const uint32_t words = (uint32_t)nblk * 9;
+      unsigned char* base = out36 + nw0 * 36;  // nw0*36 is a multiple of 16
+      if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(base);
+        const uint4* srcv = reinterpret_cast<const uint4*>(wst);
+        for (uint32_t v = lane; v < words / 4; v += 32) dst[v] = srcv[v];
+        for (uint32_t wd = (words / 4) * 4 + lane; wd < words; wd += 32)
+          reinterpret_cast<uint32_t*>(base)[wd] = wst[wd];
+      } else {
+        for (uint32_t wd = lane; wd < words; wd += 32)
+          reinterpret_cast<uint32_t*>(base)[wd] = wst[wd];
+      }
     }
   }
 }
@@ -420,6 +551,25 @@ int kdsb200_cdf_guide(const uint64_t* d_cdf, uint64_t N, int bits, uint32_t* d_g
   return 0;
 }
 
+uint64_t kdsb200_pick_table_bytes(int bits) { return (1ull << bits) * PICK_WORDS * 4; }
+
+int kdsb200_pick_table(const uint64_t* d_cdf, uint64_t N, int bits, const float* d_src8_f32,
+                       const float* d_bw, double bw_scalar, void* d_table, void* stream) {
+  if (bits < 1 || bits > 30) {
+    set_error("pick_table: bits=%d out of range 1..30", bits);
+    return 1;
+  }
+  if (N == 0 || N >= (1ull << 32)) {
+    set_error("pick_table: N must be in 1..2^32-1");
+    return 1;
+  }
+  const uint64_t K = 1ull << bits;
+  pick_table_kernel<<<(unsigned)((K + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_cdf, N, bits, d_src8_f32, d_bw, (float)bw_scalar, (uint32_t*)d_table);
+  KDSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void* d_out,
                               void* stream) {
   const uint64_t n8 = N * 8;
@@ -435,7 +585,8 @@ int kdsb200_convert_particles(const double* d_src8, uint64_t N, int to_f32, void
 }
 
 int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
-                     const uint32_t* d_guide, int guide_bits, const float* d_bw, double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
+                     const void* d_guide_v, int guide_bits, int guide_kind, const float* d_bw,
+                     double bw_scalar, int64_t N, const kdsb200_geom* h_geom, int32_t pdgcode,
                      uint64_t seed, uint64_t first, uint64_t count, int64_t seq_start,
                      const double* d_ext_uniforms, int slots, int perturb, int contract,
                      void* d_out36, int64_t* d_out_idx, double* d_out_parts, void* stream) {
@@ -454,8 +605,13 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
     set_error("resample: geometry order %d out of range", h_geom->order);
     return 1;
   }
-  if (d_guide && (guide_bits < 1 || guide_bits > 26)) {
-    set_error("resample: guide_bits=%d out of range 1..26", guide_bits);
+  const uint32_t* d_guide = (const uint32_t*)d_guide_v;
+  if (guide_kind != 0 && guide_kind != 1) {
+    set_error("resample: guide_kind %d (0 = window table, 1 = pick table)", guide_kind);
+    return 1;
+  }
+  if (d_guide && (guide_bits < 1 || guide_bits > (guide_kind ? 30 : 26))) {
+    set_error("resample: guide_bits=%d out of range", guide_bits);
     return 1;
   }
   if (d_ext_uniforms && slots < 1) {
@@ -471,11 +627,18 @@ int kdsb200_resample(const void* d_src8, int src_is_f32, const uint64_t* d_cdf,
   static int precise = -1;
   if (precise < 0) precise = getenv("KDSB200_RESAMPLE_PRECISE") ? 1 : 0;
   const bool fast = !precise && src_is_f32 && !d_ext_uniforms && sig != SIG_GENERIC;
+  // the pick table serves the fp32 Philox kernels of the specialised geometries; any other
+  // variant ignores it and searches the whole CDF (same indices)
+  const bool tab = d_guide && guide_kind == 1 && fast;
+  if (guide_kind == 1 && !tab) d_guide = nullptr;
 #define KDSB_ARGS(R)                                                                            \
   (const R*)d_src8, d_cdf, d_guide, guide_bits, d_bw, bw_scalar, N, *h_geom, pdgcode, seed,     \
       first, count, seq_start, d_ext_uniforms, slots, perturb, o36, d_out_idx, d_out_parts
 #define KDSB_LAUNCH2(R, EXT, SIG, V2)                                                           \
-  if (fast && sizeof(R) == 4 && !EXT && SIG != SIG_GENERIC)                                     \
+  if (fast && tab && sizeof(R) == 4 && !EXT && SIG != SIG_GENERIC)                              \
+    resample_kernel<float, false, SIG == SIG_GENERIC ? SIG_FLAT : SIG, true, V2, true>          \
+        <<<blocks, RS_THREADS, 0, st>>>(KDSB_ARGS(float));                                      \
+  else if (fast && sizeof(R) == 4 && !EXT && SIG != SIG_GENERIC)                                \
     resample_kernel<float, false, SIG == SIG_GENERIC ? SIG_FLAT : SIG, true, V2>                \
         <<<blocks, RS_THREADS, 0, st>>>(KDSB_ARGS(float));                                      \
   else                                                                                          \

@@ -71,7 +71,7 @@ class DeviceSampler:
     any other geometry, and ``precision="float64"``, use the fp64 store (1e-12)."""
 
     def __init__(self, parts, weights, bw, geom_struct, pdgcode=2112, precision="float32",
-                 contract=2):
+                 contract=2, pick_table="auto", pick_bits=None):
         L = _lib.load()
         t = _lib.torch()
         on_device = t.is_tensor(parts)  # (N,8) / (N,) float64 CUDA tensors (PList.get_device)
@@ -115,16 +115,6 @@ class DeviceSampler:
         self.cdf = _lib.empty(self.N, t.int64)  # uint64 payload
         _lib.check(L.kdsb200_weights_cdf(_lib.ptr(d_w), self.N, self.sum_w, _lib.ptr(scratch),
                                          _lib.ptr(self.cdf), _lib.stream()))
-        # search window table: one CDF entry per bucket while the table stays L2-resident
-        # (measured +7 % at N=1e5), ~8 per bucket for large lists where the table itself
-        # would become a second random HBM access; at most 2^24 buckets
-        per_bucket = 1.0 if self.N <= (1 << 21) else 8.0
-        self.guide_bits = int(min(24, max(4, np.ceil(np.log2(max(self.N, 16) / per_bucket)))))
-        self.guide = None
-        if self.N < (1 << 32):
-            self.guide = _lib.empty((1 << self.guide_bits) + 1, t.int32)
-            _lib.check(L.kdsb200_cdf_guide(_lib.ptr(self.cdf), self.N, self.guide_bits,
-                                           _lib.ptr(self.guide), _lib.stream()))
         if np.ndim(bw) == 0:
             self.bw = None
             self.bw_scalar = float(bw)
@@ -134,6 +124,39 @@ class DeviceSampler:
                 raise ValueError("bandwidth array shorter than the particle list")
             self.bw = _lib.to_dev(bw[:self.N], np.float32)
             self.bw_scalar = 0.0
+        self.guide, self.guide_bits, self.guide_kind = None, 0, 0
+        self.pick, self.pick_bits = None, 0
+        if self.N < (1 << 32):
+            # search window table: one CDF entry per bucket while the table stays L2-resident
+            # (measured +7 % at N=1e5), ~8 per bucket for large lists where the table itself
+            # would become a second random HBM access; at most 2^24 buckets
+            per_bucket = 1.0 if self.N <= (1 << 21) else 8.0
+            self.guide_bits = int(min(24, max(4, np.ceil(np.log2(max(self.N, 16) / per_bucket)))))
+            self.guide = _lib.empty((1 << self.guide_bits) + 1, t.int32)
+            _lib.check(L.kdsb200_cdf_guide(_lib.ptr(self.cdf), self.N, self.guide_bits,
+                                           _lib.ptr(self.guide), _lib.stream()))
+            # pick table for the fp32 Philox kernels (kdsb200_pick_table): one 128-byte line
+            # per output particle in place of the dependent guide -> CDF probes -> particle ->
+            # bandwidth chain (five lines): 2x the rate on lists that have outgrown the L2,
+            # +4..7 % on short ones.  The table takes 256-512 B per source.
+            if pick_table == "auto":
+                pick_table = self.f32
+            if pick_table:
+                if not self.f32:
+                    raise ValueError("the pick table needs the fp32 store of a specialised geometry")
+                # >= 2 buckets per source: ~1 pick in 30 then goes beyond the two inlined
+                # particles; one bucket fewer per halving of what the free memory allows
+                bits = int(np.ceil(np.log2(2.0 * max(self.N, 8))))
+                free = t.cuda.mem_get_info()[0]
+                while bits > 4 and int(L.kdsb200_pick_table_bytes(bits)) > free // 3:
+                    bits -= 1
+                if pick_bits is not None:
+                    bits = int(pick_bits)
+                self.pick_bits = bits
+                self.pick = _lib.empty(int(L.kdsb200_pick_table_bytes(bits)), t.uint8)
+                _lib.check(L.kdsb200_pick_table(_lib.ptr(self.cdf), self.N, bits, _lib.ptr(self.src),
+                                                _lib.ptr(self.bw), self.bw_scalar,
+                                                _lib.ptr(self.pick), _lib.stream()))
         t.cuda.current_stream().synchronize()
 
     def sample_device(self, count, seed=0, first=0, ext_uniforms=None, perturb=True,
@@ -160,9 +183,13 @@ class DeviceSampler:
             res["idx"] = _lib.empty(count, t.int64)
         if want_parts:
             res["parts"] = _lib.empty(count * 8, t.float64)
+        # the pick table serves the Philox mode; external uniforms go through the window table
+        use_pick = self.pick is not None and d_ext is None
         _lib.check(L.kdsb200_resample(
-            _lib.ptr(self.src), int(self.f32), _lib.ptr(self.cdf), _lib.ptr(self.guide),
-            self.guide_bits, _lib.ptr(self.bw), self.bw_scalar, self.N, ctypes.byref(self.geom), self.pdgcode,
+            _lib.ptr(self.src), int(self.f32), _lib.ptr(self.cdf),
+            _lib.ptr(self.pick if use_pick else self.guide),
+            self.pick_bits if use_pick else self.guide_bits, int(use_pick), _lib.ptr(self.bw),
+            self.bw_scalar, self.N, ctypes.byref(self.geom), self.pdgcode,
             int(seed) & 0xFFFFFFFFFFFFFFFF, int(first), count, int(seq_start), _lib.ptr(d_ext),
             slots,
             int(bool(perturb)), self.contract, _lib.ptr(res.get("records")),

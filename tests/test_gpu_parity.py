@@ -545,6 +545,42 @@ def test_resample_vs_oracle_philox(oracle, scaled, precision, contract):
         assert np.max(np.abs(out["parts"][:, 0] / ref["parts"][:, 0] - 1)) < tol
 
 
+@pytest.mark.parametrize("weights", ["normal", "skewed"])
+@pytest.mark.parametrize("scalar_bw", [False, True])
+def test_resample_pick_table_equals_plain_search(oracle, scaled, weights, scalar_bw):
+    """The pick table (kdsb200_pick_table, the default of the fp32 Philox kernels) returns
+    the same indices, particles and records as the search over the CDF, and the
+    oracle's indices -- with weights spanning nine decades (buckets holding hundreds of CDF
+    boundaries next to particles covering thousands of buckets), at every table resolution,
+    for a batch count that is not a multiple of the CTA size, and for the record-less
+    outputs."""
+    from kdsource_b200.sampler import DeviceSampler, make_geom_struct
+
+    parts, scaling = scaled["parts"], scaled["scaling"]
+    rng = np.random.default_rng(17)
+    w = scaled["w"] if weights == "normal" else 10.0 ** rng.uniform(-6, 3, len(parts))
+    bw = 0.3 if scalar_bw else rng.uniform(0.2, 0.5, len(parts)).astype(np.float32)
+    gs = make_geom_struct(scaled["geom"], scaling, "g")
+    n = 300_001
+    plain = DeviceSampler(parts, w, bw, gs, pick_table=False)
+    ref = plain.sample(n, seed=5, first=77, want=("idx", "parts", "records"))
+    oref = oracle.resample(parts, w, bw, oracle.make_geom(_metrics(scaling)), 20000, seed=5,
+                           first=77)
+    assert np.array_equal(ref["idx"][:20000], oref["idx"])
+    for bits in (None, 4, 11):
+        smp = DeviceSampler(parts, w, bw, gs, pick_table=True, pick_bits=bits)
+        assert smp.pick is not None
+        out = smp.sample(n, seed=5, first=77, want=("idx", "parts", "records"))
+        assert np.array_equal(out["idx"], ref["idx"]), bits
+        assert np.array_equal(out["parts"], ref["parts"]), bits
+        assert np.array_equal(out["records"], ref["records"]), bits
+        only_idx = smp.sample(1000, seed=5, first=77, want=("idx",))["idx"]
+        assert np.array_equal(only_idx, ref["idx"][:1000])
+        # the list walk of the w_crit <= 0 mode ignores the table
+        a = smp.sample_device(500, seed=1, seq_start=3, want_idx=True)["idx"].cpu().numpy()
+        assert np.array_equal(a, (3 + np.arange(500)) % len(parts))
+
+
 def test_resample_external_uniforms_and_split(oracle, scaled):
     from kdsource_b200.sampler import DeviceSampler, make_geom_struct
 
