@@ -402,13 +402,23 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
         rs()
     ms = float(np.median(time_events(t, rs, 3)))
     bytes_alg = 76.0 * nout
+    traffic, traffic_pp = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic_resample.json")
+    if os.path.exists(tp) and not quick:
+        with open(tp) as fh:
+            tj = json.load(fh)
+        traffic, traffic_pp = tj.get("dram_bytes_per_launch"), tj.get("dram_bytes_per_particle")
     sub["resample"] = {
         "workload": "N={:g} sources, adaptive bw, {:g} particles -> MCPL-3 records".format(Ns, nout),
         "particles_per_s": nout / (ms * 1e-3), "ms": ms,
         "roofline": {"bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": bytes_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "per_unit": "76 B per particle (40 read + 36 written)", "traffic": None}}
+                     "per_unit": "76 B per particle (40 read + 36 written)", "traffic": traffic,
+                     "traffic_note": "ncu: {} B of DRAM traffic per particle -- a random pick "
+                                     "costs a whole 128-byte HBM line; at the measured rate that "
+                                     "is {:.0f} GB/s".format(traffic_pp, (traffic_pp or 0) * nout /
+                                                            (ms * 1e-3) / 1e9)}}
     # device gzip of those records (gz_size + gz_scan + gz_encode kernels): algorithmic bytes
     # = 2 reads of the records + the compressed stream written
     nb = nout * 36

@@ -18,7 +18,7 @@ bw = kde.bw_silv(6, np.sum(w) ** 2 / np.sum(w ** 2))
 if which in ("all", "eval"):
     M = 200_000
     q = synthetic_scaled(M, seed=54321, wseed=1)[4]
-    k = TreeKDE(bw=bw, dtype="float32").fit(data, w)
+    k = TreeKDE(bw=bw).fit(data, w)  # the default path: ordered tiles, tile-local coordinates
     dev = k._device_state()
     d_q = _lib.to_dev(q)
     for _ in range(3):
@@ -45,10 +45,12 @@ if which in ("all", "knn"):
         for _ in range(2):
             kde.knn_batched(data, 11, off, precision=prec)
 if which in ("all", "resample"):
-    bws = np.random.default_rng(3).uniform(0.2, 0.5, N).astype(np.float32)
-    smp = DeviceSampler(parts, w, bws, make_geom_struct(g, scaling, "g"))
+    Nr = 10_000_000  # a list that has outgrown the L2 (configuration 4)
+    pr, wr, gr, sr, _ = synthetic_scaled(Nr, seed=7)
+    bws = np.random.default_rng(3).uniform(0.2, 0.5, Nr).astype(np.float32)
+    smp = DeviceSampler(pr, wr, bws, make_geom_struct(gr, sr, "g"))
     for _ in range(3):
-        smp.sample_device(10_000_000, seed=1)
+        smp.sample_device(100_000_000, seed=1)
     t.cuda.synchronize()
 if which in ("all", "gzip"):
     import ctypes
