@@ -337,7 +337,9 @@ def config5(args):
             nsub = min(N, 5_000_000)  # the oracle on a bounded prefix of the sources
             ksub = TreeKDE(bw=k.bw[:nsub], cutoff="adaptive").fit(k.data[:nsub], k.weights[:nsub])
             gsub = ksub.evaluate(d_q.cpu().numpy(), shard=False)
-            c = dev["cull_rel"]
+            # the radius factor follows the smallest bandwidth of the fitted set: take the
+            # subset model's own
+            c = ksub._device_state()["cull_rel"]
             ref = O.kde_sum(k.data[:nsub], k.weights[:nsub], k.bw[:nsub], d_q.cpu().numpy(),
                             cutoff_rel=c, chunk=4)
             ok = ref > 1e-9 * ref.max()
