@@ -666,7 +666,12 @@ int kdsb200_mlcv_nsplit(uint64_t N, uint64_t M) {
   const uint64_t ntl = n_tiles_for(N);
   if (!qt || !ntl) return 1;
   const uint64_t slots = (uint64_t)sm_count() * 2;
-  uint64_t lo = (3 * slots + qt - 1) / qt;  // at least ~3 waves when the problem allows
+  // CTAs differ in length (tiles inside a row block's own fold are skipped, and a rank's
+  // share of the rows sits in one or two folds), so the last wave is only as ragged as one
+  // CTA is long: aim for >= 32 CTAs per slot while a CTA keeps >= 16 tiles (a tile is
+  // ~0.2 ms of work against microseconds of pipeline fill)
+  uint64_t lo = (32 * slots + qt - 1) / qt;
+  if (lo > ntl / 16) lo = ntl / 16;
   if (lo < 1) lo = 1;
   if (lo > ntl) lo = ntl;
   uint64_t hi = lo + 7;
