@@ -315,7 +315,10 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
             sub["evaluate"][name] = eval_leg(kk, d_q, M, 13, reps=3)
             del kk
         del data2, w2
-    if cpu:
+    cpu_jobs = []  # the CPU references run after every GPU measurement (their OpenMP / joblib
+    #                workers would otherwise compete with the host side of the e2e runs)
+
+    def cpu_evaluate():
         from oracle import kds_oracle as O
 
         mq = 20_000  # bounded sample: 1e5 sources x 2e4 queries = 2e9 pairs
@@ -325,15 +328,29 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
         sub["evaluate"]["cpu_baseline"] = {
             "value": N * mq / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
             "sample": "dense fp64 sum, 1e5 sources x {} queries ({:.1f} s)".format(mq, dt)}
+
+    cpu_jobs.append(cpu_evaluate)
+
+    def host_api_seconds(fn, reps=3):
+        """Median wall time of fn() through the host API after one warm-up call (the first
+        call allocates the pinned staging buffers)."""
+        fn()
+        ts = []
+        for _ in range(reps):
+            t.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            t.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+
     # e2e through KDSource-level API: host (M,6) fp64 in, densities out
-    Me = min(M, 400_000)
-    t.cuda.synchronize()
-    t0 = time.perf_counter()
-    k.evaluate(q[:Me])
-    dt = time.perf_counter() - t0
+    Me = M
+    dt = host_api_seconds(lambda: k.evaluate(q[:Me]))
     sub["evaluate"]["e2e"] = {"value": N * Me / dt, "unit": "pairs/s",
                               "h2d_bytes_per_step": Me * 6 * 8, "d2h_bytes_per_step": Me * 8,
-                              "api": "TreeKDE.evaluate(host array), M={}".format(Me)}
+                              "api": "TreeKDE.evaluate(host array), M={}; median of 3 calls "
+                                     "after one warm-up".format(Me)}
     # --- kNN: k=10, batches of 1e4 (reference default), fp64 exact mode
     Nk = 200_000 if quick else 1_000_000
     _, wk, _, _, dk = synthetic_scaled(Nk, seed=99)
@@ -368,12 +385,12 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
     # contraction (bit-exact with numpy/sklearn): 3d-1 DP ops per pair
     sub["knn"] = {"workload": "N={:g}, k=10, batch_size=1e4, d=6".format(Nk), **res,
                   "per_unit": "17 fp64 ops (f64 mode) / 12 fp32 lane-ops (f32 mode) per pair"}
-    t0 = time.perf_counter()
-    kth, _, _ = kde.knn_batched(dk, 11, off)
-    dt = time.perf_counter() - t0
+    dt = host_api_seconds(lambda: kde.knn_batched(dk, 11, off))
     sub["knn"]["e2e"] = {"value": pk / dt, "unit": "pairs/s", "h2d_bytes_per_step": Nk * 6 * 8,
-                         "d2h_bytes_per_step": Nk * 8, "api": "kde.knn_batched(host array)"}
-    if cpu:
+                         "d2h_bytes_per_step": Nk * 8,
+                         "api": "kde.knn_batched(host array); median of 3 calls after one warm-up"}
+
+    def cpu_knn():
         from sklearn.neighbors import NearestNeighbors
 
         nb_s = 20  # bounded sample: the first 20 batches, sklearn as kde.py:93-97 calls it
@@ -387,6 +404,8 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
             "unit": "pairs/s (dense-equivalent)", "cores": cores, "kind": "reference",
             "sample": "sklearn NearestNeighbors(k+1, n_jobs=-1) kd-tree on the first {} batches "
                       "({:.1f} s)".format(nb_s, dt)}
+
+    cpu_jobs.append(cpu_knn)
     # --- resample: N=1e7 adaptive-bw sources (config 4), 1e8 particles per step
     Ns = 1_000_000 if quick else 10_000_000
     nout = 10_000_000 if quick else 100_000_000
@@ -453,9 +472,11 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
                                  "includes the memset of the output buffer".format(zbytes / nout),
                      "traffic": None}}
     del gz_out, gz_scr
-    if cpu:
-        sub["resample"]["cpu_baseline"] = cpu_resample_baseline(ps, ws_, bws, sc_, cores)
     sub["resample"]["e2e"] = resample_e2e(ps, ws_, bws, gs_, sc_, quick)
+    if cpu:
+        for job in cpu_jobs:
+            job()
+        sub["resample"]["cpu_baseline"] = cpu_resample_baseline(ps, ws_, bws, sc_, cores)
     return sub
 
 
@@ -533,6 +554,8 @@ def resample_e2e(ps, ws_, bws, gs_, sc_, quick):
         src.fit(scaling=sc_)
         xml = src.save("src.xml", adjust_N=False)
         res = {}
+        # warm-up: pinned output buffers, the writer's worker threads, file-system state
+        kds.resample_to_mcpl(xml, "out.mcpl.gz", 1 << 22, rng=1, force=True)
         for name, level, n in (("gpu_gzip", None, nout), ("host_zlib_level1", 1, nout_host)):
             t0 = time.perf_counter()
             kds.resample_to_mcpl(xml, "out.mcpl.gz", n, rng=1, force=True, compresslevel=level)
