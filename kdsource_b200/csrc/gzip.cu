@@ -18,6 +18,10 @@
 //                             gzip FNAME field carries 0-3 filler characters)
 //   pass 3 (gz_encode_kernel) header, bit-packed codes, end-of-block, CRC-32, ISIZE
 //
+// Every member announces its own compressed size in a gzip FEXTRA subfield ("KD", 4 bytes,
+// as BGZF does with "BC"), so a reader can hop from header to header and inflate the
+// members in parallel (kdsource_b200/mcpl.py); plain gzip readers skip the field.
+//
 // One Huffman table serves every member: it is built on the host
 // (kdsb200_gz_build_table) from a byte histogram of the first records
 // (kdsb200_gz_histogram), with every symbol kept encodable.
@@ -287,13 +291,14 @@ __global__ void __launch_bounds__(GZ_THREADS)
   }
 }
 
-// member m: 10-byte gzip header + k filler characters + NUL + deflate + CRC32 + ISIZE,
-// k chosen so the member is a multiple of 4 bytes
+// member m: 10-byte gzip header + FEXTRA (XLEN = 8: "KD", 4, member size) + k filler
+// characters + NUL + deflate + CRC32 + ISIZE, k chosen so the member is a multiple of 4 bytes
+constexpr uint32_t GZ_HEAD = 21u;  // bytes before the filler: 10 + 2 (XLEN) + 8 (subfield) + NUL
 __device__ __forceinline__ uint32_t gz_member_size(uint32_t bits, uint32_t hdr_bits,
                                                    uint32_t eob_len, uint32_t& k) {
   const uint32_t D = (hdr_bits + bits + eob_len + 7) / 8;
-  k = (4u - ((19u + D) & 3u)) & 3u;
-  return 19u + k + D;
+  k = (4u - ((GZ_HEAD + 8u + D) & 3u)) & 3u;
+  return GZ_HEAD + 8u + k + D;
 }
 
 __global__ void __launch_bounds__(GZ_THREADS)
@@ -369,14 +374,19 @@ __global__ void __launch_bounds__(GZ_THREADS)
   __syncthreads();
   uint32_t woff = 0;
   for (int w = 0; w < warp; w++) woff += s_scan[w];
-  const uint32_t B0 = 8u * (11u + k);  // first deflate bit
+  const uint32_t B0 = 8u * (GZ_HEAD + k);  // first deflate bit
   const uint32_t start = B0 + hb + woff + inc - mybits;
 
   // gzip header (thread 0), block header bits (threads 0..), trailer (thread 1)
   if (t == 0) {
-    atomicOr(words + 0, 0x08088b1fu);  // ID1 ID2 CM=8 FLG=FNAME; MTIME = 0
+    atomicOr(words + 0, 0x0c088b1fu);  // ID1 ID2 CM=8 FLG=FEXTRA|FNAME; MTIME = 0
     gz_or_byte(words, 9, 0xffu);       // XFL = 0, OS = 255 (unknown)
-    for (uint32_t c = 0; c < k; c++) gz_or_byte(words, 10 + c, 0x6bu);  // filler 'k', then NUL
+    gz_or_byte(words, 10, 8u);         // XLEN = 8
+    gz_or_byte(words, 12, 0x4bu);      // subfield "KD",
+    gz_or_byte(words, 13, 0x44u);
+    gz_or_byte(words, 14, 4u);         // 4 bytes: the size of this member
+    atomicOr(words + 4, msize);
+    for (uint32_t c = 0; c < k; c++) gz_or_byte(words, 20 + c, 0x6bu);  // filler 'k', then NUL
   }
   {
     const uint32_t s = B0 & 31u, nw = (s + hb + 31u) / 32u, hw = (hb + 31u) / 32u;

@@ -224,6 +224,15 @@ int kdsb200_gz_writer_put_host(kdsb200_gz_writer* w, const void* h_data, uint64_
     set_error("gz_writer_put_host: deflateInit2 failed");
     return 1;
   }
+  // the same "KD" FEXTRA subfield as the device members carry: the member's own size,
+  // patched in once it is known (the header is not covered by the CRC)
+  unsigned char extra[8] = {'K', 'D', 4, 0, 0, 0, 0, 0};
+  gz_header gh;
+  memset(&gh, 0, sizeof(gh));
+  gh.os = 255;
+  gh.extra = extra;
+  gh.extra_len = 8;
+  deflateSetHeader(&zs, &gh);
   std::vector<unsigned char> buf(deflateBound(&zs, (uLong)nbytes) + 64);
   zs.next_in = (Bytef*)h_data;
   zs.avail_in = (uInt)nbytes;
@@ -236,6 +245,11 @@ int kdsb200_gz_writer_put_host(kdsb200_gz_writer* w, const void* h_data, uint64_
     set_error("gz_writer_put_host: deflate failed (%d)", rc);
     return 1;
   }
+  if (n >= (1ull << 32) || n < 20 || buf[12] != 'K' || buf[13] != 'D') {
+    set_error("gz_writer_put_host: unexpected member layout");
+    return 1;
+  }
+  for (int c = 0; c < 4; c++) buf[16 + c] = (unsigned char)(n >> (8 * c));
   // ordered with the device batches by the running file offset
   if (!pwrite_all(w->fd, buf.data(), n, w->file_off)) {
     set_error("gz_writer_put_host: write failed");

@@ -178,12 +178,153 @@ class ParticleBlock:
         return len(self.x)
 
 
+# ---- indexed gzip members ----------------------------------------------------
+# The files this package writes (device gzip, csrc/gzip.cu; host writer below) are
+# sequences of gzip members that each announce their own compressed size in an FEXTRA
+# subfield "KD" (4 bytes, little endian) -- the idea of BGZF's "BC" field with room for
+# members beyond 64 KB.  A reader hops from header to header, takes every member's raw
+# size from its ISIZE trailer, and inflates the members in parallel (zlib releases the
+# GIL).  Any other gzip file goes through Python's gzip module as before.
+_KD_HEAD = struct.Struct("<4sIBBH2sHI")  # magic+CM+FLG, MTIME, XFL, OS, XLEN, "KD", LEN, size
+
+
+def _kd_member_size(buf, off):
+    """Compressed size of the member starting at buf[off] if it carries the "KD" subfield
+    as its first (and only) extra field, else None."""
+    if off + 20 > len(buf):
+        return None
+    magic, _, _, _, xlen, si, ln, size = _KD_HEAD.unpack_from(buf, off)
+    if magic[:3] != b"\x1f\x8b\x08" or not (magic[3] & 4) or xlen != 8 or si != b"KD" or ln != 4:
+        return None
+    if size < 28 or off + size > len(buf):
+        return None
+    return size
+
+
+def gz_member_index(buf):
+    """(offsets, sizes, raw sizes) of the members of an indexed gzip file held in `buf`
+    (bytes-like / mmap), or None if any member lacks the "KD" size field."""
+    offs, sizes, raws = [], [], []
+    off, n = 0, len(buf)
+    while off < n:
+        size = _kd_member_size(buf, off)
+        if size is None:
+            return None
+        offs.append(off)
+        sizes.append(size)
+        raws.append(struct.unpack_from("<I", buf, off + size - 4)[0])
+        off += size
+    if not offs:
+        return None
+    return (np.asarray(offs, dtype=np.int64), np.asarray(sizes, dtype=np.int64),
+            np.asarray(raws, dtype=np.int64))
+
+
+def _inflate_workers():
+    return max(1, min(32, (os.cpu_count() or 1)))
+
+
+class _IndexedGzReader:
+    """File-like reader (read / readinto / close) over an indexed multi-member gzip file:
+    members are inflated a window at a time on a thread pool."""
+
+    WINDOW_BYTES = 64 << 20  # raw bytes inflated per window
+
+    def __init__(self, filename, mm, index):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self._fh = open(filename, "rb")
+        self._mm = mm
+        self._offs, self._sizes, self._raws = index
+        self._next = 0          # next member to inflate
+        self._buf = b""         # inflated, not yet consumed
+        self._bpos = 0
+        self._pool = ThreadPoolExecutor(max_workers=_inflate_workers())
+
+    def _inflate(self, k):
+        import zlib
+
+        o, n = int(self._offs[k]), int(self._sizes[k])
+        out = zlib.decompress(self._mm[o:o + n], 31)
+        if len(out) != int(self._raws[k]) and int(self._raws[k]) < (1 << 32) - 1:
+            raise IOError("gzip member {}: size mismatch".format(k))
+        return out
+
+    def _fill(self, want):
+        """Make at least `want` unconsumed bytes available (or everything that is left)."""
+        have = len(self._buf) - self._bpos
+        if have >= want or self._next >= len(self._offs):
+            return
+        k0 = self._next
+        k1, raw = k0, 0
+        need = max(want - have, self.WINDOW_BYTES)
+        while k1 < len(self._offs) and raw < need:
+            raw += int(self._raws[k1])
+            k1 += 1
+        parts = list(self._pool.map(self._inflate, range(k0, k1), chunksize=max(1, (k1 - k0) // 64)))
+        self._next = k1
+        self._buf = self._buf[self._bpos:] + b"".join(parts)
+        self._bpos = 0
+
+    def read(self, n=-1):
+        if n is None or n < 0:
+            self._fill(1 << 62)
+            n = len(self._buf) - self._bpos
+        else:
+            self._fill(n)
+        out = self._buf[self._bpos:self._bpos + n]
+        self._bpos += len(out)
+        return out
+
+    def readinto(self, b):
+        view = memoryview(b).cast("B")
+        data = self.read(len(view))
+        view[:len(data)] = data
+        return len(data)
+
+    def close(self):
+        self._pool.shutdown(wait=False)
+        try:
+            self._mm.close()
+        finally:
+            self._fh.close()
+
+
 def _open_maybe_gz(filename):
     with open(filename, "rb") as fh:
         magic = fh.read(2)
     if magic == b"\x1f\x8b":
+        import mmap
+
+        with open(filename, "rb") as fh:
+            mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+        index = gz_member_index(mm) if _kd_member_size(mm, 0) is not None else None
+        if index is not None:
+            return _IndexedGzReader(filename, mm, index)
+        mm.close()
         return gzip.open(filename, "rb")
     return open(filename, "rb")
+
+
+def gz_indexed_members(data, member_bytes=1 << 20, compresslevel=6):
+    """`data` (bytes-like) as a sequence of indexed gzip members of `member_bytes` raw bytes,
+    deflated in parallel; readable by any gzip reader, in parallel by `_IndexedGzReader`."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    view = memoryview(data).cast("B")
+
+    def one(lo):
+        chunk = view[lo:lo + member_bytes]
+        co = zlib.compressobj(compresslevel, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        size = 20 + 1 + len(body) + 8  # header + empty FNAME's NUL + deflate + CRC32 + ISIZE
+        head = _KD_HEAD.pack(b"\x1f\x8b\x08\x0c", 0, 0, 255, 8, b"KD", 4, size) + b"\x00"
+        return head + body + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk) & 0xFFFFFFFF)
+
+    starts = range(0, max(len(view), 1), member_bytes)
+    with ThreadPoolExecutor(max_workers=_inflate_workers()) as pool:
+        return list(pool.map(one, starts))
 
 
 def _read_exact(fh, n):
@@ -437,14 +578,17 @@ def write_mcpl_file(
     rec, hdr = pack_records(ekin=ekin, x=x, y=y, z=z, ux=ux, uy=uy, uz=uz, time=time,
                             weight=weight, pdgcode=pdgcode, polx=polx, poly=poly, polz=polz,
                             userflags=userflags, double_prec=double_prec, srcname=srcname)
-    opener = (
-        (lambda f: gzip.open(f, "wb", compresslevel=compresslevel))
-        if compress
-        else (lambda f: open(f, "wb"))
-    )
-    with opener(filename) as fh:
-        fh.write(hdr)
-        fh.write(rec.tobytes())
+    with open(filename, "wb") as fh:
+        if compress:
+            # indexed gzip members, deflated on all cores (and read back the same way)
+            for member in gz_indexed_members(hdr, compresslevel=compresslevel):
+                fh.write(member)
+            for member in gz_indexed_members(rec.view(np.uint8).reshape(-1),
+                                             compresslevel=compresslevel):
+                fh.write(member)
+        else:
+            fh.write(hdr)
+            fh.write(rec.tobytes())
     return os.path.abspath(filename)
 
 

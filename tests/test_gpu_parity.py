@@ -954,8 +954,15 @@ def test_resample_to_mcpl_gpu_gzip_equals_host_gzip(oracle, tmp_path, monkeypatc
     assert a == b and len(a) > n * 36
     assert os.path.getsize("gpu.mcpl.gz") < 0.8 * len(a)
     with mcpl.MCPLFile("gpu.mcpl.gz", blocklength=n) as f:
+        # every member (MCPL header through zlib, records from the device compressor)
+        # announces its size, so the file is inflated member-parallel
+        assert isinstance(f._fh, mcpl._IndexedGzReader)
         pb = f.read_block()
     assert f.nparticles == n and len(pb) == n and np.all(pb.weight == 1)
+    raw = open("gpu.mcpl.gz", "rb").read()
+    offs, sizes, raws = mcpl.gz_member_index(raw)
+    assert int(raws.sum()) == len(a) and int(sizes.sum()) == len(raw)
+    assert np.all(sizes % 4 == 0) or np.all(sizes[1:] % 4 == 0)  # device members stay 4-byte aligned
 
 
 # ------------------------------------------ KDSource object vs the reference's own

@@ -121,6 +121,58 @@ def test_mcpl_write_read_roundtrip(tmp_path, double_prec, gz):
         assert len(f.read_block()) == 5
 
 
+def test_indexed_gzip_members_parallel_reader(tmp_path):
+    """The .gz files this package writes are sequences of gzip members that carry their own
+    size ("KD" FEXTRA subfield): any gzip reader inflates them as one stream, MCPLFile hops
+    from header to header and inflates the members in parallel -- same bytes; a file without
+    the index (or with one foreign member) falls back to the streaming reader."""
+    import gzip
+    import zlib
+
+    from kdsource_b200 import mcpl
+
+    rng = np.random.default_rng(3)
+    n = 200_000
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    fn = str(tmp_path / "idx.mcpl.gz")
+    mcpl.write_mcpl_file(fn, ekin=rng.uniform(0, 10, n), x=d[:, 0], y=d[:, 1], z=d[:, 2],
+                         ux=d[:, 0], uy=d[:, 1], uz=d[:, 2], time=rng.uniform(0, 5, n),
+                         weight=rng.uniform(0.1, 2, n), pdgcode=2112)
+    raw = open(fn, "rb").read()
+    index = mcpl.gz_member_index(raw)
+    assert index is not None and len(index[0]) >= 7  # header member + 1 MiB members
+    offs, sizes, raws = index
+    assert offs[0] == 0 and np.array_equal(offs[1:], np.cumsum(sizes)[:-1])
+    assert offs[-1] + sizes[-1] == len(raw)
+    whole = gzip.decompress(raw)
+    assert int(raws.sum()) == len(whole)
+    assert zlib.decompress(raw[offs[2]:offs[2] + sizes[2]], 31) == \
+        whole[int(raws[:2].sum()):int(raws[:3].sum())]
+    with mcpl.MCPLFile(fn) as f:
+        assert isinstance(f._fh, mcpl._IndexedGzReader)
+        buf, cnt = f.read_raw_bytes(n)
+        assert cnt == n and bytes(buf) == whole[len(whole) - len(buf):]
+        f.rewind()
+        f.skip_forward(n - 3)
+        assert len(f.read_block()) == 3
+    # small reads crossing member boundaries
+    rd = mcpl._open_maybe_gz(fn)
+    got = b"".join(iter(lambda: rd.read(777_777), b""))
+    rd.close()
+    assert got == whole
+    # no index -> streaming gzip; index broken by a foreign member -> streaming gzip
+    plain = str(tmp_path / "plain.mcpl.gz")
+    open(plain, "wb").write(gzip.compress(whole, 1))
+    mixed = str(tmp_path / "mixed.mcpl.gz")
+    open(mixed, "wb").write(raw + gzip.compress(b"", 1))
+    for other in (plain, mixed):
+        with mcpl.MCPLFile(other) as f:
+            assert not isinstance(f._fh, mcpl._IndexedGzReader)
+            buf2, cnt2 = f.read_raw_bytes(n)
+            assert cnt2 == n and bytes(buf2) == bytes(buf)
+
+
 def test_mcpl_universal_fields_polarisation_userflags(tmp_path):
     from kdsource_b200 import mcpl
 
