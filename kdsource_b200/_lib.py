@@ -136,6 +136,7 @@ _SIGNATURES = {
     "kdsb200_sorted_ctas": (c_int, []),
     "kdsb200_sorted_nsplit": (c_int, [c_u64, c_u64]),
     "kdsb200_sorted_scratch_bytes": (c_u64, [c_u64, c_u64, c_int]),
+    "kdsb200_sorted_tilebox_floats": (c_int, [c_int]),
     "kdsb200_kde_eval_sorted_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_u64, c_int,
                                             c_void_p, c_void_p, c_u64, c_u64, c_int, c_double,
                                             c_double, c_double, c_int, c_void_p, c_void_p,

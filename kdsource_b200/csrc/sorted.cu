@@ -9,6 +9,9 @@
 //   * skips every tile whose box is farther than the cutoff from the box of the CTA's
 //     1024 query points (which are ordered the same way) -- exact: a skipped tile holds no
 //     pair inside the radius, and pairs inside visited tiles are still masked one by one;
+//     a tile stays the unit of the bulk copy, but each of its eight runs of 64 sources
+//     carries a box of its own and is skipped on the same test (in six dimensions a run
+//     of 64 is ~0.7 of the tile's extent per axis, which halves the pairs computed);
 //   * forms q - x as (q - c_tile) - (x - c_tile): both terms are small, so the fp32
 //     rounding error scales with the tile size instead of the spread of the whole list
 //     (the accuracy of the split-coordinate kernel at the (2D+1) lane-op cost).
@@ -302,8 +305,12 @@ struct Center8 {
 
 // rows as in common.cuh, coordinates relative to the tile centre:
 //   rows 0..D-1 : -((x_k - c_k) - t_k) * a_i ; row D : a_i ; row D+1 : nlc_i (mode 0) or c_i (mode 1)
-// tilebox[t] = {lo[D], hi[D]} of (x - c) over the tile (rounded outwards), tilecen[t] = t_k
-// (a multiple of 1/grid, exact in fp32).
+// tilebox[t] = {lo[D], hi[D]} of (x - c) over the tile (rounded outwards), followed by
+// {lo[D], hi[D], hmax} of each of its SV_NSUB runs of TS / SV_NSUB sources (an empty run
+// has lo = +inf); tilecen[t] = t_k (a multiple of 1/grid, exact in fp32).
+constexpr int SV_NSUB = 8;
+__host__ __device__ constexpr int tilebox_stride(int D) { return 2 * D + SV_NSUB * (2 * D + 1); }
+
 template <int D>
 __global__ void __launch_bounds__(TS)
     pack_sorted_kernel(const double* __restrict__ data, const double* __restrict__ w,
@@ -353,11 +360,34 @@ __global__ void __launch_bounds__(TS)
     float lo = (float)a, hi = (float)b;
     if ((double)lo > a) lo = nextafterf(lo, -INFINITY);
     if ((double)hi < b) hi = nextafterf(hi, INFINITY);
-    tilebox[t * 2 * D + j] = lo;
-    tilebox[t * 2 * D + D + j] = hi;
+    tilebox[t * tilebox_stride(D) + j] = lo;
+    tilebox[t * tilebox_stride(D) + D + j] = hi;
     const double mid = rint(0.5 * (a + b) * grid) / grid;
     tc[j] = mid;
     tilecen[t * D + j] = (float)mid;
+  }
+  if (j >= 32 && j < 32 + SV_NSUB * (D + 1)) {  // boxes and largest bandwidths of the runs
+    constexpr int WPS = TS / 32 / SV_NSUB;  // warps per run
+    const int sub = (j - 32) / (D + 1), k = (j - 32) % (D + 1);
+    float* sb = tilebox + t * tilebox_stride(D) + 2 * D + sub * (2 * D + 1);
+    if (k < D) {
+      double a = INFINITY, b = -INFINITY;
+      for (int e = sub * WPS; e < (sub + 1) * WPS; e++) {
+        a = fmin(a, smn[k][e]);
+        b = fmax(b, smx[k][e]);
+      }
+      float lo = (float)a, hi = (float)b;
+      if ((double)lo > a) lo = nextafterf(lo, -INFINITY);
+      if ((double)hi < b) hi = nextafterf(hi, INFINITY);
+      sb[k] = lo;
+      sb[D + k] = hi;
+    } else {
+      double hm = 0.0;
+      for (int e = sub * WPS; e < (sub + 1) * WPS; e++) hm = fmax(hm, shm[e]);
+      float hf = (float)hm;
+      if ((double)hf < hm) hf = nextafterf(hf, INFINITY);
+      sb[2 * D] = hf;
+    }
   }
   if (j == TS - 1) {  // largest bandwidth of the tile, rounded up
     double hm = 0.0;
@@ -417,6 +447,7 @@ struct SortedCtl {
   unsigned int next_item;            // dynamic work counter
   unsigned int pad;
   unsigned long long tiles_visited;  // sum over work items of the tiles they loaded
+  unsigned long long runs_visited;   // ... and of the 64-source runs they computed
 };
 
 // KERN 0 gaussian, 1 epa, 2 box (rows as in kde_eval.cu).  CUT 1: one hard radius for all
@@ -520,8 +551,9 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
       for (uint32_t c0 = t0; c0 < t1; c0 += SV_THREADS) {
         const uint32_t t = c0 + tid;
         bool keep = false;
+        uint32_t mask = 0;  // the tile's runs of 64 sources that lie within the radius
         if (t < t1) {
-          const float* bx = tilebox + (uint64_t)t * 2 * D;
+          const float* bx = tilebox + (uint64_t)t * tilebox_stride(D);
           float d2 = 0.f;
 #pragma unroll
           for (int k = 0; k < D; k++) {
@@ -529,14 +561,28 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
             d2 = fmaf(g, g, d2);
           }
           const float rt = rad_scale > 0.f ? __ldg(tilehmax + t) * rad_scale : cull_r;
-          keep = d2 <= rt * rt;
+          if (d2 <= rt * rt) {
+            for (int sub = 0; sub < SV_NSUB; sub++) {
+              const float* sb = bx + 2 * D + sub * (2 * D + 1);
+              float e2 = 0.f;
+#pragma unroll
+              for (int k = 0; k < D; k++) {
+                const float g =
+                    fmaxf(fmaxf(__ldg(sb + k) - qhi[k], qlo[k] - __ldg(sb + D + k)), 0.f);
+                e2 = fmaf(g, g, e2);
+              }
+              const float rs = rad_scale > 0.f ? __ldg(sb + 2 * D) * rad_scale : cull_r;
+              if (e2 <= rs * rs) mask |= 1u << sub;  // an empty run is at infinity
+            }
+            keep = mask != 0;
+          }
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_wcnt[warp] = __popc(bal);
         __syncthreads();
         uint32_t off = s_nlist;
         for (int wv = 0; wv < warp; wv++) off += s_wcnt[wv];
-        if (keep) my_list[off + __popc(bal & ((1u << lane) - 1u))] = t;
+        if (keep) my_list[off + __popc(bal & ((1u << lane) - 1u))] = t | (mask << 24);
         __syncthreads();
         if (tid == 0) {
           uint32_t tot = 0;
@@ -547,10 +593,12 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
       }
       nlist = s_nlist;
     }
-    auto tile_id = [&](uint32_t l) -> uint32_t { return CULL ? my_list[l] : t0 + l; };
+    auto tile_id = [&](uint32_t l) -> uint32_t {
+      return CULL ? (my_list[l] & 0xffffffu) : t0 + l;
+    };
+    uint32_t nruns = 0;
 
     if (tid == 0) {
-      if (nlist) atomicAdd(&ctl->tiles_visited, (unsigned long long)nlist);
       for (uint32_t p = 0; p < (uint32_t)(SV_STAGES - 1) && p < nlist; p++) {
         const uint32_t st = (itg + p) % SV_STAGES;
         mbar_expect_tx(&full[st], TILE_BYTES);
@@ -583,6 +631,8 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
           q[qi][k] = (__ldg(qT + (uint64_t)k * Mpad + mbase + qi * SV_THREADS) - ck) +
                      __ldg(qT + (uint64_t)(D + k) * Mpad + mbase + qi * SV_THREADS);
       }
+      const uint32_t rmask = CULL ? (my_list[it] >> 24) : (1u << SV_NSUB) - 1u;
+      nruns += __popc(rmask);
       mbar_wait(&full[s], parity);
       const float* tile = tiles + s * TILE_FLOATS;
 
@@ -590,8 +640,11 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
 #pragma unroll
       for (int qi = 0; qi < SV_Q; qi++) acc[qi] = 0ull;
 
+#pragma unroll 1
+      for (int sub = 0; sub < SV_NSUB; sub++) {
+      if (CULL && !((rmask >> sub) & 1u)) continue;
 #pragma unroll 2
-      for (int j = 0; j < TS; j += 4) {
+      for (int j = sub * (TS / SV_NSUB); j < (sub + 1) * (TS / SV_NSUB); j += 4) {
         float4 r[ROWS];
 #pragma unroll
         for (int k = 0; k < ROWS; k++) r[k] = *reinterpret_cast<const float4*>(tile + k * TS + j);
@@ -654,6 +707,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
           acc[qi] = f2_add(acc[qi], f2_add(f2_pack(eA0, eA1), f2_pack(eB0, eB1)));
         }
       }
+      }
 #pragma unroll
       for (int qi = 0; qi < SV_Q; qi++) {
         float lo, hi;
@@ -665,6 +719,10 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
 #pragma unroll
     for (int qi = 0; qi < SV_Q; qi++)
       out[(uint64_t)sp * Mpad + mbase + qi * SV_THREADS] = accd[qi] * out_scale;
+    if (tid == 0 && nlist) {
+      atomicAdd(&ctl->tiles_visited, (unsigned long long)nlist);
+      atomicAdd(&ctl->runs_visited, (unsigned long long)nruns);
+    }
     __syncthreads();  // s_item / the list are rewritten by the next item
   }
 }
@@ -712,6 +770,8 @@ using namespace kdsb;
 extern "C" {
 
 uint64_t kdsb200_minmax_scratch(void) { return (uint64_t)MM_BLOCKS * 16; }
+
+int kdsb200_sorted_tilebox_floats(int D) { return tilebox_stride(D); }
 
 int kdsb200_column_minmax(const double* d_data, uint64_t N, int D, double* d_scratch,
                           double* d_minmax, void* stream) {
@@ -903,6 +963,10 @@ int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
     KDSB_CUDA(cudaMemsetAsync(d_out, 0, M * sizeof(double), st));
     return 0;
   }
+  if (ntl >= (1u << 24)) {  // the work lists carry the run mask in the top byte
+    set_error("kde_eval_sorted: more than 2^24 tiles (N < 8.6e9)");
+    return 1;
+  }
   if (nsplit < 1) nsplit = 1;
   if ((uint32_t)nsplit > ntl) nsplit = (int)ntl;
   const uint32_t tps = (ntl + nsplit - 1) / nsplit;
@@ -963,8 +1027,8 @@ int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
   reduce_scatter_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(partial, nsplit, M, Mpad,
                                                                      d_perm_q, d_out);
   KDSB_CUDA(cudaGetLastError());
-  if (d_tiles_visited)
-    KDSB_CUDA(cudaMemcpyAsync(d_tiles_visited, &ctl->tiles_visited, sizeof(uint64_t),
+  if (d_tiles_visited)  // {tiles loaded, runs of 64 sources computed}
+    KDSB_CUDA(cudaMemcpyAsync(d_tiles_visited, &ctl->tiles_visited, 2 * sizeof(uint64_t),
                               cudaMemcpyDeviceToDevice, st));
   return 0;
 }

@@ -194,8 +194,8 @@ class TreeKDE:
         (out,), visited = _lib.stream_pieces(pts, lo, hi, chunk, work, tag="eval")
         if culled and n:  # tiles loaded over all pieces of this call
             t = _lib.torch()
-            self.last_tiles_visited = t.tensor(sum(int(v.item()) for v in visited),
-                                               dtype=t.int64)
+            self.last_tiles_visited = t.tensor(sum(float(v.item()) for v in visited),
+                                               dtype=t.float64)
         if shard and world > 1:  # the ranks' disjoint slices, in rank (= query) order
             out = _dist.allgather_rows(out)
         return out
@@ -319,7 +319,8 @@ class TreeKDE:
             d_h = d_bw if gauss or d_bw is None else _lib.to_dev(bw_arr * sc)
             lc_ref = np.log2(wmax * w_scale) - D * np.log2(hmin * sc)
             packed = _lib.empty(L.kdsb200_packed_floats(N, D), t.float32)
-            tilebox = _lib.empty(ntl * 2 * D, t.float32)
+            tb_stride = int(L.kdsb200_sorted_tilebox_floats(D))
+            tilebox = _lib.empty(ntl * tb_stride, t.float32)
             tilecen = _lib.empty(ntl * D, t.float32)
             tilehmax = _lib.empty(ntl, t.float32)
             cen_keep, cen_p = _lib.hostvec(center)
@@ -327,7 +328,7 @@ class TreeKDE:
                 _lib.ptr(d_data), _lib.ptr(d_w), _lib.ptr(d_h), bw_scalar * sc, N, D,
                 _lib.ptr(perm), cen_p, grid, w_scale, lc_ref, 0 if gauss else 1,
                 _lib.ptr(packed), _lib.ptr(tilebox), _lib.ptr(tilecen), _lib.ptr(tilehmax), st))
-            box = tilebox.cpu().numpy().reshape(ntl, 2, D)
+            box = tilebox.view(ntl, tb_stride)[:, :2 * D].cpu().numpy().reshape(ntl, 2, D)
             extent = float(np.max(box[:, 1] - box[:, 0])) / 2 if N > 1 else 0.0
             if (dtype == "auto" and gauss and self.cutoff is None
                     and hmin < self.AUTO_SPLIT_BELOW * extent):
@@ -433,15 +434,17 @@ class TreeKDE:
                                                          _lib.ptr(qT), st))
             nsplit = L.kdsb200_sorted_nsplit(N, M)
             scratch = _lib.empty(L.kdsb200_sorted_scratch_bytes(N, Mpad, nsplit), t.uint8)
-            visited = _lib.empty(1, t.int64)
+            visited = _lib.empty(2, t.int64)
             _lib.check(L.kdsb200_kde_eval_sorted_f32(
                 _lib.ptr(dev["packed"]), _lib.ptr(dev["tilebox"]), _lib.ptr(dev["tilecen"]),
                 _lib.ptr(dev["tilehmax"]), N, D, _lib.ptr(qT), _lib.ptr(perm_q), M, Mpad,
                 _KERNEL_ID[dev["kernel"]], dev["cull"], dev["cull_rel"], dev["out_scale"], nsplit,
                 _lib.ptr(scratch), _lib.ptr(d_out), _lib.ptr(visited), st))
-            #: device counter of the last call: tiles loaded, summed over the (1024-query
-            #: block, source split) work items; executed pairs = that * 512 * 1024
-            self.last_tiles_visited = visited
+            #: device counters of the last call, summed over the (1024-query block, source
+            #: split) work items: tiles loaded, and 512-source tile equivalents computed (runs
+            #: of 64 sources / 8); executed pairs = last_tiles_visited * 512 * 1024
+            self.last_tiles_loaded = visited[0]
+            self.last_tiles_visited = visited[1].to(t.float64) / 8.0
             self.last_work_items_pairs = 512 * 1024
         elif dev["dtype"] == "float32_dense":
             Mpad = L.kdsb200_eval_mpad(M)
