@@ -334,6 +334,10 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
     def host_api_seconds(fn, reps=3):
         """Median wall time of fn() through the host API after one warm-up call (the first
         call allocates the pinned staging buffers)."""
+        import gc
+
+        gc.collect()
+        t.cuda.empty_cache()  # start from the allocator state a fresh process would have
         fn()
         ts = []
         for _ in range(reps):
