@@ -10,8 +10,11 @@
 //     1024 query points (which are ordered the same way) -- exact: a skipped tile holds no
 //     pair inside the radius, and pairs inside visited tiles are still masked one by one;
 //     a tile stays the unit of the bulk copy, but each of its eight runs of 64 sources
-//     carries a box of its own and is skipped on the same test (in six dimensions a run
-//     of 64 is ~0.7 of the tile's extent per axis, which halves the pairs computed);
+//     carries a box of its own, and so does each quarter of the CTA's queries (the qi-th
+//     query of every thread: 256 consecutive points of the curve); a (run, quarter) cell
+//     is computed only if its two boxes pass the same test -- a CTA-uniform decision, so no
+//     lane diverges (in six dimensions a run of 64 is ~0.7 and a quarter ~0.8 of the
+//     extent per axis);
 //   * forms q - x as (q - c_tile) - (x - c_tile): both terms are small, so the fp32
 //     rounding error scales with the tile size instead of the spread of the whole list
 //     (the accuracy of the split-coordinate kernel at the (2D+1) lane-op cost).
@@ -447,7 +450,8 @@ struct SortedCtl {
   unsigned int next_item;            // dynamic work counter
   unsigned int pad;
   unsigned long long tiles_visited;  // sum over work items of the tiles they loaded
-  unsigned long long runs_visited;   // ... and of the 64-source runs they computed
+  unsigned long long cells_visited;  // ... and of the (64-source run x 256-query quarter) cells
+                                     //     they computed
 };
 
 // KERN 0 gaussian, 1 epa, 2 box (rows as in kde_eval.cu).  CUT 1: one hard radius for all
@@ -471,8 +475,9 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
   float* tiles = reinterpret_cast<float*>(smem_raw);
   __shared__ __align__(8) uint64_t full[SV_STAGES];
   __shared__ unsigned int s_item;
-  __shared__ float s_box[2 * D];
-  __shared__ float s_red[2 * D][SV_THREADS / 32];
+  __shared__ float s_box[2 * D];            // box of the item's 1024 queries
+  __shared__ float s_qbox[SV_Q][2 * D];     // ... and of each quarter (the qi-th query of every thread)
+  __shared__ float s_red[SV_Q][2 * D][SV_THREADS / 32];
   __shared__ uint32_t s_wcnt[SV_THREADS / 32];
   __shared__ uint32_t s_nlist;
 
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
   __syncthreads();
   const uint32_t n_qb = (uint32_t)(Mpad / SV_QB);
   const uint32_t n_items = n_qb * (uint32_t)nsplit;
-  uint32_t* my_list = lists + (uint64_t)blockIdx.x * tiles_per_split;
+  uint32_t* my_list = lists + (uint64_t)blockIdx.x * tiles_per_split * 2;  // {tile, cell mask}
   uint32_t itg = 0;  // tiles consumed so far by this CTA (pipeline stage / parity)
 
   for (;;) {
@@ -499,46 +504,48 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
 
     uint32_t nlist = t1 > t0 ? t1 - t0 : 0;
     if (CULL) {
-      // bounding box of the item's queries (hi + lo, recentred coordinates)
-      float bmn[D], bmx[D];
-#pragma unroll
-      for (int k = 0; k < D; k++) {
-        bmn[k] = INFINITY;
-        bmx[k] = -INFINITY;
-      }
+      // bounding boxes of the item's queries (hi + lo, recentred coordinates): one per
+      // quarter -- the qi-th queries of all threads are 256 consecutive points of the curve
+      // -- and their union
 #pragma unroll
       for (int qi = 0; qi < SV_Q; qi++)
 #pragma unroll
         for (int k = 0; k < D; k++) {
           const float v = __ldg(qT + (uint64_t)k * Mpad + mbase + qi * SV_THREADS) +
                           __ldg(qT + (uint64_t)(D + k) * Mpad + mbase + qi * SV_THREADS);
-          bmn[k] = fminf(bmn[k], v);
-          bmx[k] = fmaxf(bmx[k], v);
-        }
+          float a = v, b = v;
 #pragma unroll
-      for (int k = 0; k < D; k++) {
-        float a = bmn[k], b = bmx[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          a = fminf(a, __shfl_down_sync(0xffffffffu, a, off));
-          b = fmaxf(b, __shfl_down_sync(0xffffffffu, b, off));
+          for (int off = 16; off > 0; off >>= 1) {
+            a = fminf(a, __shfl_down_sync(0xffffffffu, a, off));
+            b = fmaxf(b, __shfl_down_sync(0xffffffffu, b, off));
+          }
+          if (lane == 0) {
+            s_red[qi][k][warp] = a;
+            s_red[qi][D + k][warp] = b;
+          }
         }
-        if (lane == 0) {
-          s_red[k][warp] = a;
-          s_red[D + k][warp] = b;
+      __syncthreads();
+      if (tid < SV_Q * D) {
+        const int qi = tid / D, k = tid % D;
+        float a = INFINITY, b = -INFINITY;
+        for (int e = 0; e < SV_THREADS / 32; e++) {
+          a = fminf(a, s_red[qi][k][e]);
+          b = fmaxf(b, s_red[qi][D + k][e]);
         }
+        s_qbox[qi][k] = a;
+        s_qbox[qi][D + k] = b;
       }
+      if (tid == 0) s_nlist = 0;
       __syncthreads();
       if (tid < D) {
         float a = INFINITY, b = -INFINITY;
-        for (int e = 0; e < SV_THREADS / 32; e++) {
-          a = fminf(a, s_red[tid][e]);
-          b = fmaxf(b, s_red[D + tid][e]);
+        for (int qi = 0; qi < SV_Q; qi++) {
+          a = fminf(a, s_qbox[qi][tid]);
+          b = fmaxf(b, s_qbox[qi][D + tid]);
         }
         s_box[tid] = a;
         s_box[D + tid] = b;
       }
-      if (tid == 0) s_nlist = 0;
       __syncthreads();
       float qlo[D], qhi[D];
 #pragma unroll
@@ -564,15 +571,27 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
           if (d2 <= rt * rt) {
             for (int sub = 0; sub < SV_NSUB; sub++) {
               const float* sb = bx + 2 * D + sub * (2 * D + 1);
+              float slo[D], shi[D];
               float e2 = 0.f;
 #pragma unroll
               for (int k = 0; k < D; k++) {
-                const float g =
-                    fmaxf(fmaxf(__ldg(sb + k) - qhi[k], qlo[k] - __ldg(sb + D + k)), 0.f);
+                slo[k] = __ldg(sb + k);
+                shi[k] = __ldg(sb + D + k);
+                const float g = fmaxf(fmaxf(slo[k] - qhi[k], qlo[k] - shi[k]), 0.f);
                 e2 = fmaf(g, g, e2);
               }
               const float rs = rad_scale > 0.f ? __ldg(sb + 2 * D) * rad_scale : cull_r;
-              if (e2 <= rs * rs) mask |= 1u << sub;  // an empty run is at infinity
+              if (!(e2 <= rs * rs)) continue;  // an empty run is at infinity
+              for (int qi = 0; qi < SV_Q; qi++) {  // the run against each quarter's box
+                float f2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                  const float g =
+                      fmaxf(fmaxf(slo[k] - s_qbox[qi][D + k], s_qbox[qi][k] - shi[k]), 0.f);
+                  f2 = fmaf(g, g, f2);
+                }
+                if (f2 <= rs * rs) mask |= 1u << (sub * SV_Q + qi);
+              }
             }
             keep = mask != 0;
           }
@@ -582,7 +601,11 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
         __syncthreads();
         uint32_t off = s_nlist;
         for (int wv = 0; wv < warp; wv++) off += s_wcnt[wv];
-        if (keep) my_list[off + __popc(bal & ((1u << lane) - 1u))] = t | (mask << 24);
+        if (keep) {
+          const uint32_t pos = off + __popc(bal & ((1u << lane) - 1u));
+          my_list[2 * pos] = t;
+          my_list[2 * pos + 1] = mask;
+        }
         __syncthreads();
         if (tid == 0) {
           uint32_t tot = 0;
@@ -593,10 +616,8 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
       }
       nlist = s_nlist;
     }
-    auto tile_id = [&](uint32_t l) -> uint32_t {
-      return CULL ? (my_list[l] & 0xffffffu) : t0 + l;
-    };
-    uint32_t nruns = 0;
+    auto tile_id = [&](uint32_t l) -> uint32_t { return CULL ? my_list[2 * l] : t0 + l; };
+    uint32_t ncells = 0;
 
     if (tid == 0) {
       for (uint32_t p = 0; p < (uint32_t)(SV_STAGES - 1) && p < nlist; p++) {
@@ -631,8 +652,8 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
           q[qi][k] = (__ldg(qT + (uint64_t)k * Mpad + mbase + qi * SV_THREADS) - ck) +
                      __ldg(qT + (uint64_t)(D + k) * Mpad + mbase + qi * SV_THREADS);
       }
-      const uint32_t rmask = CULL ? (my_list[it] >> 24) : (1u << SV_NSUB) - 1u;
-      nruns += __popc(rmask);
+      const uint32_t cmask = CULL ? my_list[2 * it + 1] : 0xffffffffu;
+      ncells += __popc(cmask);
       mbar_wait(&full[s], parity);
       const float* tile = tiles + s * TILE_FLOATS;
 
@@ -642,7 +663,8 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
 
 #pragma unroll 1
       for (int sub = 0; sub < SV_NSUB; sub++) {
-      if (CULL && !((rmask >> sub) & 1u)) continue;
+      const uint32_t m4 = (cmask >> (sub * SV_Q)) & ((1u << SV_Q) - 1u);
+      if (CULL && !m4) continue;
 #pragma unroll 2
       for (int j = sub * (TS / SV_NSUB); j < (sub + 1) * (TS / SV_NSUB); j += 4) {
         float4 r[ROWS];
@@ -660,6 +682,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
         }
 #pragma unroll
         for (int qi = 0; qi < SV_Q; qi++) {
+          if (CULL && !((m4 >> qi) & 1u)) continue;  // the whole CTA skips this quarter
           f2_t tA = (CUT || KERN) ? 0ull : l01, tB = (CUT || KERN) ? 0ull : l23;
 #pragma unroll
           for (int k = 0; k < D; k++) {
@@ -721,7 +744,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
       out[(uint64_t)sp * Mpad + mbase + qi * SV_THREADS] = accd[qi] * out_scale;
     if (tid == 0 && nlist) {
       atomicAdd(&ctl->tiles_visited, (unsigned long long)nlist);
-      atomicAdd(&ctl->runs_visited, (unsigned long long)nruns);
+      atomicAdd(&ctl->cells_visited, (unsigned long long)ncells);
     }
     __syncthreads();  // s_item / the list are rewritten by the next item
   }
@@ -925,7 +948,7 @@ uint64_t kdsb200_sorted_scratch_bytes(uint64_t N, uint64_t Mpad, int nsplit) {
   const uint64_t ntl = n_tiles_for(N);
   if (nsplit < 1) nsplit = 1;
   const uint64_t tps = (ntl + nsplit - 1) / nsplit;
-  return 64 + (uint64_t)kdsb200_sorted_ctas() * tps * 4 + (uint64_t)nsplit * Mpad * 8 + 64;
+  return 64 + (uint64_t)kdsb200_sorted_ctas() * tps * 8 + (uint64_t)nsplit * Mpad * 8 + 64;
 }
 
 int kdsb200_sorted_nsplit(uint64_t N, uint64_t M) {
@@ -963,10 +986,6 @@ int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
     KDSB_CUDA(cudaMemsetAsync(d_out, 0, M * sizeof(double), st));
     return 0;
   }
-  if (ntl >= (1u << 24)) {  // the work lists carry the run mask in the top byte
-    set_error("kde_eval_sorted: more than 2^24 tiles (N < 8.6e9)");
-    return 1;
-  }
   if (nsplit < 1) nsplit = 1;
   if ((uint32_t)nsplit > ntl) nsplit = (int)ntl;
   const uint32_t tps = (ntl + nsplit - 1) / nsplit;
@@ -975,7 +994,7 @@ int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
   unsigned char* p = (unsigned char*)d_scratch;
   SortedCtl* ctl = (SortedCtl*)p;
   uint32_t* lists = (uint32_t*)(p + 64);
-  uint64_t off = 64 + (uint64_t)ctas * tps * 4;
+  uint64_t off = 64 + (uint64_t)ctas * tps * 8;
   off = (off + 63) / 64 * 64;
   double* partial = (double*)(p + off);
   KDSB_CUDA(cudaMemsetAsync(ctl, 0, sizeof(SortedCtl), st));
@@ -1027,7 +1046,7 @@ int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
   reduce_scatter_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(partial, nsplit, M, Mpad,
                                                                      d_perm_q, d_out);
   KDSB_CUDA(cudaGetLastError());
-  if (d_tiles_visited)  // {tiles loaded, runs of 64 sources computed}
+  if (d_tiles_visited)  // {tiles loaded, (64-source run x 256-query quarter) cells computed}
     KDSB_CUDA(cudaMemcpyAsync(d_tiles_visited, &ctl->tiles_visited, 2 * sizeof(uint64_t),
                               cudaMemcpyDeviceToDevice, st));
   return 0;

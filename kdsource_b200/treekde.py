@@ -441,10 +441,10 @@ class TreeKDE:
                 _KERNEL_ID[dev["kernel"]], dev["cull"], dev["cull_rel"], dev["out_scale"], nsplit,
                 _lib.ptr(scratch), _lib.ptr(d_out), _lib.ptr(visited), st))
             #: device counters of the last call, summed over the (1024-query block, source
-            #: split) work items: tiles loaded, and 512-source tile equivalents computed (runs
-            #: of 64 sources / 8); executed pairs = last_tiles_visited * 512 * 1024
+            #: split) work items: tiles loaded, and 512 x 1024 tile equivalents computed (cells
+            #: of 64 sources x 256 queries / 32); executed pairs = last_tiles_visited * 512 * 1024
             self.last_tiles_loaded = visited[0]
-            self.last_tiles_visited = visited[1].to(t.float64) / 8.0
+            self.last_tiles_visited = visited[1].to(t.float64) / 32.0
             self.last_work_items_pairs = 512 * 1024
         elif dev["dtype"] == "float32_dense":
             Mpad = L.kdsb200_eval_mpad(M)
