@@ -473,7 +473,7 @@ def sub_benchmarks(t, peaks, quick, cpu=True):
                      "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": (2.0 * nb + zbytes) / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "per_unit": "72 B read (two passes) + {:.1f} B written per particle; "
-                                 "includes the memset of the output buffer".format(zbytes / nout),
+                                 "the encoder zeroes its output itself".format(zbytes / nout),
                      "traffic": None}}
     del gz_out, gz_scr
     sub["resample"]["e2e"] = resample_e2e(ps, ws_, bws, gs_, sc_, quick)

@@ -205,6 +205,50 @@ __global__ void gz_hist_kernel(const unsigned char* __restrict__ data, uint64_t 
     if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
 }
 
+// ---- the member's bytes in shared memory --------------------------------------------
+// Each thread walks its own chunk of the member word by word (the bit offsets and the CRC
+// are sequential inside a chunk), which from global memory is a 32-way scattered 4-byte
+// load per step.  A full member is therefore copied into shared memory first, with
+// coalesced loads, chunk c at word offset c * (CW + pad): pad makes the stride odd, so the
+// 32 lanes of a warp -- all at the same position inside their chunks -- hit 32 banks.
+constexpr uint32_t GZ_STAGE_MAX = 96u << 10;  // members up to this size are staged
+
+struct GzSrc {
+  const uint32_t* g;   // member in global memory
+  const uint32_t* sm;  // staged copy (nullptr: read global)
+  uint32_t inv, pad;   // ceil(2^32 / CW), 0 | 1
+  __device__ __forceinline__ uint32_t word(uint32_t o) const {  // o = byte offset, % 4 == 0
+    const uint32_t i = o >> 2;
+    return sm ? sm[i + __umulhi(i, inv) * pad] : __ldg(g + i);
+  }
+};
+
+__device__ __forceinline__ uint32_t gz_stage_words(uint32_t member_bytes) {
+  const uint32_t cw = member_bytes / (4u * GZ_THREADS);
+  return GZ_THREADS * (cw + ((cw & 1u) ? 0u : 1u));
+}
+
+// nb == member_bytes (a full member) and member_bytes <= GZ_STAGE_MAX
+__device__ __forceinline__ GzSrc gz_stage(const unsigned char* member, uint32_t member_bytes,
+                                          uint32_t* sm) {
+  const uint32_t cw = member_bytes / (4u * GZ_THREADS), pad = (cw & 1u) ? 0u : 1u;
+  const uint32_t inv = (uint32_t)((0x100000000ull + cw - 1) / cw);
+  const uint32_t* g = reinterpret_cast<const uint32_t*>(member);
+  for (uint32_t i = threadIdx.x; i < cw * GZ_THREADS; i += GZ_THREADS)
+    sm[i + __umulhi(i, inv) * pad] = __ldg(g + i);
+  __syncthreads();
+  return GzSrc{g, sm, inv, pad};
+}
+
+// does the tail of the record at member offset o repeat the previous record's tail?
+// (the first record of a member has no history: every member is its own stream)
+__device__ __forceinline__ bool gz_tail_match(const GzSrc& src, uint32_t o, uint32_t R, uint32_t S) {
+  if (o < R) return false;
+  bool eq = true;
+  for (uint32_t k = 0; k < S; k += 4) eq = eq && (src.word(o + R - S + k) == src.word(o - S + k));
+  return eq;
+}
+
 // chunk of thread t in a member of nb bytes: right-aligned frames of `chunk` bytes, so
 // only leading threads are empty / partial (leading zero bytes leave a zero CRC
 // register unchanged, which keeps the combination tree uniform)
@@ -230,38 +274,51 @@ __global__ void __launch_bounds__(GZ_THREADS)
     gz_size_kernel(const unsigned char* __restrict__ data, uint64_t nbytes, uint32_t member_bytes,
                    const GzDev* __restrict__ T, uint32_t* __restrict__ thread_bits,
                    uint32_t* __restrict__ member_bits, uint32_t* __restrict__ member_crc) {
-  __shared__ uint32_t s_len[256], s_crc[256], s_mat[6][32], s_red[GZ_THREADS / 32],
+  // s_crc[k][b]: CRC register after byte b followed by k zero bytes (slicing by 4: the four
+  // look-ups of a word are independent, where the byte-wise form is one dependent chain)
+  __shared__ uint32_t s_len[256], s_crc[4][256], s_mat[6][32], s_red[GZ_THREADS / 32],
       s_wcrc[GZ_THREADS / 32];
+  extern __shared__ __align__(16) uint32_t gz_stage_mem[];
   const int t = threadIdx.x;
   s_len[t] = T->entry[t] >> 16;
-  s_crc[t] = T->crc_tab[t];
+  s_crc[0][t] = T->crc_tab[t];
   if (t < 192) s_mat[t / 32][t % 32] = T->crc_mat[t / 32][t % 32];
   __syncthreads();
+  {
+    uint32_t c = s_crc[0][t];
+#pragma unroll
+    for (int k = 1; k < 4; k++) {
+      c = (c >> 8) ^ s_crc[0][c & 255u];
+      s_crc[k][t] = c;
+    }
+  }
   const uint64_t m = blockIdx.x;
   const uint64_t base = m * member_bytes;
   const uint32_t nb = (uint32_t)min((uint64_t)member_bytes, nbytes - base);
   uint32_t lo, hi;
   gz_chunk(nb, member_bytes / GZ_THREADS, t, lo, hi);
   uint32_t bits = 0, crc = 0;
-  const unsigned char* p = data + base;
+  GzSrc src{reinterpret_cast<const uint32_t*>(data + base), nullptr, 0u, 0u};
+  if (nb == member_bytes && member_bytes <= GZ_STAGE_MAX)
+    src = gz_stage(data + base, member_bytes, gz_stage_mem);  // ends in __syncthreads()
+  else
+    __syncthreads();
   const uint32_t R = T->rec_bytes, S = T->tail_bytes, mbits = T->match_nbits;
   // chunks are whole records (or multiples of 4 bytes in plain mode)
   for (uint32_t r = lo; r < hi; r += R ? R : (hi - lo)) {
     const uint32_t rend = R ? r + R : hi;
     uint32_t lit_end = rend;
-    if (S && gz_tail_match(p, r, R, S)) {
+    if (S && gz_tail_match(src, r, R, S)) {
       lit_end -= S;
       bits += mbits;
     }
     for (uint32_t o = r; o < rend; o += 4) {
-      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + o));
-      const bool lit = o < lit_end;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t b = (w >> (8 * k)) & 255u;
-        if (lit) bits += s_len[b];
-        crc = s_crc[(crc ^ b) & 255u] ^ (crc >> 8);
-      }
+      const uint32_t w = src.word(o);
+      if (o < lit_end)
+        bits += s_len[w & 255u] + s_len[(w >> 8) & 255u] + s_len[(w >> 16) & 255u] + s_len[w >> 24];
+      const uint32_t x = crc ^ w;
+      crc = s_crc[3][x & 255u] ^ s_crc[2][(x >> 8) & 255u] ^ s_crc[1][(x >> 16) & 255u] ^
+            s_crc[0][x >> 24];
     }
   }
   thread_bits[m * GZ_THREADS + t] = bits;
@@ -349,6 +406,7 @@ __global__ void __launch_bounds__(GZ_THREADS)
                      const uint64_t* __restrict__ member_off, uint64_t capacity,
                      unsigned char* __restrict__ out) {
   __shared__ uint32_t s_ent[257], s_scan[GZ_THREADS / 32];
+  extern __shared__ __align__(16) uint32_t gz_stage_mem[];
   const int t = threadIdx.x;
   s_ent[t] = T->entry[t];
   if (t == 0) s_ent[256] = T->entry[256];
@@ -361,6 +419,11 @@ __global__ void __launch_bounds__(GZ_THREADS)
   const uint64_t off = member_off[m];
   if (off + msize > capacity) return;  // reported by the host from the scan total
   uint32_t* words = reinterpret_cast<uint32_t*>(out + off);  // off % 4 == 0
+  // the member's bytes start from zero (headers, boundary words and the trailer are OR-ed in)
+  for (uint32_t i = t; i < msize / 4; i += GZ_THREADS) words[i] = 0u;
+  GzSrc src{reinterpret_cast<const uint32_t*>(data + base), nullptr, 0u, 0u};
+  if (nb == member_bytes && member_bytes <= GZ_STAGE_MAX)
+    src = gz_stage(data + base, member_bytes, gz_stage_mem);  // ends in __syncthreads()
   // exclusive prefix of the threads' bit counts
   const uint32_t mybits = thread_bits[m * GZ_THREADS + t];
   const int lane = t & 31, warp = t >> 5;
@@ -411,7 +474,6 @@ __global__ void __launch_bounds__(GZ_THREADS)
   uint32_t nbit = start & 31u;
   uint32_t* wp = words + (start >> 5);
   bool first = true;
-  const unsigned char* p = data + base;
   auto emit_bits = [&](uint32_t v, uint32_t n) {  // n <= 32 bits, LSB first
     acc |= (uint64_t)v << nbit;
     nbit += n;
@@ -432,10 +494,10 @@ __global__ void __launch_bounds__(GZ_THREADS)
   const uint32_t mcode = T->match_bits, mbits = T->match_nbits;
   for (uint32_t r = lo; r < hi; r += R ? R : (hi - lo)) {
     uint32_t lit_end = R ? r + R : hi;
-    const bool match = S && gz_tail_match(p, r, R, S);
+    const bool match = S && gz_tail_match(src, r, R, S);
     if (match) lit_end -= S;
     for (uint32_t o = r; o < lit_end; o += 4) {
-      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + o));
+      const uint32_t w = src.word(o);
       emit(s_ent[w & 255u]);
       emit(s_ent[(w >> 8) & 255u]);
       emit(s_ent[(w >> 16) & 255u]);
@@ -628,14 +690,28 @@ int kdsb200_gz_compress(const void* d_data, uint64_t nbytes, uint32_t member_byt
   uint64_t* member_off = (uint64_t*)(sc + 8192 + ((nm * (GZ_THREADS * 4 + 8) + 7) / 8) * 8);
   KDSB_CUDA(cudaMemcpyAsync(dT, &img, sizeof(GzDev), cudaMemcpyHostToDevice, st));
   KDSB_CUDA(cudaStreamSynchronize(st));  // `img` is reused by the next call of this thread
-  gz_size_kernel<<<(unsigned)nm, GZ_THREADS, 0, st>>>((const unsigned char*)d_data, nbytes,
-                                                      member_bytes, dT, thread_bits, member_bits,
-                                                      member_crc);
+  // full members are staged in shared memory (chunks at an odd word stride)
+  size_t stage = 0;
+  if (member_bytes <= GZ_STAGE_MAX) {
+    const uint32_t cw = member_bytes / (4u * GZ_THREADS);
+    stage = (size_t)GZ_THREADS * (cw + ((cw & 1u) ? 0u : 1u)) * 4;
+  }
+  static size_t attr_set = 0;
+  if (stage > attr_set) {
+    KDSB_CUDA(cudaFuncSetAttribute(gz_size_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)stage));
+    KDSB_CUDA(cudaFuncSetAttribute(gz_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)stage));
+    attr_set = stage;
+  }
+  gz_size_kernel<<<(unsigned)nm, GZ_THREADS, stage, st>>>((const unsigned char*)d_data, nbytes,
+                                                          member_bytes, dT, thread_bits,
+                                                          member_bits, member_crc);
   KDSB_CUDA(cudaGetLastError());
   gz_scan_kernel<<<1, GZ_THREADS, 0, st>>>(member_bits, nm, dT, member_off, d_total);
   KDSB_CUDA(cudaGetLastError());
-  KDSB_CUDA(cudaMemsetAsync(d_out, 0, out_capacity, st));
-  gz_encode_kernel<<<(unsigned)nm, GZ_THREADS, 0, st>>>(
+  // (no memset of d_out: every member zeroes its own bytes before OR-ing into them)
+  gz_encode_kernel<<<(unsigned)nm, GZ_THREADS, stage, st>>>(
       (const unsigned char*)d_data, nbytes, member_bytes, dT, thread_bits, member_bits, member_crc,
       member_off, out_capacity, (unsigned char*)d_out);
   KDSB_CUDA(cudaGetLastError());
