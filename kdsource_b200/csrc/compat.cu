@@ -1234,16 +1234,39 @@ void kdsource_resample_to_mcpl(double (*rng_stateless)(void), const char* kds_so
   cuda_or_die(kdsb200_gz_writer_put_host(w, hdr.data(), hdr.size()));
   unsigned char* d_rec;
   cu(cudaMalloc(&d_rec, B * 36));
+  // the bulk path picks through the pick table (one HBM line per particle, kdsb200.h) where
+  // the fp32 Philox kernel serves the geometry and the table fits; else the window table
+  const void* d_table = I->d_guide;
+  int table_bits = I->guide_bits, table_kind = 0;
+  void* d_pick = nullptr;
+  if (I->src_f32 && I->contract == 2 && nout >= (uint64_t)I->N) {
+    int bits = 4;
+    while (bits < 30 && (1ll << bits) < 2 * I->N) bits++;
+    size_t free_b = 0, total_b = 0;
+    cu(cudaMemGetInfo(&free_b, &total_b));
+    while (bits > 4 && kdsb200_pick_table_bytes(bits) > free_b / 3) bits--;
+    if (cudaMalloc(&d_pick, kdsb200_pick_table_bytes(bits)) == cudaSuccess) {
+      cuda_or_die(kdsb200_pick_table(I->d_cdf, I->N, bits, (const float*)I->d_src, I->d_bw,
+                                     kds->geom->bw, d_pick, (void*)I->stream));
+      d_table = d_pick;
+      table_bits = bits;
+      table_kind = 1;
+    } else {
+      (void)cudaGetLastError();
+      d_pick = nullptr;
+    }
+  }
   for (uint64_t first = 0; first < nout; first += B) {
     const uint64_t n = nout - first < B ? nout - first : B;
-    cuda_or_die(kdsb200_resample(I->d_src, I->src_f32, I->d_cdf, I->d_guide, I->guide_bits, 0, I->d_bw,
-                                 kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed, first,
-                                 n, -1, nullptr, 0, 1, I->contract, d_rec, nullptr, nullptr,
+    cuda_or_die(kdsb200_resample(I->d_src, I->src_f32, I->d_cdf, d_table, table_bits, table_kind,
+                                 I->d_bw, kds->geom->bw, I->N, &I->geom, kds->plist->pdgcode, seed,
+                                 first, n, -1, nullptr, 0, 1, I->contract, d_rec, nullptr, nullptr,
                                  (void*)I->stream));
     cuda_or_die(kdsb200_gz_writer_put_device(w, d_rec, n * 36));
   }
   cuda_or_die(kdsb200_gz_writer_close(w, nullptr));
   cudaFree(d_rec);
+  cudaFree(d_pick);
   KDS_destroy(kds);
   printf("Successfully sampled %llu particles.\n", (unsigned long long)nout);
 }
