@@ -315,6 +315,21 @@ def pinned(tag, nelem, dtype):
     return buf
 
 
+_side_streams = {}
+
+
+def side_stream():
+    """The copy stream of the current device -- one per device for the life of the process:
+    the caching allocator keeps its blocks per stream, so a fresh stream per call would turn
+    every staging buffer of every call into a new cudaMalloc."""
+    t = torch()
+    dev = t.cuda.current_device()
+    s = _side_streams.get(dev)
+    if s is None:
+        s = _side_streams[dev] = t.cuda.Stream()
+    return s
+
+
 def stream_pieces(src, lo, hi, chunk, work, n_out=1, tag="pieces"):
     """Run `work(d_piece (m,C) float64 CUDA tensor, m)` -> tuple of `n_out` (m,) float64
     device tensors over rows [lo, hi) of the host array `src`, in pieces of `chunk` rows
@@ -334,7 +349,7 @@ def stream_pieces(src, lo, hi, chunk, work, n_out=1, tag="pieces"):
             outs[k][:] = res[k].cpu().numpy()
         extras.extend(res[n_out:])
         return outs, extras
-    main, side = t.cuda.current_stream(), t.cuda.Stream()
+    main, side = t.cuda.current_stream(), side_stream()
     pin_in = [pinned((tag, "in", b), chunk * C, t.float64) for b in range(2)]
     pin_out = [[pinned((tag, "out", b, k), chunk, t.float64) for k in range(n_out)]
                for b in range(2)]

@@ -92,7 +92,7 @@ def knn_batched(data, kk, batch_off, precision="float64", want_dist=False, want_
     elif n_loc > 0:
         # host input: groups of whole batches (~16 MB) go through two pinned staging
         # buffers, so the upload of the next group overlaps the kernel of this one
-        main, side = t.cuda.current_stream(), t.cuda.Stream()
+        main, side = t.cuda.current_stream(), _lib.side_stream()
         groups, g0 = [], b_lo
         while g0 < b_hi:
             g1 = g0 + 1
