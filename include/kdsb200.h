@@ -99,7 +99,7 @@ int kdsb200_hilbert_order(const double* d_data, uint64_t N, int D, const double*
  * coordinates relative to the tile centre d_tilecen[t][D] (multiples of 1/grid, grid a
  * power of two); d_tilebox[t] (kdsb200_sorted_tilebox_floats(D) floats per tile) =
  * {lo[D], hi[D]} of x - h_center over the tile, then {lo[D], hi[D], hmax} of each of its
- * eight runs of 64 sources; d_tilehmax[t] = the tile's largest bandwidth (as passed in
+ * sixteen runs of 32 sources; d_tilehmax[t] = the tile's largest bandwidth (as passed in
  * d_bw / bw_scalar). */
 int kdsb200_sorted_tilebox_floats(int D);
 int kdsb200_pack_sources_sorted_f32(const double* d_data, const double* d_w, const double* d_bw,
@@ -121,10 +121,10 @@ uint64_t kdsb200_sorted_scratch_bytes(uint64_t N, uint64_t Mpad, int nsplit);
  * culled at cutoff_rel times their largest bandwidth; both <= 0 = the exact sum over every
  * tile.  kernel 1/2: culled at the tile's largest support radius.  Culling is exact: a
  * skipped tile holds no pair inside the radius and pairs inside visited tiles are still
- * masked one by one; inside a visited tile every cell of 64 consecutive sources x 256
+ * masked one by one; inside a visited tile every cell of 32 consecutive sources x 256
  * consecutive queries is tested (and skipped) the same way.  d_tiles_visited (device, two
  * uint64, may be NULL) = {tiles loaded, cells computed}, summed over (1024-query block,
- * source split) work items: executed pairs = cells * 64 * 256. */
+ * source split) work items: executed pairs = cells * 32 * 256. */
 int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
                                 const float* d_tilecen, const float* d_tilehmax, uint64_t N,
                                 int D, const float* d_qT, const uint32_t* d_perm_q, uint64_t M,

@@ -9,11 +9,11 @@
 //   * skips every tile whose box is farther than the cutoff from the box of the CTA's
 //     1024 query points (which are ordered the same way) -- exact: a skipped tile holds no
 //     pair inside the radius, and pairs inside visited tiles are still masked one by one;
-//     a tile stays the unit of the bulk copy, but each of its eight runs of 64 sources
+//     a tile stays the unit of the bulk copy, but each of its sixteen runs of 32 sources
 //     carries a box of its own, and so does each quarter of the CTA's queries (the qi-th
 //     query of every thread: 256 consecutive points of the curve); a (run, quarter) cell
 //     is computed only if its two boxes pass the same test -- a CTA-uniform decision, so no
-//     lane diverges (in six dimensions a run of 64 is ~0.7 and a quarter ~0.8 of the
+//     lane diverges (in six dimensions a run of 32 is ~0.63 and a quarter ~0.8 of the
 //     extent per axis);
 //   * forms q - x as (q - c_tile) - (x - c_tile): both terms are small, so the fp32
 //     rounding error scales with the tile size instead of the spread of the whole list
@@ -311,7 +311,7 @@ struct Center8 {
 // tilebox[t] = {lo[D], hi[D]} of (x - c) over the tile (rounded outwards), followed by
 // {lo[D], hi[D], hmax} of each of its SV_NSUB runs of TS / SV_NSUB sources (an empty run
 // has lo = +inf); tilecen[t] = t_k (a multiple of 1/grid, exact in fp32).
-constexpr int SV_NSUB = 8;
+constexpr int SV_NSUB = 16;
 __host__ __device__ constexpr int tilebox_stride(int D) { return 2 * D + SV_NSUB * (2 * D + 1); }
 
 template <int D>
@@ -450,7 +450,7 @@ struct SortedCtl {
   unsigned int next_item;            // dynamic work counter
   unsigned int pad;
   unsigned long long tiles_visited;  // sum over work items of the tiles they loaded
-  unsigned long long cells_visited;  // ... and of the (64-source run x 256-query quarter) cells
+  unsigned long long cells_visited;  // ... and of the (32-source run x 256-query quarter) cells
                                      //     they computed
 };
 
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
   __syncthreads();
   const uint32_t n_qb = (uint32_t)(Mpad / SV_QB);
   const uint32_t n_items = n_qb * (uint32_t)nsplit;
-  uint32_t* my_list = lists + (uint64_t)blockIdx.x * tiles_per_split * 2;  // {tile, cell mask}
+  uint32_t* my_list = lists + (uint64_t)blockIdx.x * tiles_per_split * 4;  // {tile, -, cell mask lo, hi}
   uint32_t itg = 0;  // tiles consumed so far by this CTA (pipeline stage / parity)
 
   for (;;) {
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
       for (uint32_t c0 = t0; c0 < t1; c0 += SV_THREADS) {
         const uint32_t t = c0 + tid;
         bool keep = false;
-        uint32_t mask = 0;  // the tile's runs of 64 sources that lie within the radius
+        uint64_t mask = 0;  // the tile's (run, quarter) cells that lie within the radius
         if (t < t1) {
           const float* bx = tilebox + (uint64_t)t * tilebox_stride(D);
           float d2 = 0.f;
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
                       fmaxf(fmaxf(slo[k] - s_qbox[qi][D + k], s_qbox[qi][k] - shi[k]), 0.f);
                   f2 = fmaf(g, g, f2);
                 }
-                if (f2 <= rs * rs) mask |= 1u << (sub * SV_Q + qi);
+                if (f2 <= rs * rs) mask |= 1ull << (sub * SV_Q + qi);
               }
             }
             keep = mask != 0;
@@ -603,8 +603,9 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
         for (int wv = 0; wv < warp; wv++) off += s_wcnt[wv];
         if (keep) {
           const uint32_t pos = off + __popc(bal & ((1u << lane) - 1u));
-          my_list[2 * pos] = t;
-          my_list[2 * pos + 1] = mask;
+          my_list[4 * pos] = t;
+          my_list[4 * pos + 2] = (uint32_t)mask;
+          my_list[4 * pos + 3] = (uint32_t)(mask >> 32);
         }
         __syncthreads();
         if (tid == 0) {
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
       }
       nlist = s_nlist;
     }
-    auto tile_id = [&](uint32_t l) -> uint32_t { return CULL ? my_list[2 * l] : t0 + l; };
+    auto tile_id = [&](uint32_t l) -> uint32_t { return CULL ? my_list[4 * l] : t0 + l; };
     uint32_t ncells = 0;
 
     if (tid == 0) {
@@ -652,8 +653,9 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
           q[qi][k] = (__ldg(qT + (uint64_t)k * Mpad + mbase + qi * SV_THREADS) - ck) +
                      __ldg(qT + (uint64_t)(D + k) * Mpad + mbase + qi * SV_THREADS);
       }
-      const uint32_t cmask = CULL ? my_list[2 * it + 1] : 0xffffffffu;
-      ncells += __popc(cmask);
+      const uint64_t cmask =
+          CULL ? ((uint64_t)my_list[4 * it + 2] | ((uint64_t)my_list[4 * it + 3] << 32)) : ~0ull;
+      ncells += __popcll(cmask);
       mbar_wait(&full[s], parity);
       const float* tile = tiles + s * TILE_FLOATS;
 
@@ -663,7 +665,7 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
 
 #pragma unroll 1
       for (int sub = 0; sub < SV_NSUB; sub++) {
-      const uint32_t m4 = (cmask >> (sub * SV_Q)) & ((1u << SV_Q) - 1u);
+      const uint32_t m4 = (uint32_t)(cmask >> (sub * SV_Q)) & ((1u << SV_Q) - 1u);
       if (CULL && !m4) continue;
 #pragma unroll 2
       for (int j = sub * (TS / SV_NSUB); j < (sub + 1) * (TS / SV_NSUB); j += 4) {
@@ -948,7 +950,7 @@ uint64_t kdsb200_sorted_scratch_bytes(uint64_t N, uint64_t Mpad, int nsplit) {
   const uint64_t ntl = n_tiles_for(N);
   if (nsplit < 1) nsplit = 1;
   const uint64_t tps = (ntl + nsplit - 1) / nsplit;
-  return 64 + (uint64_t)kdsb200_sorted_ctas() * tps * 8 + (uint64_t)nsplit * Mpad * 8 + 64;
+  return 64 + (uint64_t)kdsb200_sorted_ctas() * tps * 16 + (uint64_t)nsplit * Mpad * 8 + 64;
 }
 
 int kdsb200_sorted_nsplit(uint64_t N, uint64_t M) {
@@ -994,7 +996,7 @@ int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
   unsigned char* p = (unsigned char*)d_scratch;
   SortedCtl* ctl = (SortedCtl*)p;
   uint32_t* lists = (uint32_t*)(p + 64);
-  uint64_t off = 64 + (uint64_t)ctas * tps * 8;
+  uint64_t off = 64 + (uint64_t)ctas * tps * 16;
   off = (off + 63) / 64 * 64;
   double* partial = (double*)(p + off);
   KDSB_CUDA(cudaMemsetAsync(ctl, 0, sizeof(SortedCtl), st));
@@ -1046,7 +1048,7 @@ int kdsb200_kde_eval_sorted_f32(const float* d_packed, const float* d_tilebox,
   reduce_scatter_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(partial, nsplit, M, Mpad,
                                                                      d_perm_q, d_out);
   KDSB_CUDA(cudaGetLastError());
-  if (d_tiles_visited)  // {tiles loaded, (64-source run x 256-query quarter) cells computed}
+  if (d_tiles_visited)  // {tiles loaded, (32-source run x 256-query quarter) cells computed}
     KDSB_CUDA(cudaMemcpyAsync(d_tiles_visited, &ctl->tiles_visited, 2 * sizeof(uint64_t),
                               cudaMemcpyDeviceToDevice, st));
   return 0;

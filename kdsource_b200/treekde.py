@@ -442,9 +442,9 @@ class TreeKDE:
                 _lib.ptr(scratch), _lib.ptr(d_out), _lib.ptr(visited), st))
             #: device counters of the last call, summed over the (1024-query block, source
             #: split) work items: tiles loaded, and 512 x 1024 tile equivalents computed (cells
-            #: of 64 sources x 256 queries / 32); executed pairs = last_tiles_visited * 512 * 1024
+            #: of 32 sources x 256 queries / 64); executed pairs = last_tiles_visited * 512 * 1024
             self.last_tiles_loaded = visited[0]
-            self.last_tiles_visited = visited[1].to(t.float64) / 32.0
+            self.last_tiles_visited = visited[1].to(t.float64) / 64.0
             self.last_work_items_pairs = 512 * 1024
         elif dev["dtype"] == "float32_dense":
             Mpad = L.kdsb200_eval_mpad(M)
