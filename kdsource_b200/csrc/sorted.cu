@@ -663,12 +663,13 @@ __global__ void __launch_bounds__(SV_THREADS, 2)
 #pragma unroll
       for (int qi = 0; qi < SV_Q; qi++) acc[qi] = 0ull;
 
+      constexpr int NRUN = CULL ? SV_NSUB : 1;  // the exact sum walks the tile in one loop
 #pragma unroll 1
-      for (int sub = 0; sub < SV_NSUB; sub++) {
+      for (int sub = 0; sub < NRUN; sub++) {
       const uint32_t m4 = (uint32_t)(cmask >> (sub * SV_Q)) & ((1u << SV_Q) - 1u);
       if (CULL && !m4) continue;
 #pragma unroll 2
-      for (int j = sub * (TS / SV_NSUB); j < (sub + 1) * (TS / SV_NSUB); j += 4) {
+      for (int j = sub * (TS / NRUN); j < (sub + 1) * (TS / NRUN); j += 4) {
         float4 r[ROWS];
 #pragma unroll
         for (int k = 0; k < ROWS; k++) r[k] = *reinterpret_cast<const float4*>(tile + k * TS + j);
