@@ -237,6 +237,7 @@ class _IndexedGzReader:
         self._mm = mm
         self._offs, self._sizes, self._raws = index
         self._next = 0          # next member to inflate
+        self._cum = None        # cumulative raw sizes (built on the first skip)
         self._buf = b""         # inflated, not yet consumed
         self._bpos = 0
         self._pool = ThreadPoolExecutor(max_workers=_inflate_workers())
@@ -276,11 +277,38 @@ class _IndexedGzReader:
         self._bpos += len(out)
         return out
 
+    def skip(self, n):
+        """Advance by n inflated bytes; members that lie wholly inside the skipped range are
+        never inflated (a rank of a sharded read hops straight to its share)."""
+        n = int(n)
+        take = min(len(self._buf) - self._bpos, n)
+        self._bpos += take
+        n -= take
+        if n <= 0:
+            return
+        self._buf, self._bpos = b"", 0  # drained: the stream now stands at member _next
+        if self._cum is None:
+            self._cum = np.cumsum(self._raws)
+        start = int(self._cum[self._next - 1]) if self._next else 0
+        k = int(np.searchsorted(self._cum, start + n, side="right"))  # members < k end inside
+        if k > self._next:
+            n -= int(self._cum[k - 1]) - start
+            self._next = k
+        if n > 0:
+            self.read(n)
+
     def readinto(self, b):
+        # window by window: a multi-gigabyte read never holds more than one window of
+        # inflated bytes besides the destination
         view = memoryview(b).cast("B")
-        data = self.read(len(view))
-        view[:len(data)] = data
-        return len(data)
+        done = 0
+        while done < len(view):
+            data = self.read(min(len(view) - done, self.WINDOW_BYTES))
+            if not data:
+                break
+            view[done:done + len(data)] = data
+            done += len(data)
+        return done
 
     def close(self):
         self._pool.shutdown(wait=False)
@@ -417,7 +445,10 @@ class MCPLFile:
     def skip_forward(self, n):
         n = int(min(max(n, 0), self.nparticles - self._pos))
         if n:
-            self._fh.read(n * self._dtype.itemsize)
+            if hasattr(self._fh, "skip"):  # indexed gzip: whole members are hopped over
+                self._fh.skip(n * self._dtype.itemsize)
+            else:
+                self._fh.read(n * self._dtype.itemsize)
             self._pos += n
 
     def read_raw(self, n):

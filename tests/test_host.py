@@ -121,7 +121,7 @@ def test_mcpl_write_read_roundtrip(tmp_path, double_prec, gz):
         assert len(f.read_block()) == 5
 
 
-def test_indexed_gzip_members_parallel_reader(tmp_path):
+def test_indexed_gzip_members_parallel_reader(tmp_path, monkeypatch):
     """The .gz files this package writes are sequences of gzip members that carry their own
     size ("KD" FEXTRA subfield): any gzip reader inflates them as one stream, MCPLFile hops
     from header to header and inflates the members in parallel -- same bytes; a file without
@@ -156,6 +156,23 @@ def test_indexed_gzip_members_parallel_reader(tmp_path):
         f.rewind()
         f.skip_forward(n - 3)
         assert len(f.read_block()) == 3
+    # skipping hops over whole members without inflating them
+    monkeypatch.setattr(mcpl._IndexedGzReader, "WINDOW_BYTES", 1 << 20)
+    inflated = []
+    real_inflate = mcpl._IndexedGzReader._inflate
+    monkeypatch.setattr(mcpl._IndexedGzReader, "_inflate",
+                        lambda self, k: inflated.append(k) or real_inflate(self, k))
+    for skip in (0, 1, 29_127, 29_128, 100_000, n - 6):
+        with mcpl.MCPLFile(fn) as f:
+            f.read_raw_bytes(5)
+            del inflated[:]
+            f.skip_forward(skip)
+            got, c = f.read_raw_bytes(7)
+            lo = (5 + skip) * 32
+            assert c == min(7, n - 5 - skip) and bytes(got) == bytes(buf[lo:lo + c * 32]), skip
+            if skip == 100_000:  # 3.2 MB further on: two whole members were never inflated
+                assert len(inflated) <= 2 and min(inflated) >= 4, inflated
+    monkeypatch.undo()
     # small reads crossing member boundaries
     rd = mcpl._open_maybe_gz(fn)
     got = b"".join(iter(lambda: rd.read(777_777), b""))
