@@ -152,11 +152,16 @@ class DeviceSampler:
                     bits -= 1
                 if pick_bits is not None:
                     bits = int(pick_bits)
-                self.pick_bits = bits
-                self.pick = _lib.empty(int(L.kdsb200_pick_table_bytes(bits)), t.uint8)
-                _lib.check(L.kdsb200_pick_table(_lib.ptr(self.cdf), self.N, bits, _lib.ptr(self.src),
-                                                _lib.ptr(self.bw), self.bw_scalar,
-                                                _lib.ptr(self.pick), _lib.stream()))
+                try:
+                    self.pick = _lib.empty(int(L.kdsb200_pick_table_bytes(bits)), t.uint8)
+                except t.cuda.OutOfMemoryError:  # the window table serves every kernel
+                    self.pick = None
+                if self.pick is not None:
+                    self.pick_bits = bits
+                    _lib.check(L.kdsb200_pick_table(_lib.ptr(self.cdf), self.N, bits,
+                                                    _lib.ptr(self.src), _lib.ptr(self.bw),
+                                                    self.bw_scalar, _lib.ptr(self.pick),
+                                                    _lib.stream()))
         t.cuda.current_stream().synchronize()
 
     def sample_device(self, count, seed=0, first=0, ext_uniforms=None, perturb=True,
