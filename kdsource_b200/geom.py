@@ -155,7 +155,17 @@ class Geometry(Metric):
 
     def transform(self, parts):
         self._to_local(parts)
-        return np.concatenate([m.transform(parts[:, m.partvars]) for m in self.ms], axis=1)
+        # written block by block into a C-ordered array: np.concatenate would inherit the
+        # column-major layout of the fancy-indexed inputs, and every consumer (scaling,
+        # uploads, the KDE kernels' staging) would then pay a strided copy
+        blocks = [m.transform(parts[:, m.partvars]) for m in self.ms]
+        out = np.empty((len(parts), sum(b.shape[1] for b in blocks)),
+                       dtype=np.result_type(*blocks) if blocks else np.float64)
+        col = 0
+        for b in blocks:
+            out[:, col:col + b.shape[1]] = b
+            col += b.shape[1]
+        return out
 
     def inverse_transform(self, vecs):
         parts = np.zeros((len(vecs), 8))
