@@ -282,6 +282,7 @@ def test_guide_and_geometry_vs_reference(golden_geom):
     assert geo.dim == 6 and geo.varnames == ["u", "x", "y", "dx", "dy", "dz"]
     assert geo.volunits == "MeV cm^2 [dir]^3"
     vecs = geo.transform(g["parts"].copy())
+    assert vecs.flags.c_contiguous  # consumers upload / stage it without a strided copy
     assert np.array_equal(vecs, g["Geometry_transform"])
     assert np.array_equal(geo.std(vecs=vecs, weights=g["w"]), g["Geometry_std"])
     assert np.array_equal(geo.inverse_transform(vecs.copy()), g["Geometry_inverse"])
